@@ -1,0 +1,225 @@
+"""fdes_b200 -- B200-native forward multislice behind the FDES interface.
+
+Host-side Python mirror of the reference's Python entry point (Python/pyFDES.py:33-41,
+``cuda_FDES``) plus a thin ctypes binding of the session API in ``include/fdes_b200.h``.
+All compute happens in ``fdes_b200/lib/libfdes_b200.so`` (hand-written sm_100a kernels);
+there is no CPU or PyTorch fallback -- importing works anywhere, computing needs a B200
+and the built library, and fails loudly otherwise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import pathlib
+from typing import Optional
+
+import numpy as np
+
+_PKG = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _PKG / "lib" / "libfdes_b200.so"
+_lib = None
+
+
+class FdesError(RuntimeError):
+    pass
+
+
+def load_library() -> ctypes.CDLL:
+    """Load libfdes_b200.so (built in-tree by ``__graft_entry__.build()`` / ``make``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise FdesError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no fallback implementation)")
+    lib = ctypes.CDLL(str(LIB_PATH), mode=ctypes.RTLD_GLOBAL)
+    c_f = ctypes.POINTER(ctypes.c_float)
+    c_i = ctypes.POINTER(ctypes.c_int)
+    vp = ctypes.c_void_p
+    lib.fdes_b200_last_error.restype = ctypes.c_char_p
+    lib.fdes_b200_version.restype = ctypes.c_int
+    lib.fdes_b200_open_cnf.restype = vp
+    lib.fdes_b200_open_cnf.argtypes = [ctypes.c_char_p, c_f, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.fdes_b200_close.argtypes = [vp]
+    lib.fdes_b200_close.restype = None
+    lib.fdes_b200_get_dims.argtypes = [vp, c_i]
+    lib.fdes_b200_get_scalars.argtypes = [vp, c_f]
+    lib.fdes_b200_set_accumulators.argtypes = [vp, vp, vp]
+    lib.fdes_b200_run_k.argtypes = [vp, ctypes.c_int]
+    lib.fdes_b200_finish_k.argtypes = [vp, ctypes.c_int, c_f, c_f]
+    lib.fdes_b200_simulate.argtypes = [vp, c_f, c_f]
+    lib.fdes_b200_potential_slices_count.argtypes = [vp]
+    lib.fdes_b200_potential.argtypes = [vp, c_f]
+    lib.fdes_b200_jitter_next.argtypes = [vp, ctypes.c_int, c_f]
+    lib.fdes_b200_bin_atoms.argtypes = [vp, c_f, c_i]
+    lib.fdes_b200_phase_grating.argtypes = [vp, c_f, ctypes.c_int, c_f]
+    lib.fdes_b200_exit_wave.argtypes = [vp, c_f, ctypes.c_int, c_f]
+    lib.fdes_b200_bench_configs.argtypes = [vp, ctypes.c_int, ctypes.c_int]
+    lib.fdes_b200_bench_configs.restype = ctypes.c_double
+    lib.fdes_b200_get_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
+    lib.fdes_b200_fft2d.argtypes = [c_f, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.fdes_b200_sort_records.argtypes = [ctypes.POINTER(ctypes.c_uint), c_i, c_f, ctypes.c_int, ctypes.c_int,
+                                           c_i, ctypes.c_int]
+    lib.FDES.restype = None
+    lib.FDES.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, c_f,
+                         ctypes.c_int, c_f]
+    _lib = lib
+    return lib
+
+
+def _fp(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+def _ip(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+
+
+def cuda_FDES(gpu_Index, print_Level, input_name, image_name, emd_save_name, pointerAtomsArray, numAtoms,
+              pointerImagesArray):
+    """Same call as ``cuda_FDES`` in the reference's Python/pyFDES.py:33-41; the two array
+    arguments may be ctypes float pointers (as there) or float32 numpy arrays."""
+    lib = load_library()
+    if isinstance(pointerAtomsArray, np.ndarray):
+        pointerAtomsArray = _fp(np.ascontiguousarray(pointerAtomsArray, np.float32))
+    if isinstance(pointerImagesArray, np.ndarray):
+        assert pointerImagesArray.dtype == np.float32 and pointerImagesArray.flags.c_contiguous
+        pointerImagesArray = _fp(pointerImagesArray)
+    enc = lambda s: s if isinstance(s, bytes) else str(s).encode()
+    return lib.FDES(int(gpu_Index), int(print_Level), enc(input_name), enc(image_name), enc(emd_save_name),
+                    pointerAtomsArray, int(numAtoms), pointerImagesArray)
+
+
+class Simulation:
+    """One .cnf simulation on one GPU (session API of include/fdes_b200.h)."""
+
+    def __init__(self, cnf_path, atoms6: Optional[np.ndarray] = None, gpu_index: int = 0, batch: int = 0,
+                 rank: int = 0, world: int = 1, want_exitwave: bool = False):
+        self._lib = load_library()
+        self._h = None
+        a_ptr, n_at = None, 0
+        if atoms6 is not None:
+            self._atoms6 = np.ascontiguousarray(atoms6, np.float32).reshape(-1, 6)
+            a_ptr, n_at = _fp(self._atoms6), self._atoms6.shape[0]
+        h = self._lib.fdes_b200_open_cnf(str(cnf_path).encode(), a_ptr, n_at, gpu_index, batch, rank, world,
+                                         1 if want_exitwave else 0)
+        if not h:
+            raise FdesError(self._lib.fdes_b200_last_error().decode())
+        self._h = h
+        d = np.zeros(10, np.int32)
+        self._ck(self._lib.fdes_b200_get_dims(h, _ip(d)))
+        (self.n1, self.n2, self.n3, self.m1, self.m2, self.m3, self.nAt, self.nZ, self.configs, _) = map(int, d)
+        s = np.zeros(8, np.float32)
+        self._ck(self._lib.fdes_b200_get_scalars(h, _fp(s)))
+        self.lam, self.sigma, self.gamma, self.d1, self.d2, self.d3, self.E0, self.imPot = map(float, s)
+        self.want_exitwave = want_exitwave
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise FdesError(self._lib.fdes_b200_last_error().decode())
+
+    def close(self):
+        if self._h:
+            self._lib.fdes_b200_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- reference-facing -------------------------------------------------------------------
+    def simulate(self):
+        """All measurements on this GPU: (image [n3,n2,n1] float32, exitwave [n3,m2,m1] complex64|None)."""
+        img = np.zeros((self.n3, self.n2, self.n1), np.float32)
+        ew = np.zeros((self.n3, self.m2, self.m1), np.complex64) if self.want_exitwave else None
+        self._ck(self._lib.fdes_b200_simulate(self._h, _fp(img), _fp(ew.view(np.float32)) if ew is not None else None))
+        return img, ew
+
+    def set_accumulators(self, intensity_dev_ptr: int, exitwave_dev_ptr: int = 0):
+        """Install device accumulators (raw pointers, e.g. torch tensor .data_ptr())."""
+        self._ck(self._lib.fdes_b200_set_accumulators(self._h, ctypes.c_void_p(intensity_dev_ptr or None),
+                                                      ctypes.c_void_p(exitwave_dev_ptr or None)))
+
+    def run_k(self, k: int):
+        self._ck(self._lib.fdes_b200_run_k(self._h, k))
+
+    def finish_k(self, k: int):
+        img = np.zeros((self.n2, self.n1), np.float32)
+        ew = np.zeros((self.m2, self.m1), np.complex64) if self.want_exitwave else None
+        self._ck(self._lib.fdes_b200_finish_k(self._h, k, _fp(img),
+                                              _fp(ew.view(np.float32)) if ew is not None else None))
+        return img, ew
+
+    def potential(self):
+        n = self._lib.fdes_b200_potential_slices_count(self._h)
+        out = np.zeros((n, self.m2, self.m1), np.complex64)
+        self._ck(self._lib.fdes_b200_potential(self._h, _fp(out.view(np.float32))))
+        return out
+
+    # ---- building blocks ----------------------------------------------------------------------
+    def jitter_next(self, k: int = 0):
+        xyz = np.zeros((self.nAt, 3), np.float32)
+        self._ck(self._lib.fdes_b200_jitter_next(self._h, k, _fp(xyz)))
+        return xyz
+
+    def bin_atoms(self, xyz: np.ndarray):
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        bins = np.zeros((self.nAt, 4), np.int32)
+        self._ck(self._lib.fdes_b200_bin_atoms(self._h, _fp(xyz), _ip(bins)))
+        return bins
+
+    def phase_grating(self, xyz: np.ndarray, s: int):
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        V = np.zeros((self.m2, self.m1), np.complex64)
+        self._ck(self._lib.fdes_b200_phase_grating(self._h, _fp(xyz), s, _fp(V.view(np.float32))))
+        return V
+
+    def exit_wave(self, xyz: np.ndarray, k: int = 0):
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        psi = np.zeros((self.m2, self.m1), np.complex64)
+        self._ck(self._lib.fdes_b200_exit_wave(self._h, _fp(xyz), k, _fp(psi.view(np.float32))))
+        return psi
+
+    def bench_configs(self, k: int, configs: int) -> float:
+        ms = self._lib.fdes_b200_bench_configs(self._h, k, configs)
+        if ms < 0:
+            raise FdesError(self._lib.fdes_b200_last_error().decode())
+        return float(ms)
+
+    def counters(self, reset: bool = False):
+        c = (ctypes.c_longlong * 4)()
+        self._ck(self._lib.fdes_b200_get_counters(self._h, c, 1 if reset else 0))
+        return {"slices": int(c[0]), "launches": int(c[1])}
+
+
+def fft2d(a: np.ndarray, direction: int = -1, gpu_index: int = 0) -> np.ndarray:
+    """2-D complex64 FFT with the library's sweeps (unnormalised; -1 forward, +1 inverse)."""
+    lib = load_library()
+    out = np.ascontiguousarray(a, np.complex64).copy()
+    n = out.shape[0]
+    assert out.shape == (n, n)
+    if lib.fdes_b200_fft2d(_fp(out.view(np.float32)), n, direction, gpu_index) != 0:
+        raise FdesError(lib.fdes_b200_last_error().decode())
+    return out
+
+
+def sort_records(keys: np.ndarray, cols: np.ndarray, w: np.ndarray, nkeys: int, gpu_index: int = 0):
+    lib = load_library()
+    k = np.ascontiguousarray(keys, np.uint32).copy()
+    c = np.ascontiguousarray(cols, np.int32).copy()
+    ww = np.ascontiguousarray(w, np.float32).copy()
+    rp = np.zeros(nkeys + 1, np.int32)
+    rc = lib.fdes_b200_sort_records(k.ctypes.data_as(ctypes.POINTER(ctypes.c_uint)), _ip(c), _fp(ww), len(k), nkeys,
+                                    _ip(rp), gpu_index)
+    if rc != 0:
+        raise FdesError(lib.fdes_b200_last_error().decode())
+    return k, c, ww, rp

@@ -1,0 +1,306 @@
+// fdes_b200 -- C ABI (include/fdes_b200.h): the drop-in FDES() symbol of the reference
+// (src/FDESExport.cu:59-178) and the session API over the engine.
+#include "../../include/fdes_b200.h"
+#include "engine.h"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <memory>
+#include <stdexcept>
+#include <vector>
+#include <algorithm>
+#include <string>
+
+using namespace fdes;
+
+struct fdes_b200_sim {
+    std::unique_ptr<Engine> eng;
+    Params params;   // as read (before sub-slicing)
+    Atoms atoms;
+    int m3_orig = 1;
+};
+
+static thread_local std::string g_err;
+
+#define API_TRY try {
+#define API_CATCH(ret)                                                                           \
+    }                                                                                            \
+    catch (const std::exception& e) { g_err = e.what(); return ret; }                            \
+    catch (...) { g_err = "unknown error"; return ret; }
+
+extern "C" {
+
+const char* fdes_b200_last_error(void) { return g_err.c_str(); }
+int fdes_b200_version(void) { return 100; }
+
+fdes_b200_sim* fdes_b200_open_cnf(const char* cnf_path, const float* atoms6, int numAtoms,
+                                  int gpu_index, int batch, int rank, int world, int want_exitwave)
+{
+    API_TRY
+    auto sim = std::make_unique<fdes_b200_sim>();
+    if (!cnf_path) throw std::runtime_error("cnf_path is NULL");
+    if (!read_cnf(cnf_path, sim->params, &sim->atoms, atoms6 != nullptr))
+        throw std::runtime_error(std::string("cannot read ") + cnf_path);
+    if (atoms6) {
+        if (numAtoms <= 0) throw std::runtime_error("numAtoms must be positive");
+        atoms_from_array(atoms6, numAtoms, sim->atoms);
+    }
+    sim->params.nAt = sim->atoms.size();
+    sim->m3_orig = sim->params.m3;
+    EngineOptions opt;
+    opt.gpu_index = gpu_index; opt.batch = batch; opt.rank = rank; opt.world = world;
+    opt.want_exitwave = want_exitwave != 0;
+    sim->eng = std::make_unique<Engine>(sim->params, sim->atoms, opt);
+    return sim.release();
+    API_CATCH(nullptr)
+}
+
+void fdes_b200_close(fdes_b200_sim* sim) { delete sim; }
+
+int fdes_b200_get_dims(const fdes_b200_sim* sim, int* d)
+{
+    API_TRY
+    const Params& p = sim->eng->params();
+    d[0] = p.n1; d[1] = p.n2; d[2] = p.n3; d[3] = p.m1; d[4] = p.m2; d[5] = p.m3;
+    d[6] = sim->atoms.size(); d[7] = sim->eng->num_species(); d[8] = sim->eng->configs_total();
+    d[9] = 0;
+    return 0;
+    API_CATCH(-1)
+}
+
+int fdes_b200_get_scalars(const fdes_b200_sim* sim, float* s)
+{
+    API_TRY
+    const Params& p = sim->eng->params();
+    s[0] = p.lambda; s[1] = p.sigma; s[2] = p.gamma; s[3] = p.d1; s[4] = p.d2; s[5] = p.d3;
+    s[6] = p.E0; s[7] = p.imPot;
+    return 0;
+    API_CATCH(-1)
+}
+
+int fdes_b200_set_accumulators(fdes_b200_sim* sim, float* intensity_dev, float* exitwave_dev)
+{
+    API_TRY
+    sim->eng->set_accumulators(intensity_dev, reinterpret_cast<cpx*>(exitwave_dev));
+    return 0;
+    API_CATCH(-1)
+}
+
+int fdes_b200_run_k(fdes_b200_sim* sim, int k)
+{
+    API_TRY
+    sim->eng->run_k(k);
+    return 0;
+    API_CATCH(-1)
+}
+
+int fdes_b200_finish_k(fdes_b200_sim* sim, int k, float* image_host, float* exitwave_host)
+{
+    API_TRY
+    sim->eng->finish_k(k, image_host, exitwave_host);
+    return 0;
+    API_CATCH(-1)
+}
+
+int fdes_b200_simulate(fdes_b200_sim* sim, float* image_host, float* exitwave_host)
+{
+    API_TRY
+    const Params& p = sim->eng->params();
+    const size_t n12 = (size_t)p.n1 * p.n2, m12 = (size_t)p.m1 * p.m2;
+    for (int k = 0; k < p.n3; k++) {
+        sim->eng->run_k(k);
+        sim->eng->finish_k(k, image_host ? image_host + k * n12 : nullptr,
+                           exitwave_host ? exitwave_host + 2 * k * m12 : nullptr);
+    }
+    return 0;
+    API_CATCH(-1)
+}
+
+int fdes_b200_potential_slices_count(const fdes_b200_sim* sim) { return sim ? sim->m3_orig : -1; }
+
+int fdes_b200_potential(fdes_b200_sim* sim, float* out_host)
+{
+    API_TRY
+    sim->eng->potential_slices(out_host);
+    return 0;
+    API_CATCH(-1)
+}
+
+int fdes_b200_jitter_next(fdes_b200_sim* sim, int k, float* xyz_host)
+{
+    API_TRY
+    sim->eng->next_jittered_coords(k, xyz_host);
+    return 0;
+    API_CATCH(-1)
+}
+
+int fdes_b200_bin_atoms(fdes_b200_sim* sim, const float* xyz_host, int* bins_host)
+{
+    API_TRY
+    sim->eng->bin_tuples(xyz_host, bins_host);
+    return 0;
+    API_CATCH(-1)
+}
+
+int fdes_b200_phase_grating(fdes_b200_sim* sim, const float* xyz_host, int slice, float* V_host)
+{
+    API_TRY
+    if (slice < 0 || slice >= sim->eng->params().m3) throw std::runtime_error("slice out of range");
+    sim->eng->phase_grating(xyz_host, slice, V_host);
+    return 0;
+    API_CATCH(-1)
+}
+
+int fdes_b200_exit_wave(fdes_b200_sim* sim, const float* xyz_host, int k, float* psi_host)
+{
+    API_TRY
+    sim->eng->exit_wave(xyz_host, k, psi_host);
+    return 0;
+    API_CATCH(-1)
+}
+
+double fdes_b200_bench_configs(fdes_b200_sim* sim, int k, int configs)
+{
+    API_TRY
+    return sim->eng->bench_configs(k, configs);
+    API_CATCH(-1.0)
+}
+
+int fdes_b200_get_counters(fdes_b200_sim* sim, long long* c, int reset)
+{
+    API_TRY
+    const EngineTimings& t = sim->eng->timings();
+    c[0] = t.slices_executed; c[1] = t.kernel_launches; c[2] = 0; c[3] = 0;
+    if (reset) sim->eng->reset_timings();
+    return 0;
+    API_CATCH(-1)
+}
+
+static void ck(cudaError_t e, const char* what)
+{
+    if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+int fdes_b200_fft2d(float* data_host, int N, int dir, int gpu_index)
+{
+    API_TRY
+    if (!fft_size_supported(N)) throw std::runtime_error("unsupported FFT size");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw std::runtime_error("no CUDA device");
+    ck(cudaSetDevice(gpu_index), "cudaSetDevice");
+    const size_t NN = (size_t)N * N;
+    cpx *d = nullptr, *tw = nullptr;
+    ck(cudaMalloc(&d, NN * sizeof(cpx)), "cudaMalloc");
+    ck(cudaMalloc(&tw, N * sizeof(cpx)), "cudaMalloc");
+    std::vector<cpx> h(N);
+    for (int n = 0; n < N; n++) {
+        const double a = -2.0 * M_PI * (double)n / (double)N;
+        h[n] = make_float2((float)cos(a), (float)sin(a));
+    }
+    ck(cudaMemcpy(tw, h.data(), N * sizeof(cpx), cudaMemcpyHostToDevice), "cudaMemcpy");
+    ck(cudaMemcpy(d, data_host, NN * sizeof(cpx), cudaMemcpyHostToDevice), "cudaMemcpy");
+    SweepGeom g{N, N, N, tw};
+    RowOpts ro;
+    launch_rows_fft(g, d, d, dir, ROW_STORE, ro, 1, 0);
+    launch_cols_fft(g, d, d, dir, COL_PLAIN, nullptr, 1.f, 1, 0);
+    ck(cudaDeviceSynchronize(), "fft2d kernels");
+    ck(cudaMemcpy(data_host, d, NN * sizeof(cpx), cudaMemcpyDeviceToHost), "cudaMemcpy");
+    cudaFree(d); cudaFree(tw);
+    return 0;
+    API_CATCH(-1)
+}
+
+int fdes_b200_sort_records(unsigned int* keys, int* cols, float* w, int n, int nkeys, int* rowptr,
+                           int gpu_index)
+{
+    API_TRY
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw std::runtime_error("no CUDA device");
+    ck(cudaSetDevice(gpu_index), "cudaSetDevice");
+    SortBuffers sb{};
+    int* rp = nullptr;
+    const size_t nn = (size_t)std::max(n, 1);
+    ck(cudaMalloc(&sb.keys, nn * 4), "cudaMalloc"); ck(cudaMalloc(&sb.keys_tmp, nn * 4), "cudaMalloc");
+    ck(cudaMalloc(&sb.cols, nn * 4), "cudaMalloc"); ck(cudaMalloc(&sb.cols_tmp, nn * 4), "cudaMalloc");
+    ck(cudaMalloc(&sb.w, nn * 4), "cudaMalloc"); ck(cudaMalloc(&sb.w_tmp, nn * 4), "cudaMalloc");
+    ck(cudaMalloc(&sb.hist, 256 * (size_t)sort_num_blocks(n) * 4), "cudaMalloc");
+    ck(cudaMalloc(&rp, ((size_t)nkeys + 1) * 4), "cudaMalloc");
+    ck(cudaMemcpy(sb.keys, keys, (size_t)n * 4, cudaMemcpyHostToDevice), "cudaMemcpy");
+    ck(cudaMemcpy(sb.cols, cols, (size_t)n * 4, cudaMemcpyHostToDevice), "cudaMemcpy");
+    ck(cudaMemcpy(sb.w, w, (size_t)n * 4, cudaMemcpyHostToDevice), "cudaMemcpy");
+    int bits = 0;
+    while ((1LL << bits) <= (long long)nkeys) bits++;
+    launch_radix_sort(sb, n, bits, 0);
+    launch_row_pointers(sb.keys, n, rp, nkeys, 0);
+    ck(cudaDeviceSynchronize(), "sort kernels");
+    ck(cudaMemcpy(keys, sb.keys, (size_t)n * 4, cudaMemcpyDeviceToHost), "cudaMemcpy");
+    ck(cudaMemcpy(cols, sb.cols, (size_t)n * 4, cudaMemcpyDeviceToHost), "cudaMemcpy");
+    ck(cudaMemcpy(w, sb.w, (size_t)n * 4, cudaMemcpyDeviceToHost), "cudaMemcpy");
+    ck(cudaMemcpy(rowptr, rp, ((size_t)nkeys + 1) * 4, cudaMemcpyDeviceToHost), "cudaMemcpy");
+    cudaFree(sb.keys); cudaFree(sb.keys_tmp); cudaFree(sb.cols); cudaFree(sb.cols_tmp);
+    cudaFree(sb.w); cudaFree(sb.w_tmp); cudaFree(sb.hist); cudaFree(rp);
+    return 0;
+    API_CATCH(-1)
+}
+
+// ---------------------------------------------------------------------------------------------
+// drop-in export (reference src/FDESExport.cu:59-178)
+// ---------------------------------------------------------------------------------------------
+void FDES(int gpu_Index, int print_Level, char* input_name, char* image_name, char* emd_save_name,
+          float* atomsArray, int numAtoms, float* dstImage)
+{
+    fprintf(stderr, "\n  fdes_b200: B200-native forward multislice behind the FDES interface\n\n");
+    fprintf(stderr, "   input_name %s  \n", input_name ? input_name : "(null)");
+    if (!input_name || !(strstr(input_name, ".emd") || strstr(input_name, ".cnf") || strstr(input_name, ".qsc"))) {
+        fprintf(stderr, " \n input file %s error   \n", input_name ? input_name : "(null)");
+        exit(0);   // reference: src/FDESExport.cu:100-101
+    }
+    if (!strstr(input_name, ".cnf")) {
+        fprintf(stderr, " \n fdes_b200: only .cnf parameter files are supported by this build "
+                        "(.emd needs libhdf5, .qsc the QSTEM reader) \n");
+        exit(EXIT_FAILURE);
+    }
+    if (numAtoms <= 0) exit(0);   // readAtomsFromArray, src/paramStructure.cu:306-307
+    if (print_Level < 0 || print_Level > 2) {
+        fprintf(stderr, " \n printLevel error %s  \n", input_name);
+        exit(EXIT_FAILURE);
+    }
+    fdes_b200_sim* sim = fdes_b200_open_cnf(input_name, atomsArray, numAtoms, gpu_Index, 0, 0, 1,
+                                            print_Level > 1);
+    if (!sim) {
+        fprintf(stderr, " \n fdes_b200: %s \n", fdes_b200_last_error());
+        exit(EXIT_FAILURE);
+    }
+    // side-effect file of getParams (src/paramStructure.cu:629-631)
+    write_cnf("dataFDES_used.cnf", sim->eng->params(), sim->atoms, gpu_Index);
+    fprintf(stderr, "  Number of atoms %d \n", sim->atoms.size());
+    const Params& p = sim->eng->params();
+    const size_t n123 = (size_t)p.n1 * p.n2 * p.n3, m12 = (size_t)p.m1 * p.m2;
+    std::vector<float> image(n123), ew, pot;
+    if (print_Level > 1) ew.resize(2 * m12 * p.n3);
+    if (fdes_b200_simulate(sim, image.data(), ew.empty() ? nullptr : ew.data()) != 0) {
+        fprintf(stderr, " \n fdes_b200: %s \n", fdes_b200_last_error());
+        exit(EXIT_FAILURE);
+    }
+    if (print_Level > 0) {
+        pot.resize(2 * m12 * (size_t)sim->m3_orig);
+        if (fdes_b200_potential(sim, pot.data()) != 0) {
+            fprintf(stderr, " \n fdes_b200: %s \n", fdes_b200_last_error());
+            exit(EXIT_FAILURE);
+        }
+    }
+    if (image_name && image_name[0]) write_binary(image_name, image.data(), n123);
+    if (emd_save_name && emd_save_name[0]) {
+        // libhdf5 is not available in this build: the EMD payload is written as raw float32
+        // side files next to the requested name (layout: INTEGRATION.md).
+        std::string base(emd_save_name);
+        write_binary((base + ".images.f32").c_str(), image.data(), n123);
+        if (!ew.empty()) write_binary((base + ".exit_wave.f32").c_str(), ew.data(), ew.size());
+        if (!pot.empty()) write_binary((base + ".potential_slices.f32").c_str(), pot.data(), pot.size());
+    }
+    if (dstImage) memcpy(dstImage, image.data(), n123 * sizeof(float));   // exportFormedimage
+    fdes_b200_close(sim);
+}
+
+}  // extern "C"

@@ -1,0 +1,511 @@
+// fdes_b200 -- multislice engine (host orchestration of the sm_100a sweeps).
+// Mirrors the k / j / s loop structure of buildMeasurements (reference
+// src/crystalMaker.cu:227-424) with a different execution plan:
+//   * all per-simulation constants (propagator, scattering factors, twiddles, lens and detector
+//     tables) are computed once instead of once per slice;
+//   * atoms are binned and sorted once per phonon configuration instead of being scanned
+//     m3*nZ times;
+//   * B phonon configurations advance together through the six sweeps of a slice;
+//   * the wave function stays in the row-transformed (kx, y) domain between slices.
+#include "engine.h"
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+
+namespace fdes {
+
+static const KirklandRow kKirkland[103] = {
+#include "kirkland_table.inc"
+};
+
+#define CK(x)                                                                                    \
+    do {                                                                                         \
+        cudaError_t e_ = (x);                                                                    \
+        if (e_ != cudaSuccess)                                                                   \
+            throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) +      \
+                                     " at " + __FILE__ + ":" + std::to_string(__LINE__));        \
+    } while (0)
+
+template <typename T>
+static void dmalloc(T*& p, size_t n)
+{
+    CK(cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(n, 1) * sizeof(T)));
+}
+
+Engine::Engine(const Params& pin, const Atoms& atoms, const EngineOptions& opt) : p_(pin), opt_(opt)
+{
+    if (atoms.size() <= 0) throw std::runtime_error("no atoms in the specimen");
+    if (p_.mode < 0 || p_.mode > 2) throw std::runtime_error("mode must be 0 (imaging), 1 (DP) or 2 (CBED)");
+    if (p_.m1 != p_.m2)
+        throw std::runtime_error("non-square grids are not supported (the reference's phaseGrating "
+                                 "uses a transposed cuFFT plan for m1 != m2, src/crystalMaker.cu:575)");
+    if (!fft_size_supported(p_.m1))
+        throw std::runtime_error("grid size " + std::to_string(p_.m1) +
+                                 " unsupported: sample size (image + 2*border) must be a power of two in [64, 4096]");
+    if (p_.pD > FLT_EPSILON)
+        throw std::runtime_error("pixel_dose > 0 (Poisson noise) is not implemented yet; set pixel_dose: 0");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        throw std::runtime_error("no CUDA device: fdes_b200 has no CPU fallback");
+    CK(cudaSetDevice(opt_.gpu_index));
+
+    // sub-slicing (subSliceRatio / setSubSlices, src/crystalMaker.cu:246-247, 720-743)
+    m3_orig_ = p_.m3; d3_orig_ = p_.d3;
+    const float ratio = sub_slice_ratio(p_.d3, p_.subSlTh);
+    set_sub_slices(p_, ratio);
+    if (p_.m3 < 1) throw std::runtime_error("sample_size_z must be >= 1");
+
+    N_ = p_.m1;
+    nAt_ = atoms.size();
+    p_.nAt = nAt_;
+    Zlist_ = list_of_elements(atoms.Z);
+    nZ_ = (int)Zlist_.size();
+    count_ = p_.frPh > 0 ? p_.frPh : 1;
+    const int world = std::max(1, opt_.world), rank = std::min(std::max(0, opt_.rank), world - 1);
+    j0_ = (int)(((long long)count_ * rank) / world);
+    j1_ = (int)(((long long)count_ * (rank + 1)) / world);
+    rng_burn_ = j0_;
+    const int mine = std::max(1, j1_ - j0_);
+    B_ = opt_.batch > 0 ? opt_.batch : std::max(1, (2048 * 2048) / (N_ * N_));
+    B_ = std::min(B_, mine);
+    const long long nk = (long long)p_.m3 * nZ_ * N_;
+    if (nk >= (1LL << 31) - 2) throw std::runtime_error("slices * species * rows too large for 32-bit row keys");
+    nkeys_ = (int)nk;
+    key_bits_ = 0;
+    while ((1LL << key_bits_) <= nk) key_bits_++;
+    nrec_ = 4 * nAt_;
+    rec_stride_ = (size_t)nrec_;
+    rp_stride_ = (size_t)nkeys_ + 1;
+
+    CK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&ev0_));
+    CK(cudaEventCreate(&ev1_));
+
+    const size_t NN = (size_t)N_ * N_, Q = (size_t)(N_ / 2 + 1);
+    dmalloc(tw_, N_); dmalloc(Pq_, Q * Q); dmalloc(Gq_, (size_t)nZ_ * Q * Q);
+    dmalloc(psi_in_, NN); dmalloc(Psi_, (size_t)B_ * NN); dmalloc(W_, (size_t)B_ * NN);
+    dmalloc(A_, (size_t)B_ * nZ_ * NN);
+    dmalloc(I_own_, NN); dmalloc(lens_, NN); dmalloc(det_, NN); dmalloc(scratch_, NN);
+    dmalloc(J_, (size_t)p_.n1 * p_.n2);
+    if (opt_.want_exitwave) dmalloc(ew_own_, NN);
+    I_ = I_own_; ew_ = ew_own_;
+    dmalloc(xyz0_, 3 * (size_t)nAt_); dmalloc(xyzTO_, 3 * (size_t)nAt_); dmalloc(xyzK_, 3 * (size_t)nAt_);
+    dmalloc(xyzFP_, (size_t)B_ * 3 * nAt_); dmalloc(dwf_, nAt_); dmalloc(occ_, nAt_); dmalloc(zidx_, nAt_);
+    dmalloc(keys_, (size_t)B_ * nrec_); dmalloc(cols_, (size_t)B_ * nrec_); dmalloc(w_, (size_t)B_ * nrec_);
+    dmalloc(keys_tmp_, nrec_); dmalloc(cols_tmp_, nrec_); dmalloc(w_tmp_, nrec_);
+    dmalloc(rowptr_, (size_t)B_ * rp_stride_);
+    dmalloc(bins_, 4 * (size_t)nAt_);
+    dmalloc(hist_, 256 * (size_t)sort_num_blocks(nrec_));
+    dmalloc(norm_partial_, 256); dmalloc(norm_result_, 1);
+
+    std::vector<int> zidx(nAt_);
+    for (int i = 0; i < nAt_; i++)
+        zidx[i] = (int)(std::find(Zlist_.begin(), Zlist_.end(), atoms.Z[i]) - Zlist_.begin());
+    CK(cudaMemcpyAsync(zidx_, zidx.data(), nAt_ * sizeof(int), cudaMemcpyHostToDevice, st_));
+    CK(cudaMemcpyAsync(xyz0_, atoms.xyz.data(), 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyHostToDevice, st_));
+    CK(cudaMemcpyAsync(dwf_, atoms.dwf.data(), nAt_ * sizeof(float), cudaMemcpyHostToDevice, st_));
+    CK(cudaMemcpyAsync(occ_, atoms.occ.data(), nAt_ * sizeof(float), cudaMemcpyHostToDevice, st_));
+    CK(cudaStreamSynchronize(st_));   // host vectors above go out of scope
+
+    // coordinates with the tilt offset (src/crystalMaker.cu:282-283)
+    CK(cudaMemcpyAsync(xyzTO_, xyz0_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
+    tilt(xyzTO_, p_.tilt_off[0], p_.tilt_off[1], p_.tilt_off[2]);
+
+    if (p_.frPh > 0) {
+        CK(cudaMalloc(&rng_, rng_state_bytes() * 3 * (size_t)nAt_));
+        launch_rng_init(rng_, 3 * nAt_, 1ULL, st_);   // seed 1, src/crystalMaker.cu:292
+    }
+    setup_tables();
+    CK(cudaStreamSynchronize(st_));
+}
+
+Engine::~Engine()
+{
+    if (graph_) cudaGraphExecDestroy(graph_);
+    void* ptrs[] = {tw_, Pq_, Gq_, psi_in_, Psi_, W_, A_, I_own_, ew_own_, lens_, det_, scratch_, J_,
+                    xyz0_, xyzTO_, xyzK_, xyzFP_, dwf_, occ_, zidx_, rng_, keys_, keys_tmp_, cols_,
+                    cols_tmp_, w_, w_tmp_, rowptr_, bins_, hist_, norm_partial_, norm_result_};
+    for (void* q : ptrs) if (q) cudaFree(q);
+    if (ev0_) cudaEventDestroy(ev0_);
+    if (ev1_) cudaEventDestroy(ev1_);
+    if (st_) cudaStreamDestroy(st_);
+}
+
+void Engine::setup_tables()
+{
+    // twiddles in double precision
+    std::vector<cpx> tw(N_);
+    for (int n = 0; n < N_; n++) {
+        const double a = -2.0 * M_PI * (double)n / (double)N_;
+        tw[n] = make_float2((float)cos(a), (float)sin(a));
+    }
+    // exact values on the axes
+    tw[0] = make_float2(1.f, 0.f);
+    tw[N_ / 4] = make_float2(0.f, -1.f);
+    tw[N_ / 2] = make_float2(-1.f, 0.f);
+    tw[3 * N_ / 4] = make_float2(0.f, 1.f);
+    CK(cudaMemcpyAsync(tw_, tw.data(), N_ * sizeof(cpx), cudaMemcpyHostToDevice, st_));
+    CK(cudaStreamSynchronize(st_));
+
+    // 2/3 band limit: largest |i1| kept on the axis by zeroHighFreq's float test
+    int kb = 0;
+    const float mind = (float)N_;
+    while (kb + 1 <= N_ / 2 && !(((float)((kb + 1) * (kb + 1)) * 9.f / (mind * mind)) > 1.f)) kb++;
+    g_.N = N_;
+    g_.tw = tw_;
+    g_.lo_end = ((kb + 1 + 31) / 32) * 32;
+    g_.hi_start = ((N_ - kb) / 32) * 32;
+    if (g_.lo_end >= g_.hi_start) { g_.lo_end = N_; g_.hi_start = N_; }
+
+    launch_propagator_table(Pq_, N_, p_.d1, p_.d2, p_.d3, p_.lambda, p_.cst_pi, st_);
+    const size_t Q = (size_t)(N_ / 2 + 1);
+    for (int z = 0; z < nZ_; z++) {
+        KirklandRow kr;
+        const int Z = Zlist_[z];
+        if (Z >= 1 && Z <= 103) kr = kKirkland[Z - 1];
+        else {   // unknown element: a = 0, b = 1, c = 1, d = 0 (src/projectedPotential.cu:2984-3009)
+            const float fb[12] = {0, 1, 0, 1, 0, 1, 1, 0, 1, 0, 1, 0};
+            memcpy(kr.v, fb, sizeof fb);
+        }
+        launch_scattering_table(Gq_ + (size_t)z * Q * Q, N_, kr, p_.d1, p_.d2, p_.sigma, p_.cst_pi, st_);
+    }
+    tm_.kernel_launches += 1 + nZ_;
+}
+
+void Engine::tilt(float* xyz, float t0, float t1, float t2)
+{
+    // tiltCoordinates, src/crystalMaker.cu:427-454
+    if (fabsf(t2) > FLT_EPSILON) launch_rot(xyz, nAt_, 0, 1, cosf(t2), -sinf(t2), st_);
+    if (fabsf(t1) > FLT_EPSILON) launch_rot(xyz, nAt_, 0, 2, cosf(t1), -sinf(t1), st_);
+    if (fabsf(t0) > FLT_EPSILON) launch_rot(xyz, nAt_, 1, 2, cosf(t0), -sinf(t0), st_);
+}
+
+void Engine::set_accumulators(float* intensity_dev, cpx* exitwave_dev)
+{
+    I_ = intensity_dev ? intensity_dev : I_own_;
+    ew_ = exitwave_dev ? exitwave_dev : ew_own_;
+}
+
+static LensParams lens_params(const Params& p, int k, int mode)
+{
+    LensParams lp;
+    for (int a = 0; a < AB_COUNT; a++) { lp.ab0[a] = p.ab0[a]; lp.ab1[a] = p.ab1[a]; }
+    lp.defocus_k = p.defoci[k];
+    lp.defocspread = p.defocspread; lp.lambda = p.lambda; lp.d1 = p.d1; lp.d2 = p.d2;
+    lp.ObjAp = p.ObjAp; lp.pi = p.cst_pi; lp.mode = mode;
+    return lp;
+}
+
+// incomingWave, src/multisliceSimulation.cu:563-591 -> psi_in_ in the (kx, y) domain
+void Engine::make_incident(int k)
+{
+    if (incident_k_ == k) return;
+    const size_t NN = (size_t)N_ * N_;
+    RowOpts ro;
+    if (p_.mode == 2) {
+        // aperture * exp(-i chi) on the Fourier grid, inverse 2-D transform, fftshift
+        launch_lens_table(scratch_, N_, lens_params(p_, k, 2), 1.f, st_);
+        launch_cols_fft(g_, scratch_, scratch_, +1, COL_PLAIN, nullptr, 1.f, 1, st_);
+        launch_rows_fft(g_, scratch_, psi_in_, +1, ROW_STORE_SHIFT, ro, 1, st_);
+        // bandwidthLimit (:552-560): FFT2, 2/3 mask, IFFT2, 1/N -- left in row space
+        ro.band_only_out = true;
+        launch_rows_fft(g_, psi_in_, psi_in_, -1, ROW_STORE, ro, 1, st_);
+        launch_bandlimit_cols(g_, psi_in_, 1, st_);
+        // normalise to n1*n2 total intensity; psi = IFFT_row(Psi) => sum |psi|^2 = N * sum |Psi|^2
+        launch_norm2(psi_in_, NN, norm_partial_, norm_result_, st_);
+        double s = 0.0;
+        CK(cudaMemcpyAsync(&s, norm_result_, sizeof(double), cudaMemcpyDeviceToHost, st_));
+        CK(cudaStreamSynchronize(st_));
+        const float nrm = (float)sqrt(s * (double)N_);
+        const float alpha = sqrtf((float)(p_.n1 * p_.n2)) / nrm;
+        launch_scale_cpx(psi_in_, NN, alpha, st_);
+        tm_.kernel_launches += 8;
+    } else {
+        launch_plane_wave_rowspace(psi_in_, N_, 1, st_);
+        tm_.kernel_launches += 1;
+    }
+    if (p_.doBeamTilt) {
+        // phase ramp in real space (tiltBeam_d, :89-120)
+        RowOpts r2;
+        r2.band_only_in = (p_.mode == 2);
+        launch_rows_fft(g_, psi_in_, scratch_, +1, ROW_STORE, r2, 1, st_);
+        launch_tilt_beam(scratch_, N_, p_.d1, p_.d2, p_.lambda, p_.tiltbeam[2 * k], p_.tiltbeam[2 * k + 1],
+                         p_.cst_pi, 1, st_);
+        RowOpts r3;
+        if (p_.mode == 0 || p_.mode == 1) {
+            launch_tukey_window(scratch_, N_, p_.dn1, p_.dn2, p_.cst_pi, st_);
+            r3.band_only_out = true;
+            launch_rows_fft(g_, scratch_, psi_in_, -1, ROW_STORE, r3, 1, st_);
+            launch_bandlimit_cols(g_, psi_in_, 1, st_);
+        } else {
+            r3.scale = 1.f / (float)N_;   // row-space convention: Psi = FFT_row(psi) / N
+            launch_rows_fft(g_, scratch_, psi_in_, -1, ROW_STORE, r3, 1, st_);
+        }
+        tm_.kernel_launches += 5;
+    }
+    incident_k_ = k;
+}
+
+void Engine::bin_and_sort(int b, const float* xyz_dev)
+{
+    BinGeom bg{N_, N_, p_.m3, nZ_, p_.d1, p_.d2, p_.d3};
+    uint32_t* keys = keys_ + (size_t)b * nrec_;
+    int* cols = cols_ + (size_t)b * nrec_;
+    float* w = w_ + (size_t)b * nrec_;
+    launch_bin_atoms(xyz_dev, zidx_, occ_, nAt_, bg, keys, cols, w, nullptr, st_);
+    SortBuffers sb{keys, keys_tmp_, cols, cols_tmp_, w, w_tmp_, hist_};
+    launch_radix_sort(sb, nrec_, key_bits_, st_);
+    launch_row_pointers(keys, nrec_, rowptr_ + (size_t)b * rp_stride_, nkeys_, st_);
+    int passes = (key_bits_ + 7) / 8; if (passes & 1) passes++; if (!passes) passes = 2;
+    tm_.kernel_launches += 2 + 3 * passes;
+}
+
+void Engine::prepare_config(int b, const float* xyz_k)
+{
+    float* fp = xyzFP_ + (size_t)b * 3 * nAt_;
+    if (p_.frPh > 0) {
+        launch_atom_jitter(fp, xyz_k, dwf_, nAt_, rng_, rng_burn_, st_);
+        rng_burn_ = 0;
+        tm_.kernel_launches += 1;
+    } else {
+        CK(cudaMemcpyAsync(fp, xyz_k, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
+    }
+    bin_and_sort(b, fp);
+}
+
+void Engine::run_slices_plain(int nb, cpx* Vtrace)
+{
+    const size_t NN = (size_t)N_ * N_;
+    const bool first_full = p_.doBeamTilt && p_.mode == 2;
+    for (int s = 0; s < p_.m3; s++) {
+        launch_density_rows(g_, A_, rowptr_, cols_, w_, s, nZ_, nb, rec_stride_, rp_stride_, p_.imPot, st_);
+        launch_potential_cols(g_, W_, A_, Gq_, rowptr_, s, nZ_, nb, rp_stride_, st_);
+        launch_transmit_rows(g_, W_, Vtrace ? Vtrace + (size_t)s * NN : nullptr, nb, st_);
+        launch_bandlimit_cols(g_, W_, nb, st_);
+        launch_multiply_rows(g_, Psi_, W_, NN, nb, first_full && s == 0, st_);
+        launch_propagate_cols(g_, Psi_, Pq_, nb, st_);
+    }
+    if (first_full) launch_zero_outband(Psi_, N_, g_.lo_end, g_.hi_start, nb, st_);
+}
+
+void Engine::slice_loop(int nb, cpx* Vtrace)
+{
+    tm_.slices_executed += (long long)p_.m3 * nb;
+    tm_.kernel_launches += 6LL * p_.m3;
+    if (!opt_.use_graph || Vtrace) { run_slices_plain(nb, Vtrace); return; }
+    if (!graph_ || graph_nb_ != nb) {
+        if (graph_) { cudaGraphExecDestroy(graph_); graph_ = nullptr; }
+        // first use of each kernel must happen outside capture (function attributes are set there)
+        if (!warmed_) { run_slices_plain(nb, nullptr); warmed_ = true; graph_nb_ = -1; return; }
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(st_, cudaStreamCaptureModeThreadLocal));
+        run_slices_plain(nb, nullptr);
+        CK(cudaStreamEndCapture(st_, &g));
+        CK(cudaGraphInstantiate(&graph_, g, 0));
+        CK(cudaGraphDestroy(g));
+        graph_nb_ = nb;
+    }
+    CK(cudaGraphLaunch(graph_, st_));
+}
+
+void Engine::accumulate_outputs(int k, int nb)
+{
+    const size_t NN = (size_t)N_ * N_;
+    const float alpha = 1.f / ((float)count_);
+    if (p_.mode == 0 && lens_k_ != k) {
+        // CTF with the 1/N of applyLensFunction folded in (src/multisliceSimulation.cu:614-622)
+        launch_lens_table(lens_, N_, lens_params(p_, k, 0), 1.f, st_);
+        lens_k_ = k;
+        tm_.kernel_launches += 1;
+    }
+    for (int b = 0; b < nb; b++) {   // fixed order: deterministic phonon average
+        cpx* psi = Psi_ + (size_t)b * NN;
+        if (ew_) {
+            RowOpts ro; ro.scale = alpha; ro.band_only_in = true;
+            launch_rows_fft(g_, psi, ew_, +1, ROW_ACCUM, ro, 1, st_);
+            tm_.kernel_launches += 1;
+        }
+        if (p_.mode == 0) {
+            launch_cols_fft(g_, psi, scratch_, -1, COL_MUL_CPX_INV, lens_, 1.f / ((float)N_), 1, st_);
+            RowOpts ro; ro.scale = alpha;
+            launch_rows_fft(g_, scratch_, I_, +1, ROW_INTENS_ACCUM, ro, 1, st_);
+            tm_.kernel_launches += 2;
+        } else {
+            // diffractionPattern, src/crystalMaker.cu:700-718
+            // |fftshift(FFT2 psi)|^2 / N^2: FFT_col(Psi) = FFT2(psi) / N already carries the 1/N
+            const float scale = alpha;
+            const cpx* src = psi;
+            if (p_.doBeamTilt || p_.mode == 1) {
+                RowOpts ro; ro.band_only_in = true;
+                launch_rows_fft(g_, psi, scratch_, +1, ROW_STORE, ro, 1, st_);
+                if (p_.doBeamTilt)
+                    launch_tilt_beam(scratch_, N_, p_.d1, p_.d2, p_.lambda, p_.tiltbeam[2 * k],
+                                     p_.tiltbeam[2 * k + 1], p_.cst_pi, -1, st_);
+                RowOpts r2;
+                if (p_.mode == 1) {
+                    launch_area_mask_blend(scratch_, N_, p_.dn1, p_.dn2, st_);
+                    r2.band_only_out = true;
+                    launch_rows_fft(g_, scratch_, scratch_, -1, ROW_STORE, r2, 1, st_);
+                    launch_bandlimit_cols(g_, scratch_, 1, st_);
+                } else {
+                    r2.scale = 1.f / (float)N_;
+                    launch_rows_fft(g_, scratch_, scratch_, -1, ROW_STORE, r2, 1, st_);
+                }
+                src = scratch_;
+                tm_.kernel_launches += 4;
+            }
+            launch_cols_fft(g_, src, I_, -1, COL_DP_ACCUM, nullptr, scale, 1, st_);
+            tm_.kernel_launches += 1;
+        }
+    }
+}
+
+void Engine::run_k(int k)
+{
+    if (k < 0 || k >= p_.n3) throw std::runtime_error("measurement index out of range");
+    const size_t NN = (size_t)N_ * N_;
+    launch_fill_f32(I_, NN, 0.f, st_);
+    if (ew_) launch_fill_cpx(ew_, NN, make_float2(0.f, 0.f), st_);
+    CK(cudaMemcpyAsync(xyzK_, xyzTO_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
+    tilt(xyzK_, p_.tiltspec[2 * k], p_.tiltspec[2 * k + 1], 0.f);
+    make_incident(k);
+    for (int j = j0_; j < j1_; j += B_) {
+        const int nb = std::min(B_, j1_ - j);
+        for (int b = 0; b < nb; b++) {
+            prepare_config(b, xyzK_);
+            CK(cudaMemcpyAsync(Psi_ + (size_t)b * NN, psi_in_, NN * sizeof(cpx), cudaMemcpyDeviceToDevice, st_));
+        }
+        slice_loop(nb);
+        accumulate_outputs(k, nb);
+    }
+    CK(cudaStreamSynchronize(st_));
+}
+
+void Engine::finish_k(int k, float* image_host, float* exitwave_host)
+{
+    const size_t NN = (size_t)N_ * N_;
+    // addNoiseAndMtf (src/crystalMaker.cu:579-613) without the noise branch + copyMiddleOut
+    DetectorParams dp{p_.mtfa, p_.mtfb, p_.mtfc, p_.mtfd, p_.illangle, p_.defoci[k], p_.lambda,
+                      p_.d1, p_.d2, p_.cst_pi, p_.mode, fabsf(p_.illangle) > FLT_EPSILON ? 1 : 0};
+    launch_detector_table(det_, N_, dp, 1.f / ((float)(N_ * N_)), st_);
+    RowOpts ri; ri.in_is_real = true;
+    launch_rows_fft(g_, I_, scratch_, -1, ROW_STORE, ri, 1, st_);
+    launch_cols_fft(g_, scratch_, scratch_, -1, COL_MUL_REAL_INV, det_, 1.f, 1, st_);
+    RowOpts rc; rc.dn1 = p_.dn1; rc.dn2 = p_.dn2; rc.n1 = p_.n1; rc.n2 = p_.n2;
+    launch_rows_fft(g_, scratch_, J_, +1, ROW_CROP_REAL, rc, 1, st_);
+    tm_.kernel_launches += 4;
+    if (image_host)
+        CK(cudaMemcpyAsync(image_host, J_, (size_t)p_.n1 * p_.n2 * sizeof(float), cudaMemcpyDeviceToHost, st_));
+    if (exitwave_host && ew_)
+        CK(cudaMemcpyAsync(exitwave_host, ew_, NN * sizeof(cpx), cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+}
+
+void Engine::potential_slices(float* out_host)
+{
+    // untilted (offset only), phonon-free potential with the original slicing
+    // (src/crystalMaker.cu:381-397).  NOTE: the reference leaves this buffer uninitialised when
+    // no sub-slicing/phonons/tilt are active; here it is always computed.
+    const size_t NN = (size_t)N_ * N_;
+    Params save = p_;
+    p_.m3 = m3_orig_; p_.d3 = d3_orig_;
+    const int nkeys_save = nkeys_, bits_save = key_bits_;
+    nkeys_ = m3_orig_ * nZ_ * N_;
+    key_bits_ = 0; while ((1LL << key_bits_) <= nkeys_) key_bits_++;
+    bin_and_sort(0, xyzTO_);
+    RowOpts ro; ro.scale = 1.f;
+    for (int s = 0; s < m3_orig_; s++) {
+        launch_density_rows(g_, A_, rowptr_, cols_, w_, s, nZ_, 1, rec_stride_, rp_stride_, p_.imPot, st_);
+        launch_potential_cols(g_, W_, A_, Gq_, rowptr_, s, nZ_, 1, rp_stride_, st_);
+        launch_rows_fft(g_, W_, scratch_, +1, ROW_STORE, ro, 1, st_);
+        CK(cudaMemcpyAsync(out_host + (size_t)s * 2 * NN, scratch_, NN * sizeof(cpx), cudaMemcpyDeviceToHost, st_));
+        CK(cudaStreamSynchronize(st_));
+    }
+    tm_.kernel_launches += 3LL * m3_orig_;
+    p_ = save; nkeys_ = nkeys_save; key_bits_ = bits_save;
+}
+
+// ---------------------------------------------------------------------------------------------
+// building blocks for tests / benchmarks
+// ---------------------------------------------------------------------------------------------
+void Engine::next_jittered_coords(int k, float* xyz_host)
+{
+    CK(cudaMemcpyAsync(xyzK_, xyzTO_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
+    tilt(xyzK_, p_.tiltspec[2 * k], p_.tiltspec[2 * k + 1], 0.f);
+    if (p_.frPh > 0) { launch_atom_jitter(xyzFP_, xyzK_, dwf_, nAt_, rng_, rng_burn_, st_); rng_burn_ = 0; }
+    else CK(cudaMemcpyAsync(xyzFP_, xyzK_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
+    CK(cudaMemcpyAsync(xyz_host, xyzFP_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+}
+
+void Engine::bin_tuples(const float* xyz_host, int* bins_host)
+{
+    CK(cudaMemcpyAsync(xyzFP_, xyz_host, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyHostToDevice, st_));
+    BinGeom bg{N_, N_, p_.m3, nZ_, p_.d1, p_.d2, p_.d3};
+    launch_bin_atoms(xyzFP_, zidx_, occ_, nAt_, bg, keys_, cols_, w_, bins_, st_);
+    CK(cudaMemcpyAsync(bins_host, bins_, 4 * (size_t)nAt_ * sizeof(int), cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+}
+
+void Engine::phase_grating(const float* xyz_host, int s, float* V_host)
+{
+    const size_t NN = (size_t)N_ * N_;
+    CK(cudaMemcpyAsync(xyzFP_, xyz_host, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyHostToDevice, st_));
+    bin_and_sort(0, xyzFP_);
+    launch_density_rows(g_, A_, rowptr_, cols_, w_, s, nZ_, 1, rec_stride_, rp_stride_, p_.imPot, st_);
+    launch_potential_cols(g_, W_, A_, Gq_, rowptr_, s, nZ_, 1, rp_stride_, st_);
+    RowOpts ro;
+    launch_rows_fft(g_, W_, scratch_, +1, ROW_STORE, ro, 1, st_);
+    CK(cudaMemcpyAsync(V_host, scratch_, NN * sizeof(cpx), cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+}
+
+void Engine::exit_wave(const float* xyz_host, int k, float* psi_host)
+{
+    const size_t NN = (size_t)N_ * N_;
+    CK(cudaMemcpyAsync(xyzFP_, xyz_host, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyHostToDevice, st_));
+    bin_and_sort(0, xyzFP_);
+    make_incident(k);
+    CK(cudaMemcpyAsync(Psi_, psi_in_, NN * sizeof(cpx), cudaMemcpyDeviceToDevice, st_));
+    const bool ug = opt_.use_graph;
+    opt_.use_graph = false;
+    slice_loop(1);
+    opt_.use_graph = ug;
+    RowOpts ro; ro.band_only_in = true; ro.scale = 1.f;
+    launch_rows_fft(g_, Psi_, scratch_, +1, ROW_STORE, ro, 1, st_);
+    CK(cudaMemcpyAsync(psi_host, scratch_, NN * sizeof(cpx), cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+}
+
+double Engine::bench_configs(int k, int configs)
+{
+    const size_t NN = (size_t)N_ * N_;
+    launch_fill_f32(I_, NN, 0.f, st_);
+    if (ew_) launch_fill_cpx(ew_, NN, make_float2(0.f, 0.f), st_);
+    CK(cudaMemcpyAsync(xyzK_, xyzTO_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
+    tilt(xyzK_, p_.tiltspec[2 * k], p_.tiltspec[2 * k + 1], 0.f);
+    make_incident(k);
+    CK(cudaStreamSynchronize(st_));
+    CK(cudaEventRecord(ev0_, st_));
+    for (int j = 0; j < configs; j += B_) {
+        const int nb = std::min(B_, configs - j);
+        for (int b = 0; b < nb; b++) {
+            prepare_config(b, xyzK_);
+            CK(cudaMemcpyAsync(Psi_ + (size_t)b * NN, psi_in_, NN * sizeof(cpx), cudaMemcpyDeviceToDevice, st_));
+        }
+        slice_loop(nb);
+        accumulate_outputs(k, nb);
+    }
+    CK(cudaEventRecord(ev1_, st_));
+    CK(cudaEventSynchronize(ev1_));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    tm_.slice_loop_ms += ms;
+    return (double)ms;
+}
+
+}  // namespace fdes

@@ -1,0 +1,102 @@
+// fdes_b200 -- command-line front end with the option set of the reference CLI
+// (reference src/FDES.cu:61-263, Useage.txt:26-37):
+//   FDES [--input_name f.cnf] [--image_name out.bin] [--emd_name out.emd]
+//        [--print_level 0|1|2] [--gpu_index n] [--help] [--version]
+// Defaults as in src/FDES.cu:40-44: dataFDES.cnf -> Measurements.bin, results.emd.
+#include "../../include/fdes_b200.h"
+#include "params.h"
+#include <getopt.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+int main(int argc, char** argv)
+{
+    std::string input = "dataFDES.cnf", image = "Measurements.bin", emd = "results.emd";
+    int gpu_index = 0, print_level = 0;
+    static struct option opts[] = {{"gpu_index", required_argument, 0, 0},
+                                   {"input_name", required_argument, 0, 0},
+                                   {"image_name", required_argument, 0, 0},
+                                   {"emd_name", required_argument, 0, 0},
+                                   {"print_level", required_argument, 0, 0},
+                                   {"help", no_argument, 0, 0},
+                                   {"version", no_argument, 0, 0},
+                                   {NULL, 0, 0, 0}};
+    while (true) {
+        int idx = 0;
+        const int c = getopt_long(argc, argv, "", opts, &idx);
+        if (c == -1) break;
+        if (c != 0) { fprintf(stderr, "  unknown option, try --help\n"); return EXIT_FAILURE; }
+        switch (idx) {
+            case 0: gpu_index = atoi(optarg); break;
+            case 1: input = optarg; fprintf(stderr, "  input_name %s  \n", optarg); break;
+            case 2: image = optarg; break;
+            case 3: emd = optarg; break;
+            case 4:
+                print_level = atoi(optarg);
+                if (print_level < 0 || print_level > 2) {
+                    fprintf(stderr, " \n printLevel error %s  \n", input.c_str());
+                    return EXIT_FAILURE;
+                }
+                break;
+            case 5:
+                fprintf(stderr,
+                        " \nUsage: \n"
+                        "  [ --input_name  <parameter file (.cnf)> ]\n"
+                        "  [ --image_name  <raw float32 image output, default Measurements.bin> ]\n"
+                        "  [ --emd_name    <results name, default results.emd> ]\n"
+                        "  [ --print_level <0 images | 1 + potential slices | 2 + exit waves> ]\n"
+                        "  [ --gpu_index   <CUDA device ordinal, default 0> ]\n"
+                        "  [ --help ] [ --version ]\n");
+                return EXIT_FAILURE;
+            case 6: fprintf(stderr, " \n FDES (fdes_b200) Version : %1.1f  \n", fdes_b200_version() / 100.0); return EXIT_FAILURE;
+        }
+    }
+    // The CLI takes the atoms from the file; FDES() wants them as an array (atomsFromExternal).
+    fdes::Params p;
+    fdes::Atoms atoms;
+    if (!fdes::read_cnf(input.c_str(), p, &atoms, false)) {
+        fprintf(stderr, " \n Errors occur when reading \"%s\" \n", input.c_str());
+        return EXIT_FAILURE;
+    }
+    if (atoms.size() == 0) { fprintf(stderr, "No valid configuration for simulation!.\n"); return EXIT_FAILURE; }
+    std::vector<float> a6(6 * (size_t)atoms.size());
+    for (int i = 0; i < atoms.size(); i++) {
+        a6[6 * i + 0] = (float)atoms.Z[i];
+        a6[6 * i + 1] = atoms.xyz[3 * i + 0];
+        a6[6 * i + 2] = atoms.xyz[3 * i + 1];
+        a6[6 * i + 3] = atoms.xyz[3 * i + 2];
+        a6[6 * i + 4] = atoms.dwf[i];
+        a6[6 * i + 5] = atoms.occ[i];
+    }
+    // NOTE: FDES() truncates the occupancy to an integer like the reference's readAtomsFromArray;
+    // the file path keeps fractional occupancies, so the CLI goes through the session API.
+    fdes_b200_sim* sim = fdes_b200_open_cnf(input.c_str(), nullptr, 0, gpu_index, 0, 0, 1, print_level > 1);
+    if (!sim) { fprintf(stderr, " \n fdes_b200: %s \n", fdes_b200_last_error()); return EXIT_FAILURE; }
+    int d[10];
+    fdes_b200_get_dims(sim, d);
+    const size_t n123 = (size_t)d[0] * d[1] * d[2], m12 = (size_t)d[3] * d[4];
+    std::vector<float> img(n123), ew, pot;
+    if (print_level > 1) ew.resize(2 * m12 * d[2]);
+    if (fdes_b200_simulate(sim, img.data(), ew.empty() ? nullptr : ew.data()) != 0) {
+        fprintf(stderr, " \n fdes_b200: %s \n", fdes_b200_last_error());
+        return EXIT_FAILURE;
+    }
+    if (print_level > 0) {
+        pot.resize(2 * m12 * (size_t)fdes_b200_potential_slices_count(sim));
+        if (fdes_b200_potential(sim, pot.data()) != 0) {
+            fprintf(stderr, " \n fdes_b200: %s \n", fdes_b200_last_error());
+            return EXIT_FAILURE;
+        }
+    }
+    fdes::write_cnf("dataFDES_used.cnf", p, atoms, gpu_index);
+    fdes::write_binary(image.c_str(), img.data(), n123);
+    fdes::write_binary((emd + ".images.f32").c_str(), img.data(), n123);
+    if (!ew.empty()) fdes::write_binary((emd + ".exit_wave.f32").c_str(), ew.data(), ew.size());
+    if (!pot.empty()) fdes::write_binary((emd + ".potential_slices.f32").c_str(), pot.data(), pot.size());
+    fdes_b200_close(sim);
+    fprintf(stderr, "  Done.\n");
+    return 0;
+}

@@ -1,0 +1,145 @@
+// fdes_b200 -- launch interface of the sm_100a multislice kernels (kernels.cu).
+// Everything here is plain device pointers + sizes; the engine (engine.cu) owns the memory.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace fdes {
+
+typedef float2 cpx;
+
+// Geometry shared by all sweeps of one simulation (square grid, N = m1 = m2).
+struct SweepGeom {
+    int N;              // grid size (power of two, 64..4096)
+    int lo_end;         // columns kx in [0, lo_end) or [hi_start, N) can be non-zero after the
+    int hi_start;       //   2/3 band limit (bounds rounded outwards to multiples of 32)
+    const cpx* tw;      // forward twiddles exp(-2 pi i n / N), n < N
+};
+
+bool fft_size_supported(int N);
+int rows_per_block(int N);
+int cols_per_block(int N);
+
+// ---- per-slice sweeps (S1..S6) -------------------------------------------
+// S1: per-species density rows from the sorted deposit records -> row FFT -> A
+void launch_density_rows(const SweepGeom& g, cpx* A, const int* rowptr, const int* rec_col,
+                         const float* rec_w, int slice, int nZ, int batch, size_t rec_stride,
+                         size_t rowptr_stride, float imPot, cudaStream_t st);
+// S2: column FFT of every species, x scattering factor, species sum, inverse column FFT -> B
+void launch_potential_cols(const SweepGeom& g, cpx* B, const cpx* A, const float* Gq,
+                           const int* rowptr, int slice, int nZ, int batch, size_t rowptr_stride,
+                           cudaStream_t st);
+// S3: inverse row FFT -> V -> exp(iV) -> row FFT (in place on W).  Vout (may be null) receives V.
+void launch_transmit_rows(const SweepGeom& g, cpx* W, cpx* Vout, int batch, cudaStream_t st);
+// S4: column FFT -> 2/3 mask and 1/N -> inverse column FFT (in place, band columns only)
+void launch_bandlimit_cols(const SweepGeom& g, cpx* W, int batch, cudaStream_t st);
+// S5: t = IFFT_row(E), psi = IFFT_row(Psi); Psi <- FFT_row(t * psi).  E batch stride may be 0
+//     (shared transmission stack).  psi_full: Psi may have out-of-band columns (first slice).
+void launch_multiply_rows(const SweepGeom& g, cpx* Psi, const cpx* E, size_t e_batch_stride,
+                          int batch, bool psi_full, cudaStream_t st);
+// S6: column FFT -> x Fresnel propagator (quarter table, mask and 1/N folded in) -> inverse
+void launch_propagate_cols(const SweepGeom& g, cpx* Psi, const cpx* Pq, int batch, cudaStream_t st);
+
+// ---- generic sweeps used outside the slice loop ------------------------------------------
+enum RowEpilogue {
+    ROW_STORE = 0,         // out = scale * v
+    ROW_ACCUM = 1,         // out += scale * v                      (exit-wave average)
+    ROW_INTENS_ACCUM = 2,  // outI += scale * |v|^2  (float array)  (image intensity)
+    ROW_STORE_SHIFT = 3,   // out[(y+N/2)%N][(x+N/2)%N] = scale * v (fftshift)
+    ROW_CROP_REAL = 4      // outI[(y-dn2)*n1 + (x-dn1)] = scale * Re v inside the crop
+};
+struct RowOpts {
+    float scale = 1.f;
+    int dn1 = 0, dn2 = 0, n1 = 0, n2 = 0;   // ROW_CROP_REAL
+    bool in_is_real = false;                // input is a float array (imag = 0)
+    bool band_only_in = false;              // load only band columns (others are 0)
+    bool band_only_out = false;             // ROW_STORE: write 0 outside the band
+};
+// dir = -1 forward, +1 inverse (unnormalised).  in/out batch strides are N*N elements.
+void launch_rows_fft(const SweepGeom& g, const void* in, void* out, int dir, RowEpilogue epi,
+                     const RowOpts& o, int batch, cudaStream_t st);
+
+enum ColOp {
+    COL_PLAIN = 0,        // out = FFT_dir(in)
+    COL_MUL_CPX_INV = 1,  // out = IFFT( FFT(in) * tab_c[ky][kx] )      (lens function / CTF)
+    COL_MUL_REAL_INV = 2, // out = IFFT( FFT(in) * tab_r[ky][kx] )      (MTF / incoherence)
+    COL_DP_ACCUM = 3      // outI[fftshift(ky,kx)] += scale * |FFT(in)|^2   (diffraction pattern)
+};
+void launch_cols_fft(const SweepGeom& g, const cpx* in, void* out, int dir, ColOp op,
+                     const void* table, float scale, int batch, cudaStream_t st);
+
+// ---- set-up kernels (tables follow the reference's float32 expressions) ------------------
+struct KirklandRow { float v[12]; };  // a0 b0 a1 b1 a2 b2 c0 d0 c1 d1 c2 d2
+// Gq[(N/2+1)^2]: scattering factor * sinc correction * normalisation (projectedPotential_d +
+// divideBySinc, reference src/projectedPotential.cu:30-73, src/crystalMaker.cu:136-158)
+void launch_scattering_table(float* Gq, int N, KirklandRow kr, float d1, float d2, float sigma,
+                             float pi, cudaStream_t st);
+// Pq[(N/2+1)^2]: Fresnel propagator with 2/3 mask and 1/N (src/multisliceSimulation.cu:253-274,
+// 594-603)
+void launch_propagator_table(cpx* Pq, int N, float d1, float d2, float d3, float lambda, float pi,
+                             cudaStream_t st);
+struct LensParams {
+    float ab0[14], ab1[14];  // C1 A1 A2 B2 C3 A3 S3 A4 B4 D4 C5 A5 R5 S5
+    float defocus_k, defocspread, lambda, d1, d2, ObjAp, pi;
+    int mode;
+};
+// full [N][N] complex table of multiplyLensFunction (src/multisliceSimulation.cu:277-343);
+// 0 outside the aperture; extra_scale folded in.
+void launch_lens_table(cpx* tab, int N, const LensParams& lp, float extra_scale, cudaStream_t st);
+// full [N][N] real table: MTF * (optional spatial incoherence) * scale
+// (src/multisliceSimulation.cu:362-442)
+struct DetectorParams {
+    float mtfa, mtfb, mtfc, mtfd, illangle, defocus_k, lambda, d1, d2, pi;
+    int mode; int use_incoherence;
+};
+void launch_detector_table(float* tab, int N, const DetectorParams& dp, float scale, cudaStream_t st);
+
+// ---- small utilities ----------------------------------------------------------------------
+void launch_fill_cpx(cpx* p, size_t n, cpx v, cudaStream_t st);
+void launch_fill_f32(float* p, size_t n, float v, cudaStream_t st);
+// plane wave psi = 1 in the (kx, y) domain (Psi = FFT_row(psi)/N): Psi[y][0] = 1, rest 0
+void launch_plane_wave_rowspace(cpx* Psi, int N, int batch, cudaStream_t st);
+void launch_scale_cpx(cpx* p, size_t n, float s, cudaStream_t st);
+// Psi[y][kx] = 0 for the columns outside the band (kx in [lo_end, hi_start))
+void launch_zero_outband(cpx* Psi, int N, int lo_end, int hi_start, int batch, cudaStream_t st);
+// deterministic sum of |p|^2 in double (two-stage tree); result[0] on device
+void launch_norm2(const cpx* p, size_t n, double* partial, double* result, cudaStream_t st);
+// real-space pointwise ops for the rarely used beam-tilt / Tukey / area-mask paths
+void launch_tilt_beam(cpx* psi, int N, float d1, float d2, float lambda, float tb_x, float tb_y,
+                      float pi, int flag, cudaStream_t st);
+void launch_tukey_window(cpx* psi, int N, int dn1, int dn2, float pi, cudaStream_t st);
+void launch_area_mask_blend(cpx* psi, int N, int dn1, int dn2, cudaStream_t st);
+
+// ---- atoms: tilt, frozen phonons, binning, sort, row pointers -----------------------------
+struct BinGeom {
+    int m1, m2, m3, nZ;
+    float d1, d2, d3;
+};
+void launch_rot(float* xyz, int nAt, int axA, int axB, float c, float s, cudaStream_t st);
+// XORWOW states: curand_init(seed, i, 0) for i < n  (reference src/crystalMaker.cu:28-35)
+size_t rng_state_bytes();
+void launch_rng_init(void* states, int n, unsigned long long seed, cudaStream_t st);
+// xyz_out[i] = xyz_in[i] + N(0,1) * 0.112539540f * sqrtf(dwf[i/3]); burn: draws to discard first
+void launch_atom_jitter(float* xyz_out, const float* xyz_in, const float* dwf, int nAt,
+                        void* states, int burn, cudaStream_t st);
+// per atom: 4 deposit records (key = (i3*nZ + zidx)*m2 + row, col, weight) and the integer bin
+// tuple (i1, i2, i3, zidx; -1 when rejected) -- squareAtoms_d, src/crystalMaker.cu:73-134
+void launch_bin_atoms(const float* xyz, const int* zidx, const float* occ, int nAt,
+                      const BinGeom& bg, uint32_t* keys, int* cols, float* w, int* bins_out,
+                      cudaStream_t st);
+// stable LSD radix sort of (key, col, w) by key; tmp buffers same sizes; hist: 256*nblocks ints
+struct SortBuffers {
+    uint32_t *keys, *keys_tmp;
+    int *cols, *cols_tmp;
+    float *w, *w_tmp;
+    unsigned int* hist;   // 256 * sort_num_blocks(n) entries
+};
+int sort_num_blocks(int n);
+void launch_radix_sort(const SortBuffers& sb, int n, int key_bits, cudaStream_t st);
+// rowptr[k] = first sorted record with key >= k, k in [0, nkeys]; records with key >= nkeys
+// (rejected atoms) stay beyond rowptr[nkeys]
+void launch_row_pointers(const uint32_t* keys_sorted, int n, int* rowptr, int nkeys,
+                         cudaStream_t st);
+
+}  // namespace fdes

@@ -1,0 +1,571 @@
+// fdes_b200 -- the multislice sweeps: hand-written sm_100a kernels that replace the
+// cuFFT + cuBLAS + one-thread-per-pixel chain of the reference's per-slice loop
+// (phaseGrating, src/crystalMaker.cu:507-536; forwardPropagation,
+// src/multisliceSimulation.cu:538-611).
+//
+// The wave function lives in the mixed (kx, y) domain between slices ("row space": rows are
+// Fourier transformed, columns are not).  One slice is six sweeps over the grid:
+//   S1 rows : density rows of each species (from sorted deposit records) -> FFT_row          -> A_z
+//   S2 cols : FFT_col(A_z) * G_z, sum over species, IFFT_col                                -> B
+//   S3 rows : IFFT_row(B) = V ; t0 = exp(iV) ; FFT_row(t0)                                   -> D
+//   S4 cols : FFT_col(D) * (2/3 mask / N) ; IFFT_col                                         -> E
+//   S5 rows : t = IFFT_row(E), psi = IFFT_row(Psi) ; FFT_row(t * psi)                        -> F
+//   S6 cols : FFT_col(F) * P ; IFFT_col                                                      -> Psi'
+// Every sweep reads and writes each pixel once; all multipliers come from small L2-resident
+// quarter tables.  Columns that the 2/3 band limit zeroes entirely (|kx| > N/3) are neither
+// stored, loaded nor transformed by S3..S6.
+#include "fft_core.cuh"
+#include "kernels.cuh"
+#include <cstdio>
+#include <cstdlib>
+
+namespace fdes {
+
+#define FDES_CUDA_CHECK(x)                                                                       \
+    do {                                                                                         \
+        cudaError_t e_ = (x);                                                                    \
+        if (e_ != cudaSuccess) {                                                                 \
+            fprintf(stderr, "fdes_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_),       \
+                    __FILE__, __LINE__);                                                         \
+            abort();                                                                             \
+        }                                                                                        \
+    } while (0)
+
+template <int N>
+struct RowCfg {
+    static constexpr int T = N / FFT_E;
+    static constexpr int RPB = (256 / T) > 0 ? (256 / T) : 1;
+    static constexpr int THREADS = RPB * T;
+    static constexpr int LSTRIDE = line_smem_elems(N);
+    static constexpr size_t SMEM = (size_t)RPB * LSTRIDE * sizeof(cpx);
+};
+// HEAVY kernels keep two register sets per thread -> fewer columns per CTA for large N.
+template <int N, bool HEAVY>
+struct ColCfg {
+    static constexpr int T = N / FFT_E;
+    static constexpr int CW0 = N <= 256 ? 16 : (N <= 1024 ? 8 : 4);
+    static constexpr int CW = (HEAVY && CW0 * T > 512) ? 512 / T : CW0;
+    static constexpr int THREADS = CW * T;
+    static constexpr int LSTRIDE = line_smem_elems(N) + 16 / CW;  // bank-conflict-free line stride
+    static constexpr size_t SMEM = (size_t)CW * LSTRIDE * sizeof(cpx);
+};
+
+bool fft_size_supported(int N)
+{
+    return N == 64 || N == 128 || N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096;
+}
+int rows_per_block(int N) { return (256 / (N / FFT_E)) > 0 ? 256 / (N / FFT_E) : 1; }
+int cols_per_block(int N) { return N <= 256 ? 16 : (N <= 1024 ? 8 : 4); }
+
+#define FDES_DISPATCH_N(N_, ...)                                                               \
+    switch (N_) {                                                                                \
+        case 64: { constexpr int NN = 64; __VA_ARGS__; } break;                                         \
+        case 128: { constexpr int NN = 128; __VA_ARGS__; } break;                                       \
+        case 256: { constexpr int NN = 256; __VA_ARGS__; } break;                                       \
+        case 512: { constexpr int NN = 512; __VA_ARGS__; } break;                                       \
+        case 1024: { constexpr int NN = 1024; __VA_ARGS__; } break;                                     \
+        case 2048: { constexpr int NN = 2048; __VA_ARGS__; } break;                                     \
+        case 4096: { constexpr int NN = 4096; __VA_ARGS__; } break;                                     \
+        default:                                                                                 \
+            fprintf(stderr, "fdes_b200: unsupported grid size %d (need a power of two in "       \
+                            "[64, 4096])\n", N_);                                                \
+            abort();                                                                             \
+    }
+
+template <typename K>
+static void allow_smem(K kernel, size_t bytes)
+{
+    if (bytes > 48 * 1024)
+        FDES_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)bytes));
+}
+
+__device__ __forceinline__ bool in_band(int kx, int lo_end, int hi_start)
+{
+    return kx < lo_end || kx >= hi_start;
+}
+// band column tiles are numbered contiguously: [0, lo_end) then [hi_start, N)
+__device__ __forceinline__ int band_col0(int tile_col, int lo_end, int hi_start)
+{
+    return tile_col < lo_end ? tile_col : hi_start + (tile_col - lo_end);
+}
+static int band_cols(const SweepGeom& g)
+{
+    return g.lo_end >= g.hi_start ? g.N : g.lo_end + (g.N - g.hi_start);
+}
+
+// f0 * f1 in the reference's 3-multiply form (multiplyElementwise, src/complexMath.cu:44-62)
+__device__ __forceinline__ cpx mul3(cpx f0, cpx f1)
+{
+    const float a = f0.x, b = f0.y, c = f1.x, d = f1.y;
+    const float k = a * (c + d);
+    const float dd = d * (a + b);
+    const float cc = c * (b - a);
+    return make_float2(k - dd, k + cc);
+}
+
+// =============================================================================================
+// S1  density rows
+// =============================================================================================
+template <int N>
+__global__ void __launch_bounds__(RowCfg<N>::THREADS)
+k_density_rows(cpx* __restrict__ A, const int* __restrict__ rowptr, const int* __restrict__ rec_col,
+               const float* __restrict__ rec_w, int slice, int nZ, size_t rec_stride,
+               size_t rp_stride, float imPot, const cpx* __restrict__ tw)
+{
+    using C = RowCfg<N>;
+    extern __shared__ cpx smem[];
+    const int line = threadIdx.x / C::T, theta = threadIdx.x % C::T;
+    const int z = blockIdx.y, b = blockIdx.z;
+    const int row = blockIdx.x * C::RPB + line;
+    const int* rp = rowptr + (size_t)b * rp_stride + (size_t)(slice * nZ + z) * N;
+    const int lo = rp[row], hi = rp[row + 1];
+    // rows without deposits are never read by S2 (it consults the same row pointers)
+    if (!__syncthreads_or(hi > lo)) return;
+    float* dens = reinterpret_cast<float*>(smem + C::RPB * C::LSTRIDE) + line * N;
+#pragma unroll
+    for (int m = 0; m < FFT_E; m++) dens[theta + m * C::T] = 0.f;
+    __syncthreads();
+    if (theta == 0) {
+        // sorted, stable order -> the summation order is fixed (deterministic, unlike the
+        // float atomicAdd of squareAtoms_d, src/crystalMaker.cu:100-119)
+        const int* cc = rec_col + (size_t)b * rec_stride;
+        const float* ww = rec_w + (size_t)b * rec_stride;
+        for (int i = lo; i < hi; i++) dens[cc[i]] += ww[i];
+    }
+    __syncthreads();
+    cpx x[FFT_E];
+#pragma unroll
+    for (int m = 0; m < FFT_E; m++) {
+        const float d = dens[theta + m * C::T];
+        x[m] = make_float2(d, d * imPot);
+    }
+    fft_line<N, -1>(x, smem + line * C::LSTRIDE, theta, tw);
+    cpx* out = A + ((size_t)(b * nZ + z) * N + row) * N;
+#pragma unroll
+    for (int m = 0; m < FFT_E; m++) out[theta + m * C::T] = x[m];
+}
+
+void launch_density_rows(const SweepGeom& g, cpx* A, const int* rowptr, const int* rec_col,
+                         const float* rec_w, int slice, int nZ, int batch, size_t rec_stride,
+                         size_t rowptr_stride, float imPot, cudaStream_t st)
+{
+    FDES_DISPATCH_N(g.N, {
+        using C = RowCfg<NN>;
+        const size_t smem = C::SMEM + (size_t)C::RPB * NN * sizeof(float);
+        static bool once = false;
+        if (!once) { allow_smem(k_density_rows<NN>, smem); once = true; }
+        dim3 grid(NN / C::RPB, nZ, batch);
+        k_density_rows<NN><<<grid, C::THREADS, smem, st>>>(A, rowptr, rec_col, rec_w, slice, nZ,
+                                                          rec_stride, rowptr_stride, imPot, g.tw);
+    });
+}
+
+// =============================================================================================
+// S2  potential columns
+// =============================================================================================
+template <int N>
+__global__ void __launch_bounds__(ColCfg<N, true>::THREADS)
+k_potential_cols(cpx* __restrict__ B, const cpx* __restrict__ A, const float* __restrict__ Gq,
+                 const int* __restrict__ rowptr, int slice, int nZ, size_t rp_stride,
+                 const cpx* __restrict__ tw)
+{
+    using C = ColCfg<N, true>;
+    extern __shared__ cpx smem[];
+    constexpr int Q = N / 2 + 1;
+    const int c = threadIdx.x % C::CW, theta = threadIdx.x / C::CW;
+    const int kx = blockIdx.x * C::CW + c, b = blockIdx.y;
+    const int ax = min(kx, N - kx);
+    cpx* sm = smem + c * C::LSTRIDE;
+    cpx acc[FFT_E];
+#pragma unroll
+    for (int m = 0; m < FFT_E; m++) acc[m] = make_float2(0.f, 0.f);
+    bool any = false;
+    for (int z = 0; z < nZ; z++) {
+        const int* rp = rowptr + (size_t)b * rp_stride + (size_t)(slice * nZ + z) * N;
+        if (rp[N] == rp[0]) continue;  // species absent from this slice (CTA-uniform)
+        any = true;
+        const cpx* Az = A + (size_t)(b * nZ + z) * N * N + kx;
+        cpx x[FFT_E];
+#pragma unroll
+        for (int m = 0; m < FFT_E; m++) {
+            const int y = theta + m * C::T;
+            x[m] = (rp[y + 1] > rp[y]) ? Az[(size_t)y * N] : make_float2(0.f, 0.f);
+        }
+        fft_line<N, -1>(x, sm, theta, tw);
+        const float* G = Gq + (size_t)z * Q * Q + ax;
+#pragma unroll
+        for (int m = 0; m < FFT_E; m++) {
+            const int ky = theta + m * C::T;
+            const float gz = __ldg(G + min(ky, N - ky) * Q);
+            acc[m].x += x[m].x * gz;
+            acc[m].y += x[m].y * gz;
+        }
+    }
+    if (any) fft_line<N, 1>(acc, sm, theta, tw);
+    cpx* out = B + (size_t)b * N * N + kx;
+#pragma unroll
+    for (int m = 0; m < FFT_E; m++) out[(size_t)(theta + m * C::T) * N] = acc[m];
+}
+
+void launch_potential_cols(const SweepGeom& g, cpx* B, const cpx* A, const float* Gq,
+                           const int* rowptr, int slice, int nZ, int batch, size_t rowptr_stride,
+                           cudaStream_t st)
+{
+    FDES_DISPATCH_N(g.N, {
+        using C = ColCfg<NN, true>;
+        static bool once = false;
+        if (!once) { allow_smem(k_potential_cols<NN>, C::SMEM); once = true; }
+        dim3 grid(NN / C::CW, batch);
+        k_potential_cols<NN><<<grid, C::THREADS, C::SMEM, st>>>(B, A, Gq, rowptr, slice, nZ,
+                                                               rowptr_stride, g.tw);
+    });
+}
+
+// =============================================================================================
+// S3  transmission rows
+// =============================================================================================
+template <int N>
+__global__ void __launch_bounds__(RowCfg<N>::THREADS)
+k_transmit_rows(cpx* __restrict__ W, cpx* __restrict__ Vout, int lo_end, int hi_start,
+                const cpx* __restrict__ tw)
+{
+    using C = RowCfg<N>;
+    extern __shared__ cpx smem[];
+    const int line = threadIdx.x / C::T, theta = threadIdx.x % C::T;
+    const size_t rowoff = ((size_t)blockIdx.y * N + blockIdx.x * C::RPB + line) * N;
+    cpx* sm = smem + line * C::LSTRIDE;
+    cpx x[FFT_E];
+#pragma unroll
+    for (int m = 0; m < FFT_E; m++) x[m] = W[rowoff + theta + m * C::T];
+    fft_line<N, 1>(x, sm, theta, tw);
+    if (Vout) {
+#pragma unroll
+        for (int m = 0; m < FFT_E; m++) Vout[rowoff + theta + m * C::T] = x[m];
+    }
+    // potential2Transmission, src/multisliceSimulation.cu:41-52
+#pragma unroll
+    for (int m = 0; m < FFT_E; m++) {
+        const float Vx = x[m].x, Vy = x[m].y;
+        const float e = expf(-Vy);
+        x[m] = make_float2(e * cosf(Vx), e * sinf(Vx));
+    }
+    fft_line<N, -1>(x, sm, theta, tw);
+#pragma unroll
+    for (int m = 0; m < FFT_E; m++) {
+        const int kx = theta + m * C::T;
+        if (in_band(kx, lo_end, hi_start)) W[rowoff + kx] = x[m];
+    }
+}
+
+void launch_transmit_rows(const SweepGeom& g, cpx* W, cpx* Vout, int batch, cudaStream_t st)
+{
+    FDES_DISPATCH_N(g.N, {
+        using C = RowCfg<NN>;
+        static bool once = false;
+        if (!once) { allow_smem(k_transmit_rows<NN>, C::SMEM); once = true; }
+        dim3 grid(NN / C::RPB, batch);
+        k_transmit_rows<NN><<<grid, C::THREADS, C::SMEM, st>>>(W, Vout, g.lo_end, g.hi_start, g.tw);
+    });
+}
+
+// =============================================================================================
+// S4  band-limit columns
+// =============================================================================================
+template <int N>
+__global__ void __launch_bounds__(ColCfg<N, false>::THREADS)
+k_bandlimit_cols(cpx* __restrict__ W, int lo_end, int hi_start, const cpx* __restrict__ tw)
+{
+    using C = ColCfg<N, false>;
+    extern __shared__ cpx smem[];
+    const int c = threadIdx.x % C::CW, theta = threadIdx.x / C::CW;
+    const int kx = band_col0(blockIdx.x * C::CW, lo_end, hi_start) + c;
+    cpx* sm = smem + c * C::LSTRIDE;
+    cpx* col = W + (size_t)blockIdx.y * N * N + kx;
+    cpx x[FFT_E];
+#pragma unroll
+    for (int m = 0; m < FFT_E; m++) x[m] = col[(size_t)(theta + m * C::T) * N];
+    fft_line<N, -1>(x, sm, theta, tw);
+    // zeroHighFreq (src/multisliceSimulation.cu:225-250) and the 1/N of bandwidthLimit (:558-559)
+    const int i1 = kx > N / 2 ? kx - N : kx;
+    const float mind = (float)N;
+    const float alpha = 1.f / ((float)(N * N));
+#pragma unroll
+    for (int m = 0; m < FFT_E; m++) {
+        const int ky = theta + m * C::T;
+        const int i2 = ky > N / 2 ? ky - N : ky;
+        const bool cut = ((float)(i1 * i1 + i2 * i2) * 9.f / (mind * mind)) > 1.f;
+        x[m] = cut ? make_float2(0.f, 0.f) : make_float2(x[m].x * alpha, x[m].y * alpha);
+    }
+    fft_line<N, 1>(x, sm, theta, tw);
+#pragma unroll
+    for (int m = 0; m < FFT_E; m++) col[(size_t)(theta + m * C::T) * N] = x[m];
+}
+
+void launch_bandlimit_cols(const SweepGeom& g, cpx* W, int batch, cudaStream_t st)
+{
+    FDES_DISPATCH_N(g.N, {
+        using C = ColCfg<NN, false>;
+        static bool once = false;
+        if (!once) { allow_smem(k_bandlimit_cols<NN>, C::SMEM); once = true; }
+        dim3 grid(band_cols(g) / C::CW, batch);
+        k_bandlimit_cols<NN><<<grid, C::THREADS, C::SMEM, st>>>(W, g.lo_end, g.hi_start, g.tw);
+    });
+}
+
+// =============================================================================================
+// S5  multiply rows
+// =============================================================================================
+template <int N>
+__global__ void __launch_bounds__(RowCfg<N>::THREADS)
+k_multiply_rows(cpx* __restrict__ Psi, const cpx* __restrict__ E, size_t e_batch_stride,
+                int lo_end, int hi_start, int psi_full, const cpx* __restrict__ tw)
+{
+    using C = RowCfg<N>;
+    extern __shared__ cpx smem[];
+    const int line = threadIdx.x / C::T, theta = threadIdx.x % C::T;
+    const size_t row = (size_t)blockIdx.x * C::RPB + line;
+    const cpx* e = E + (size_t)blockIdx.y * e_batch_stride + row * N;
+    cpx* p = Psi + ((size_t)blockIdx.y * N + row) * N;
+    cpx* sm = smem + line * C::LSTRIDE;
+    cpx t[FFT_E], x[FFT_E];
+#pragma unroll
+    for (int m = 0; m < FFT_E; m++) {
+        const int kx = theta + m * C::T;
+        const bool ib = in_band(kx, lo_end, hi_start);
+        t[m] = ib ? e[kx] : make_float2(0.f, 0.f);
+        x[m] = (ib || psi_full) ? p[kx] : make_float2(0.f, 0.f);
+    }
+    fft_line<N, 1>(t, sm, theta, tw);
+    fft_line<N, 1>(x, sm, theta, tw);
+#pragma unroll
+    for (int m = 0; m < FFT_E; m++) x[m] = mul3(t[m], x[m]);
+    fft_line<N, -1>(x, sm, theta, tw);
+#pragma unroll
+    for (int m = 0; m < FFT_E; m++) {
+        const int kx = theta + m * C::T;
+        if (in_band(kx, lo_end, hi_start)) p[kx] = x[m];
+    }
+}
+
+void launch_multiply_rows(const SweepGeom& g, cpx* Psi, const cpx* E, size_t e_batch_stride,
+                          int batch, bool psi_full, cudaStream_t st)
+{
+    FDES_DISPATCH_N(g.N, {
+        using C = RowCfg<NN>;
+        static bool once = false;
+        if (!once) { allow_smem(k_multiply_rows<NN>, C::SMEM); once = true; }
+        dim3 grid(NN / C::RPB, batch);
+        k_multiply_rows<NN><<<grid, C::THREADS, C::SMEM, st>>>(Psi, E, e_batch_stride, g.lo_end,
+                                                              g.hi_start, psi_full ? 1 : 0, g.tw);
+    });
+}
+
+// =============================================================================================
+// S6  propagate columns
+// =============================================================================================
+template <int N>
+__global__ void __launch_bounds__(ColCfg<N, false>::THREADS)
+k_propagate_cols(cpx* __restrict__ Psi, const cpx* __restrict__ Pq, int lo_end, int hi_start,
+                 const cpx* __restrict__ tw)
+{
+    using C = ColCfg<N, false>;
+    extern __shared__ cpx smem[];
+    constexpr int Q = N / 2 + 1;
+    const int c = threadIdx.x % C::CW, theta = threadIdx.x / C::CW;
+    const int kx = band_col0(blockIdx.x * C::CW, lo_end, hi_start) + c;
+    cpx* sm = smem + c * C::LSTRIDE;
+    cpx* col = Psi + (size_t)blockIdx.y * N * N + kx;
+    cpx x[FFT_E];
+#pragma unroll
+    for (int m = 0; m < FFT_E; m++) x[m] = col[(size_t)(theta + m * C::T) * N];
+    fft_line<N, -1>(x, sm, theta, tw);
+    const cpx* P = Pq + min(kx, N - kx);
+#pragma unroll
+    for (int m = 0; m < FFT_E; m++) {
+        const int ky = theta + m * C::T;
+        x[m] = mul3(x[m], __ldg(P + min(ky, N - ky) * Q));
+    }
+    fft_line<N, 1>(x, sm, theta, tw);
+#pragma unroll
+    for (int m = 0; m < FFT_E; m++) col[(size_t)(theta + m * C::T) * N] = x[m];
+}
+
+void launch_propagate_cols(const SweepGeom& g, cpx* Psi, const cpx* Pq, int batch, cudaStream_t st)
+{
+    FDES_DISPATCH_N(g.N, {
+        using C = ColCfg<NN, false>;
+        static bool once = false;
+        if (!once) { allow_smem(k_propagate_cols<NN>, C::SMEM); once = true; }
+        dim3 grid(band_cols(g) / C::CW, batch);
+        k_propagate_cols<NN><<<grid, C::THREADS, C::SMEM, st>>>(Psi, Pq, g.lo_end, g.hi_start, g.tw);
+    });
+}
+
+// =============================================================================================
+// generic row sweep
+// =============================================================================================
+template <int N, int DIR, int EPI>
+__global__ void __launch_bounds__(RowCfg<N>::THREADS)
+k_rows_fft(const void* __restrict__ in_, void* __restrict__ out_, RowOpts o, int lo_end,
+           int hi_start, const cpx* __restrict__ tw)
+{
+    using C = RowCfg<N>;
+    extern __shared__ cpx smem[];
+    const int line = threadIdx.x / C::T, theta = threadIdx.x % C::T;
+    const int y = blockIdx.x * C::RPB + line;
+    const size_t rowoff = ((size_t)blockIdx.y * N + y) * N;
+    cpx x[FFT_E];
+#pragma unroll
+    for (int m = 0; m < FFT_E; m++) {
+        const int kx = theta + m * C::T;
+        if (o.in_is_real)
+            x[m] = make_float2(static_cast<const float*>(in_)[rowoff + kx], 0.f);
+        else if (!o.band_only_in || in_band(kx, lo_end, hi_start))
+            x[m] = static_cast<const cpx*>(in_)[rowoff + kx];
+        else
+            x[m] = make_float2(0.f, 0.f);
+    }
+    fft_line<N, DIR>(x, smem + line * C::LSTRIDE, theta, tw);
+#pragma unroll
+    for (int m = 0; m < FFT_E; m++) {
+        const int xx = theta + m * C::T;
+        const cpx v = make_float2(x[m].x * o.scale, x[m].y * o.scale);
+        if (EPI == ROW_STORE) {
+            static_cast<cpx*>(out_)[rowoff + xx] =
+                (o.band_only_out && !in_band(xx, lo_end, hi_start)) ? make_float2(0.f, 0.f) : v;
+        } else if (EPI == ROW_ACCUM) {
+            cpx* q = static_cast<cpx*>(out_) + rowoff + xx;
+            const cpx old = *q;
+            *q = make_float2(old.x + v.x, old.y + v.y);
+        } else if (EPI == ROW_INTENS_ACCUM) {
+            float* q = static_cast<float*>(out_) + rowoff + xx;
+            *q += o.scale * (x[m].x * x[m].x + x[m].y * x[m].y);
+        } else if (EPI == ROW_STORE_SHIFT) {
+            const int ys = (y + N / 2) & (N - 1), xs = (xx + N / 2) & (N - 1);
+            static_cast<cpx*>(out_)[((size_t)blockIdx.y * N + ys) * N + xs] = v;
+        } else {  // ROW_CROP_REAL
+            const int cx = xx - o.dn1, cy = y - o.dn2;
+            if (cx >= 0 && cx < o.n1 && cy >= 0 && cy < o.n2)
+                static_cast<float*>(out_)[((size_t)blockIdx.y * o.n2 + cy) * o.n1 + cx] = v.x;
+        }
+    }
+}
+
+template <int N, int DIR>
+static void rows_fft_epi(const SweepGeom& g, const void* in, void* out, RowEpilogue epi,
+                         const RowOpts& o, int batch, cudaStream_t st)
+{
+    using C = RowCfg<N>;
+    dim3 grid(N / C::RPB, batch);
+#define FDES_ROWS_CASE(EPI_)                                                                     \
+    case EPI_: {                                                                                 \
+        static bool once = false;                                                                \
+        if (!once) { allow_smem(k_rows_fft<N, DIR, EPI_>, C::SMEM); once = true; }               \
+        k_rows_fft<N, DIR, EPI_><<<grid, C::THREADS, C::SMEM, st>>>(in, out, o, g.lo_end,        \
+                                                                   g.hi_start, g.tw);            \
+    } break;
+    switch (epi) {
+        FDES_ROWS_CASE(ROW_STORE)
+        FDES_ROWS_CASE(ROW_ACCUM)
+        FDES_ROWS_CASE(ROW_INTENS_ACCUM)
+        FDES_ROWS_CASE(ROW_STORE_SHIFT)
+        FDES_ROWS_CASE(ROW_CROP_REAL)
+    }
+#undef FDES_ROWS_CASE
+}
+
+void launch_rows_fft(const SweepGeom& g, const void* in, void* out, int dir, RowEpilogue epi,
+                     const RowOpts& o, int batch, cudaStream_t st)
+{
+    FDES_DISPATCH_N(g.N, {
+        if (dir < 0) rows_fft_epi<NN, -1>(g, in, out, epi, o, batch, st);
+        else rows_fft_epi<NN, 1>(g, in, out, epi, o, batch, st);
+    });
+}
+
+// =============================================================================================
+// generic column sweep
+// =============================================================================================
+template <int N, int DIR, int OP>
+__global__ void __launch_bounds__(ColCfg<N, false>::THREADS)
+k_cols_fft(const cpx* __restrict__ in, void* __restrict__ out_, const void* __restrict__ table,
+           float scale, const cpx* __restrict__ tw)
+{
+    using C = ColCfg<N, false>;
+    extern __shared__ cpx smem[];
+    const int c = threadIdx.x % C::CW, theta = threadIdx.x / C::CW;
+    const int kx = blockIdx.x * C::CW + c;
+    cpx* sm = smem + c * C::LSTRIDE;
+    const size_t boff = (size_t)blockIdx.y * N * N;
+    cpx x[FFT_E];
+#pragma unroll
+    for (int m = 0; m < FFT_E; m++) x[m] = in[boff + (size_t)(theta + m * C::T) * N + kx];
+    if (OP == COL_PLAIN) {
+        fft_line<N, DIR>(x, sm, theta, tw);
+        cpx* out = static_cast<cpx*>(out_);
+#pragma unroll
+        for (int m = 0; m < FFT_E; m++)
+            out[boff + (size_t)(theta + m * C::T) * N + kx] = make_float2(x[m].x * scale, x[m].y * scale);
+        return;
+    }
+    fft_line<N, -1>(x, sm, theta, tw);
+    if (OP == COL_DP_ACCUM) {
+        // |fftshift(FFT psi)|^2 / N accumulated with weight (diffractionPattern,
+        // src/crystalMaker.cu:714-717; cufftShift2D_h, src/complexMath.cu:510-557)
+        float* out = static_cast<float*>(out_);
+        const int xs = (kx + N / 2) & (N - 1);
+#pragma unroll
+        for (int m = 0; m < FFT_E; m++) {
+            const int ys = (theta + m * C::T + N / 2) & (N - 1);
+            out[boff + (size_t)ys * N + xs] += scale * (x[m].x * x[m].x + x[m].y * x[m].y);
+        }
+        return;
+    }
+#pragma unroll
+    for (int m = 0; m < FFT_E; m++) {
+        const size_t idx = (size_t)(theta + m * C::T) * N + kx;
+        if (OP == COL_MUL_CPX_INV) {
+            // psi * CTF as in multiplyLensFunction (src/multisliceSimulation.cu:339-340)
+            const cpx w = __ldg(static_cast<const cpx*>(table) + idx);
+            x[m] = make_float2(w.x * x[m].x - w.y * x[m].y, w.x * x[m].y + w.y * x[m].x);
+        } else {
+            const float w = __ldg(static_cast<const float*>(table) + idx);
+            x[m] = make_float2(x[m].x * w, x[m].y * w);
+        }
+    }
+    fft_line<N, 1>(x, sm, theta, tw);
+    cpx* out = static_cast<cpx*>(out_);
+#pragma unroll
+    for (int m = 0; m < FFT_E; m++)
+        out[boff + (size_t)(theta + m * C::T) * N + kx] = make_float2(x[m].x * scale, x[m].y * scale);
+}
+
+template <int N, int DIR, int OP>
+static void cols_fft_one(const SweepGeom& g, const cpx* in, void* out, const void* table,
+                         float scale, int batch, cudaStream_t st)
+{
+    using C = ColCfg<N, false>;
+    static bool once = false;
+    if (!once) { allow_smem(k_cols_fft<N, DIR, OP>, C::SMEM); once = true; }
+    dim3 grid(N / C::CW, batch);
+    k_cols_fft<N, DIR, OP><<<grid, C::THREADS, C::SMEM, st>>>(in, out, table, scale, g.tw);
+}
+
+void launch_cols_fft(const SweepGeom& g, const cpx* in, void* out, int dir, ColOp op,
+                     const void* table, float scale, int batch, cudaStream_t st)
+{
+    FDES_DISPATCH_N(g.N, {
+        switch (op) {
+            case COL_PLAIN:
+                if (dir < 0) cols_fft_one<NN, -1, COL_PLAIN>(g, in, out, table, scale, batch, st);
+                else cols_fft_one<NN, 1, COL_PLAIN>(g, in, out, table, scale, batch, st);
+                break;
+            case COL_MUL_CPX_INV: cols_fft_one<NN, -1, COL_MUL_CPX_INV>(g, in, out, table, scale, batch, st); break;
+            case COL_MUL_REAL_INV: cols_fft_one<NN, -1, COL_MUL_REAL_INV>(g, in, out, table, scale, batch, st); break;
+            case COL_DP_ACCUM: cols_fft_one<NN, -1, COL_DP_ACCUM>(g, in, out, table, scale, batch, st); break;
+        }
+    });
+}
+
+}  // namespace fdes

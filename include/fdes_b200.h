@@ -1,0 +1,107 @@
+/* fdes_b200 -- C ABI of the B200-native FDES forward-multislice library (libfdes_b200.so).
+ *
+ * Plain C: pointers and sizes only, no C++ or torch types.  Two layers:
+ *
+ *  (1) The drop-in symbol.  `FDES` has the exact signature the reference exports from
+ *      libFDES_SHARED_LIB.so (reference src/FDESExport.cu:59-60) and that
+ *      Python/pyFDES.py:33-41 binds through ctypes, so `ctypes.CDLL("libfdes_b200.so").FDES`
+ *      (or a symlink named libFDES_SHARED_LIB.so) replaces it without touching the caller.
+ *
+ *  (2) A session API over the same engine.  It exposes the seam the reference keeps internal
+ *      (buildMeasurements, include/crystalMaker.h:77) so a host framework can shard frozen-phonon
+ *      configurations over several GPUs (one process per GPU) and reduce the partial intensity /
+ *      exit-wave sums itself (e.g. torch.distributed all_reduce over NCCL), plus the building
+ *      blocks the parity tests compare against the oracle.
+ *
+ * All functions returning int return 0 on success and -1 on failure; the message is available
+ * from fdes_b200_last_error().  There is no CPU fallback: without a CUDA device every entry point
+ * that computes fails.
+ */
+#ifndef FDES_B200_H
+#define FDES_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- (1) drop-in for the reference export ------------------------------------------------
+ * Replaces: extern "C" void FDES(...)                     reference src/FDESExport.cu:59-178
+ *   gpu_Index      CUDA device ordinal                    (:68, :106)
+ *   print_Level    0 images | 1 + potential | 2 + exit waves (:69)
+ *   input_name     parameter file; ".cnf" (".qsc"/".emd" are rejected with a message, see
+ *                  INTEGRATION.md)                         (:73-102)
+ *   image_name     raw float32 output file [n3][n2][n1]    (src/crystalMaker.cu:399)
+ *   emd_save_name  results file (see INTEGRATION.md for the layout written)
+ *   atomsArray     host float32 [numAtoms][6] = Z, x, y, z [m], DWF [m^2], occupancy
+ *                                                          (src/paramStructure.cu:316-324)
+ *   dstImage       host float32 [n3][n2][n1], caller-allocated (:162, src/paramStructure.cu:347-359)
+ * Like the reference it returns void and terminates the process (exit) on unusable input. */
+void FDES(int gpu_Index, int print_Level, char* input_name, char* image_name, char* emd_save_name,
+          float* atomsArray, int numAtoms, float* dstImage);
+
+/* ---- (2) session API ---------------------------------------------------------------------- */
+typedef struct fdes_b200_sim fdes_b200_sim;
+
+const char* fdes_b200_last_error(void);
+int fdes_b200_version(void);
+
+/* Open a simulation from a .cnf file (reader: getParams, reference src/paramStructure.cu:588-635).
+ * atoms6 == NULL: atoms come from the file's `atom:` lines; otherwise [numAtoms][6] like FDES().
+ * batch: phonon configurations advanced together (0 = automatic).
+ * rank/world: this process handles configurations [count*rank/world, count*(rank+1)/world).
+ * want_exitwave: keep the coherent exit-wave average (reference print_level 2). */
+fdes_b200_sim* fdes_b200_open_cnf(const char* cnf_path, const float* atoms6, int numAtoms,
+                                  int gpu_index, int batch, int rank, int world, int want_exitwave);
+void fdes_b200_close(fdes_b200_sim* sim);
+
+/* dims[10] = n1 n2 n3 m1 m2 m3(after sub-slicing) nAt nZ phonon_configs batch */
+int fdes_b200_get_dims(const fdes_b200_sim* sim, int* dims);
+/* scalars[8] = lambda sigma gamma d1 d2 d3(after sub-slicing) E0 imPot */
+int fdes_b200_get_scalars(const fdes_b200_sim* sim, float* scalars);
+
+/* Device accumulators for the partial sums of this rank (float32 on the sim's device):
+ * intensity_dev [m2*m1], exitwave_dev [m2*m1*2] (may be NULL).  NULL restores the internal ones. */
+int fdes_b200_set_accumulators(fdes_b200_sim* sim, float* intensity_dev, float* exitwave_dev);
+/* All phonon configurations of this rank for measurement k (loop body of
+ * src/crystalMaker.cu:324-367): accumulators <- sum_j (.)/count. */
+int fdes_b200_run_k(fdes_b200_sim* sim, int k);
+/* Detector tail on the (reduced) accumulators (addNoiseAndMtf, src/crystalMaker.cu:579-613):
+ * image_host [n2*n1]; exitwave_host [m2*m1*2] or NULL. */
+int fdes_b200_finish_k(fdes_b200_sim* sim, int k, float* image_host, float* exitwave_host);
+/* Whole single-GPU run: image_host [n3][n2][n1], exitwave_host [n3][m2][m1][2] or NULL.
+ * Host buffers in, host buffers out (this is what FDES() calls). */
+int fdes_b200_simulate(fdes_b200_sim* sim, float* image_host, float* exitwave_host);
+/* Untilted phonon-free potential slices, original slicing: out_host [m3_orig][m2][m1][2]
+ * (src/crystalMaker.cu:381-397).  m3_orig is returned by fdes_b200_potential_slices_count. */
+int fdes_b200_potential_slices_count(const fdes_b200_sim* sim);
+int fdes_b200_potential(fdes_b200_sim* sim, float* out_host);
+
+/* ---- building blocks (parity tests, benchmarks) ------------------------------------------- */
+/* next frozen-phonon coordinates for measurement k -> xyz_host [nAt][3]
+ * (atomJitter_d, src/crystalMaker.cu:37-48; advances the XORWOW streams) */
+int fdes_b200_jitter_next(fdes_b200_sim* sim, int k, float* xyz_host);
+/* integer bin tuples (i1, i2, i3, species index) per atom, -1 when the atom is rejected
+ * (squareAtoms_d index arithmetic, src/crystalMaker.cu:85-92): bins_host [nAt][4] */
+int fdes_b200_bin_atoms(fdes_b200_sim* sim, const float* xyz_host, int* bins_host);
+/* phase grating of one slice (phaseGrating, src/crystalMaker.cu:507-536): V_host [m2*m1*2] */
+int fdes_b200_phase_grating(fdes_b200_sim* sim, const float* xyz_host, int slice, float* V_host);
+/* exit wave of one configuration with given coordinates (incomingWave + m3 x
+ * (phaseGrating + forwardPropagation)): psi_host [m2*m1*2] */
+int fdes_b200_exit_wave(fdes_b200_sim* sim, const float* xyz_host, int k, float* psi_host);
+/* Throughput loop: `configs` configurations with everything resident in HBM; returns the
+ * CUDA-event milliseconds of the loop (negative on failure). */
+double fdes_b200_bench_configs(fdes_b200_sim* sim, int k, int configs);
+/* counters[4] = slices executed, kernels launched, 0, 0 (since open or last reset) */
+int fdes_b200_get_counters(fdes_b200_sim* sim, long long* counters, int reset);
+/* 2-D complex64 FFT of a host array [N][N] in place with the library's own sweeps
+ * (dir -1 forward, +1 unnormalised inverse) -- replaces cufftExecC2C for the tests. */
+int fdes_b200_fft2d(float* data_host, int N, int dir, int gpu_index);
+/* stable radix sort + row pointers on host arrays (test hook for the binning pipeline):
+ * keys [n] (values < nkeys are valid), cols [n], w [n] sorted in place; rowptr [nkeys+1]. */
+int fdes_b200_sort_records(unsigned int* keys, int* cols, float* w, int n, int nkeys, int* rowptr,
+                           int gpu_index);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDES_B200_H */
