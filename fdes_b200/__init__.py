@@ -41,6 +41,7 @@ def load_library() -> ctypes.CDLL:
     lib.fdes_b200_open_cnf.restype = vp
     lib.fdes_b200_open_cnf.argtypes = [ctypes.c_char_p, c_f, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.fdes_b200_parse_cnf.argtypes = [ctypes.c_char_p, c_i, c_f, c_f, c_f, ctypes.c_int]
     lib.fdes_b200_close.argtypes = [vp]
     lib.fdes_b200_close.restype = None
     lib.fdes_b200_get_dims.argtypes = [vp, c_i]
@@ -57,6 +58,7 @@ def load_library() -> ctypes.CDLL:
     lib.fdes_b200_exit_wave.argtypes = [vp, c_f, ctypes.c_int, c_f]
     lib.fdes_b200_bench_configs.argtypes = [vp, ctypes.c_int, ctypes.c_int]
     lib.fdes_b200_bench_configs.restype = ctypes.c_double
+    lib.fdes_b200_time_sweeps.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f]
     lib.fdes_b200_get_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
     lib.fdes_b200_fft2d.argtypes = [c_f, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     lib.fdes_b200_sort_records.argtypes = [ctypes.POINTER(ctypes.c_uint), c_i, c_f, ctypes.c_int, ctypes.c_int,
@@ -66,6 +68,14 @@ def load_library() -> ctypes.CDLL:
                          ctypes.c_int, c_f]
     _lib = lib
     return lib
+
+
+def declared_symbols():
+    """Names of every function include/fdes_b200.h declares (the drop-in boundary)."""
+    import re
+    text = (_PKG.parent / "include" / "fdes_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(FDES|fdes_b200_\w+)\s*\(", text)))
 
 
 def _fp(a: np.ndarray):
@@ -91,6 +101,27 @@ def cuda_FDES(gpu_Index, print_Level, input_name, image_name, emd_save_name, poi
                     pointerAtomsArray, int(numAtoms), pointerImagesArray)
 
 
+def parse_cnf(cnf_path):
+    """Host-only view of what the engine would run for a .cnf (no GPU needed): dict of dims,
+    scalars, per-measurement tilts/defoci and the atom table [nAt, 6]."""
+    lib = load_library()
+    d = np.zeros(10, np.int32)
+    s = np.zeros(8, np.float32)
+    n = lib.fdes_b200_parse_cnf(str(cnf_path).encode(), _ip(d), _fp(s), None, None, 0)
+    if n < 0:
+        raise FdesError(lib.fdes_b200_last_error().decode())
+    per_k = np.zeros((int(d[2]), 5), np.float32)
+    atoms = np.zeros((n, 6), np.float32)
+    lib.fdes_b200_parse_cnf(str(cnf_path).encode(), _ip(d), _fp(s), _fp(per_k), _fp(atoms), n)
+    keys_d = ["n1", "n2", "n3", "m1", "m2", "m3", "nAt", "nZ", "frPh", "mode"]
+    keys_s = ["lam", "sigma", "gamma", "d1", "d2", "d3", "E0", "imPot"]
+    out = {k: int(v) for k, v in zip(keys_d, d)}
+    out.update({k: np.float32(v) for k, v in zip(keys_s, s)})
+    out["tiltspec"], out["tiltbeam"], out["defoci"] = per_k[:, 0:2].copy(), per_k[:, 2:4].copy(), per_k[:, 4].copy()
+    out["atoms"] = atoms
+    return out
+
+
 class Simulation:
     """One .cnf simulation on one GPU (session API of include/fdes_b200.h)."""
 
@@ -109,7 +140,7 @@ class Simulation:
         self._h = h
         d = np.zeros(10, np.int32)
         self._ck(self._lib.fdes_b200_get_dims(h, _ip(d)))
-        (self.n1, self.n2, self.n3, self.m1, self.m2, self.m3, self.nAt, self.nZ, self.configs, _) = map(int, d)
+        (self.n1, self.n2, self.n3, self.m1, self.m2, self.m3, self.nAt, self.nZ, self.configs, self.batch) = map(int, d)
         s = np.zeros(8, np.float32)
         self._ck(self._lib.fdes_b200_get_scalars(h, _fp(s)))
         self.lam, self.sigma, self.gamma, self.d1, self.d2, self.d3, self.E0, self.imPot = map(float, s)
@@ -198,7 +229,13 @@ class Simulation:
     def counters(self, reset: bool = False):
         c = (ctypes.c_longlong * 4)()
         self._ck(self._lib.fdes_b200_get_counters(self._h, c, 1 if reset else 0))
-        return {"slices": int(c[0]), "launches": int(c[1])}
+        return {"slices": int(c[0]), "launches": int(c[1]), "band_columns": int(c[2])}
+
+    def time_sweeps(self, k: int = 0, batch: int = 0, reps: int = 20):
+        """Average launch duration [ms] of the six per-slice sweeps S1..S6."""
+        ms = np.zeros(6, np.float32)
+        self._ck(self._lib.fdes_b200_time_sweeps(self._h, k, batch or self.batch, reps, _fp(ms)))
+        return ms
 
 
 def fft2d(a: np.ndarray, direction: int = -1, gpu_index: int = 0) -> np.ndarray:

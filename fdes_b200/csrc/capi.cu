@@ -34,6 +34,39 @@ extern "C" {
 const char* fdes_b200_last_error(void) { return g_err.c_str(); }
 int fdes_b200_version(void) { return 100; }
 
+int fdes_b200_parse_cnf(const char* cnf_path, int* dims, float* scalars, float* per_k,
+                        float* atoms6_out, int max_atoms)
+{
+    API_TRY
+    if (!cnf_path) throw std::runtime_error("cnf_path is NULL");
+    Params p;
+    Atoms at;
+    if (!read_cnf(cnf_path, p, &at, false)) throw std::runtime_error(std::string("cannot read ") + cnf_path);
+    set_sub_slices(p, sub_slice_ratio(p.d3, p.subSlTh));
+    if (dims) {
+        dims[0] = p.n1; dims[1] = p.n2; dims[2] = p.n3; dims[3] = p.m1; dims[4] = p.m2; dims[5] = p.m3;
+        dims[6] = at.size(); dims[7] = (int)list_of_elements(at.Z).size(); dims[8] = p.frPh; dims[9] = p.mode;
+    }
+    if (scalars) {
+        scalars[0] = p.lambda; scalars[1] = p.sigma; scalars[2] = p.gamma; scalars[3] = p.d1;
+        scalars[4] = p.d2; scalars[5] = p.d3; scalars[6] = p.E0; scalars[7] = p.imPot;
+    }
+    if (per_k)
+        for (int k = 0; k < p.n3; k++) {
+            per_k[5 * k + 0] = p.tiltspec[2 * k]; per_k[5 * k + 1] = p.tiltspec[2 * k + 1];
+            per_k[5 * k + 2] = p.tiltbeam[2 * k]; per_k[5 * k + 3] = p.tiltbeam[2 * k + 1];
+            per_k[5 * k + 4] = p.defoci[k];
+        }
+    if (atoms6_out)
+        for (int i = 0; i < at.size() && i < max_atoms; i++) {
+            float* a = atoms6_out + 6 * (size_t)i;
+            a[0] = (float)at.Z[i]; a[1] = at.xyz[3 * i]; a[2] = at.xyz[3 * i + 1]; a[3] = at.xyz[3 * i + 2];
+            a[4] = at.dwf[i]; a[5] = at.occ[i];
+        }
+    return at.size();
+    API_CATCH(-1)
+}
+
 fdes_b200_sim* fdes_b200_open_cnf(const char* cnf_path, const float* atoms6, int numAtoms,
                                   int gpu_index, int batch, int rank, int world, int want_exitwave)
 {
@@ -64,7 +97,7 @@ int fdes_b200_get_dims(const fdes_b200_sim* sim, int* d)
     const Params& p = sim->eng->params();
     d[0] = p.n1; d[1] = p.n2; d[2] = p.n3; d[3] = p.m1; d[4] = p.m2; d[5] = p.m3;
     d[6] = sim->atoms.size(); d[7] = sim->eng->num_species(); d[8] = sim->eng->configs_total();
-    d[9] = 0;
+    d[9] = sim->eng->batch();
     return 0;
     API_CATCH(-1)
 }
@@ -167,11 +200,20 @@ double fdes_b200_bench_configs(fdes_b200_sim* sim, int k, int configs)
     API_CATCH(-1.0)
 }
 
+int fdes_b200_time_sweeps(fdes_b200_sim* sim, int k, int batch, int reps, float* ms6)
+{
+    API_TRY
+    if (reps < 1) throw std::runtime_error("reps must be >= 1");
+    sim->eng->time_sweeps(k, batch, reps, ms6);
+    return 0;
+    API_CATCH(-1)
+}
+
 int fdes_b200_get_counters(fdes_b200_sim* sim, long long* c, int reset)
 {
     API_TRY
     const EngineTimings& t = sim->eng->timings();
-    c[0] = t.slices_executed; c[1] = t.kernel_launches; c[2] = 0; c[3] = 0;
+    c[0] = t.slices_executed; c[1] = t.kernel_launches; c[2] = sim->eng->band_columns(); c[3] = 0;
     if (reset) sim->eng->reset_timings();
     return 0;
     API_CATCH(-1)

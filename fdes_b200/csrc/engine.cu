@@ -508,4 +508,40 @@ double Engine::bench_configs(int k, int configs)
     return (double)ms;
 }
 
+// Each of the six sweeps launched `reps` times back to back on the buffers of a prepared batch,
+// bracketed by CUDA events on the engine's stream: ms6[i] = average launch duration of S(i+1).
+void Engine::time_sweeps(int k, int nb, int reps, float* ms6)
+{
+    const size_t NN = (size_t)N_ * N_;
+    nb = std::max(1, std::min(nb, B_));
+    CK(cudaMemcpyAsync(xyzK_, xyzTO_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
+    make_incident(k);
+    for (int b = 0; b < nb; b++) {
+        float* fp = xyzFP_ + (size_t)b * 3 * nAt_;
+        CK(cudaMemcpyAsync(fp, xyzK_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
+        bin_and_sort(b, fp);
+        CK(cudaMemcpyAsync(Psi_ + (size_t)b * NN, psi_in_, NN * sizeof(cpx), cudaMemcpyDeviceToDevice, st_));
+    }
+    const int s = p_.m3 / 2;
+    for (int i = 0; i < 6; i++) {
+        for (int r = -1; r < reps; r++) {   // r = -1: untimed warm-up launch
+            if (r == 0) CK(cudaEventRecord(ev0_, st_));
+            switch (i) {
+                case 0: launch_density_rows(g_, A_, rowptr_, cols_, w_, s, nZ_, nb, rec_stride_, rp_stride_, p_.imPot, st_); break;
+                case 1: launch_potential_cols(g_, W_, A_, Gq_, rowptr_, s, nZ_, nb, rp_stride_, st_); break;
+                case 2: launch_transmit_rows(g_, W_, nullptr, nb, st_); break;
+                case 3: launch_bandlimit_cols(g_, W_, nb, st_); break;
+                case 4: launch_multiply_rows(g_, Psi_, W_, NN, nb, false, st_); break;
+                case 5: launch_propagate_cols(g_, Psi_, Pq_, nb, st_); break;
+            }
+        }
+        CK(cudaEventRecord(ev1_, st_));
+        CK(cudaEventSynchronize(ev1_));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+        ms6[i] = ms / (float)reps;
+        tm_.kernel_launches += reps + 1;
+    }
+}
+
 }  // namespace fdes

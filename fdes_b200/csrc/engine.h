@@ -68,6 +68,10 @@ public:
     // throughput loop used by bench.py: `configs` configurations (coordinates resident in HBM,
     // jitter applied if frPh > 0), returns CUDA-event milliseconds of the whole loop
     double bench_configs(int k, int configs);
+    // average launch duration [ms] of each of the six sweeps on a prepared batch of nb configs
+    void time_sweeps(int k, int nb, int reps, float* ms6);
+    int batch() const { return B_; }
+    int band_columns() const { return g_.lo_end >= g_.hi_start ? N_ : g_.lo_end + (N_ - g_.hi_start); }
 
     const EngineTimings& timings() const { return tm_; }
     void reset_timings() { tm_ = EngineTimings(); }

@@ -45,6 +45,15 @@ typedef struct fdes_b200_sim fdes_b200_sim;
 const char* fdes_b200_last_error(void);
 int fdes_b200_version(void);
 
+/* Host-only (no CUDA call): parse a .cnf exactly as fdes_b200_open_cnf does and report what the
+ * engine would run (readConfig + consitentParams, src/paramStructure.cu:42-302, 637-673; sub-slice
+ * logic src/crystalMaker.cu:720-743).  dims[10] = n1 n2 n3 m1 m2 m3(after sub-slicing) nAt nZ
+ * frozen_phonons mode; scalars[8] as fdes_b200_get_scalars; per_k [n3][5] = specimen_tilt x y,
+ * beam_tilt x y, defocus (may be NULL); atoms6_out [max_atoms][6] (may be NULL).
+ * Returns the number of atoms in the file, -1 on failure. */
+int fdes_b200_parse_cnf(const char* cnf_path, int* dims, float* scalars, float* per_k,
+                        float* atoms6_out, int max_atoms);
+
 /* Open a simulation from a .cnf file (reader: getParams, reference src/paramStructure.cu:588-635).
  * atoms6 == NULL: atoms come from the file's `atom:` lines; otherwise [numAtoms][6] like FDES().
  * batch: phonon configurations advanced together (0 = automatic).
@@ -91,7 +100,13 @@ int fdes_b200_exit_wave(fdes_b200_sim* sim, const float* xyz_host, int k, float*
 /* Throughput loop: `configs` configurations with everything resident in HBM; returns the
  * CUDA-event milliseconds of the loop (negative on failure). */
 double fdes_b200_bench_configs(fdes_b200_sim* sim, int k, int configs);
-/* counters[4] = slices executed, kernels launched, 0, 0 (since open or last reset) */
+/* Average launch duration [ms] of each of the six per-slice sweeps (S1 density rows, S2 potential
+ * columns, S3 transmission rows, S4 band-limit columns, S5 multiply rows, S6 propagate columns)
+ * over `reps` back-to-back launches on a prepared batch -- the live kernel times behind the
+ * roofline figures of bench.py. */
+int fdes_b200_time_sweeps(fdes_b200_sim* sim, int k, int batch, int reps, float* ms6);
+/* counters[4] = slices executed, kernels launched (since open or last reset), band columns
+ * (columns kept by the 2/3 limit, rounded to tiles), 0 */
 int fdes_b200_get_counters(fdes_b200_sim* sim, long long* counters, int reset);
 /* 2-D complex64 FFT of a host array [N][N] in place with the library's own sweeps
  * (dir -1 forward, +1 unnormalised inverse) -- replaces cufftExecC2C for the tests. */

@@ -246,18 +246,42 @@ def read_cnf(path: str, atoms_from_external: bool = False):
         if field.startswith("mode:"):
             seti("mode")
 
-    # atoms: numberOfAtoms/readCoordinates use a 200-byte fgets (src/paramStructure.cu:1019-1077)
+    # atoms: numberOfAtoms/readCoordinates use a 200-byte fgets (src/paramStructure.cu:1019-1077).
+    # The field name is only refreshed when sscanf("%s") converts and the loop runs until feof():
+    # a file ending in "atom: ...\n" therefore goes round once more with a failed fgets, the
+    # stale field name "atom:" and the stale line buffer ("#tom: ..." after resetLine, same
+    # numbers) -> the last atom is read twice.  A blank line after an atom line also re-dispatches
+    # "atom:" but converts nothing (the reference then keeps uninitialised memory; zeros here).
     Z, xyz, dwf, occ = [], [], [], []
     if not atoms_from_external:
-        for line in chunks(raw, 200):
-            toks = line.split()
-            if toks and toks[0].startswith("atom:"):
-                vals = toks[1:7]
-                Z.append(_sscanf_i(vals[0]))
-                nums = [_sscanf_g(v) for v in vals[1:6]]
+        alines = list(chunks(raw, 200))
+        if raw.endswith("\n"):
+            alines[-1] = None      # the failed fgets at end-of-file
+        else:
+            alines[-1] = alines[-1][:-1]
+        field, stale = "", ""
+        for line in alines:
+            if line is None:
+                line = stale
+            else:
+                toks = line.split()
+                if toks:
+                    field = toks[0]
+            if field.startswith("atom:"):
+                vals = line.split()[1:7]
+                zi = _sscanf_i(vals[0]) if vals else None
+                nums = [(_sscanf_g(v) if zi is not None else None) for v in vals[1:6]]
+                nums += [None] * (5 - len(nums))
+                for i in range(5):          # sscanf stops at the first failed conversion
+                    if nums[i] is None:
+                        nums[i:] = [None] * (5 - i)
+                        break
+                nums = [f32(0) if v is None else v for v in nums]
+                Z.append(zi if zi is not None else 0)
                 xyz.append(nums[0:3])
                 dwf.append(nums[3])
                 occ.append(nums[4])
+            stale = "#" + line[1:]
     p2 = p.copy()
     n3 = p2.n3
     p2.tiltspec, p2.tiltbeam, p2.defoci = p.tiltspec[: 2 * n3].copy(), p.tiltbeam[: 2 * n3].copy(), p.defoci[:n3].copy()

@@ -36,6 +36,14 @@
  *   ref_harness time  <input.{cnf,qsc}> <reps> <configs_per_rep>
  *       CUDA-event time of the slice loop (phaseGrating+forwardPropagation),
  *       prints one JSON line.
+ *   ref_harness e2e   <input.cnf> <reps> <warmup>
+ *       whole-call wall time of the reference's exported entry point, replayed
+ *       step by step as src/FDESExport.cu:59-178 does it (atoms handed over as a
+ *       host array, image copied back into a host buffer): getParams ->
+ *       readAtomsFromArray -> buildMeasurements -> image copy -> frees.  The
+ *       exported FDES() itself is not called because it copies the image out of
+ *       a buffer buildMeasurements has already freed (src/crystalMaker.cu:414 vs
+ *       src/FDESExport.cu:162).  Prints one JSON line.
  */
 #include <cstdio>
 #include <cstdlib>
@@ -43,6 +51,7 @@
 #include <string>
 #include <vector>
 #include <unistd.h>
+#include <time.h>
 #include <sys/stat.h>
 #include <cuda_runtime.h>
 #include <cufft.h>
@@ -75,6 +84,7 @@ float* potential = NULL;
 float* exitwave = NULL;
 
 static std::string g_outdir = ".";
+static float* g_e2e_dst = NULL;   /* e2e mode: host buffer that receives the image */
 
 static void dumpRaw(const std::string& name, const void* p, size_t bytes)
 {
@@ -102,6 +112,7 @@ void writeHdf5(const char*, float* img, float* pot, float* ew, params_t* params,
 {
     const size_t n123 = (size_t)params->IM.n1 * params->IM.n2 * params->IM.n3;
     const size_t m12 = (size_t)params->IM.m1 * params->IM.m2;
+    if (g_e2e_dst) { memcpy(g_e2e_dst, img, n123 * sizeof(float)); return; }
     dumpRaw("image.f32", img, n123 * sizeof(float));
     if (printLevel > 1 && ew)
         dumpRaw("exitwave.f32", ew, 2 * m12 * params->IM.n3 * sizeof(float));
@@ -274,6 +285,59 @@ static int modeTime(const std::string& in, int reps, int configs)
     return 0;
 }
 
+static int modeE2E(const std::string& in, int reps, int warm)
+{
+    /* atoms as a host [nAt][6] array, taken once from the file */
+    params_t* p0 = NULL; int* Z_d = NULL; float *xyz_d = NULL, *DWF_d = NULL, *occ_d = NULL;
+    confOption = 1;
+    if (!getParams(in.c_str(), &p0, &Z_d, &xyz_d, &DWF_d, &occ_d)) return 2;
+    const int nAt = p0->SAMPLE.nAt;
+    std::vector<int> Zh(nAt); std::vector<float> xyz(3 * (size_t)nAt), dwf(nAt), occ(nAt);
+    cudaMemcpy(Zh.data(), Z_d, nAt * sizeof(int), cudaMemcpyDeviceToHost);
+    cudaMemcpy(xyz.data(), xyz_d, 3 * (size_t)nAt * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaMemcpy(dwf.data(), DWF_d, nAt * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaMemcpy(occ.data(), occ_d, nAt * sizeof(float), cudaMemcpyDeviceToHost);
+    std::vector<float> a6(6 * (size_t)nAt);
+    for (int i = 0; i < nAt; i++) {
+        a6[6 * i] = (float)Zh[i]; a6[6 * i + 1] = xyz[3 * i]; a6[6 * i + 2] = xyz[3 * i + 1];
+        a6[6 * i + 3] = xyz[3 * i + 2]; a6[6 * i + 4] = dwf[i]; a6[6 * i + 5] = occ[i];
+    }
+    const int n123 = p0->IM.n1 * p0->IM.n2 * p0->IM.n3;
+    const int m1 = p0->IM.m1, m2 = p0->IM.m2, frPh = p0->IM.frPh;
+    std::vector<float> dst(n123);
+    cudaFree(Z_d); cudaFree(xyz_d); cudaFree(DWF_d); cudaFree(occ_d);
+    freeParams(&p0);
+    std::vector<double> ms;
+    int slices = 0;
+    for (int rep = 0; rep < reps + warm; rep++) {
+        cudaDeviceSynchronize();
+        timespec t0, t1;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        params_t* params = NULL; Z_d = NULL; xyz_d = DWF_d = occ_d = NULL;
+        atomsFromExternal = true;
+        printLevel = 0;
+        if (!getParams(in.c_str(), &params, &Z_d, &xyz_d, &DWF_d, &occ_d)) return 2;
+        readAtomsFromArray(params, &Z_d, &xyz_d, &DWF_d, &occ_d, a6.data(), nAt);
+        g_e2e_dst = dst.data();
+        buildMeasurements(params, Z_d, xyz_d, DWF_d, occ_d, (char*)"Measurements.bin", (char*)"results.emd");
+        slices = params->IM.m3;
+        freeParams(&params);
+        cudaFree(xyz_d); cudaFree(DWF_d); cudaFree(occ_d); cudaFree(Z_d);
+        cudaDeviceSynchronize();
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        if (rep >= warm) ms.push_back((t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6);
+    }
+    double sum = 0; for (double t : ms) sum += t;
+    const double mean_ms = sum / ms.size();
+    const int count = frPh > 0 ? frPh : 1;
+    const double pxsl = (double)m1 * m2 * slices * count;
+    double chk = 0; for (float v : dst) chk += v;
+    printf("{\"ref_e2e\": true, \"m1\": %d, \"m2\": %d, \"slices\": %d, \"configs\": %d, \"nAt\": %d, "
+           "\"reps\": %d, \"ms_per_call\": %.6f, \"mpx_slices_per_s\": %.6f, \"image_mean\": %.6f}\n",
+           m1, m2, slices, count, nAt, reps, mean_ms, pxsl / (mean_ms * 1e-3) / 1e6, chk / n123);
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
     if (argc < 4) {
@@ -283,10 +347,11 @@ int main(int argc, char** argv)
     const std::string mode = argv[1];
     const std::string in = absPath(argv[2]);
     cudaSetDevice(gpu_index);
-    if (mode == "time") {
+    if (mode == "time" || mode == "e2e") {
         /* side-effect files of the readers (dataFDES_used.cnf, ...) go to a scratch dir */
         const char* tmp = getenv("TMPDIR") ? getenv("TMPDIR") : "/tmp";
         if (chdir(tmp) != 0) return 3;
+        if (mode == "e2e") return modeE2E(in, atoi(argv[3]), argc > 4 ? atoi(argv[4]) : 1);
         return modeTime(in, atoi(argv[3]), argc > 4 ? atoi(argv[4]) : 1);
     }
     g_outdir = absPath(argv[3]);
