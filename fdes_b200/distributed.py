@@ -1,0 +1,70 @@
+"""Multi-GPU driver: one process per GPU, frozen-phonon configurations sharded across ranks.
+
+The reference is single-GPU (no NCCL/MPI anywhere); its driver loop
+(src/crystalMaker.cu:324-373) averages the configurations j of every measurement k into the
+intensity I_k and the coherent exit wave E_k and only then applies the detector tail once
+(addNoiseAndMtf, :372).  That structure shards naturally:
+
+    rank r runs configurations [count*r/world, count*(r+1)/world) of every k   (no data exchange)
+    all_reduce(SUM) of the partial I_k (m1*m2 float32) and, if wanted, E_k     (the only collective)
+    detector tail on the reduced I_k                                           (every rank, identical)
+
+Every rank seeds the XORWOW streams like the reference (curand_init(1, i, 0)) and discards the
+normals of the configurations before its own, so configuration j sees the same displacements as
+in a single-GPU run.  torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests) is
+plumbing only: the partial sums are written by the library's kernels straight into the tensors
+that are reduced.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+
+
+def shard_range(count: int, rank: int, world: int) -> Tuple[int, int]:
+    """Configurations [begin, end) of `rank`; contiguous blocks, sizes differ by at most one.
+    Same arithmetic as Engine::Engine in fdes_b200/csrc/engine.cu."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    return (count * rank) // world, (count * (rank + 1)) // world
+
+
+def simulate_sharded(open_sim: Callable[[int, int], object], *, want_exitwave: bool = False, group=None,
+                     device=None):
+    """Run a whole simulation with the configurations sharded over the ranks of `group`.
+
+    open_sim(rank, world) must return an object with the session interface of
+    fdes_b200.Simulation (n1 n2 n3 m1 m2, set_accumulators, run_k, finish_k, close) that handles
+    this rank's share.  Returns (image [n3, n2, n1] float32, exitwave [n3, m2, m1] complex64 | None)
+    -- identical on every rank.
+    """
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    sim = open_sim(rank, world)
+    try:
+        dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                                 if torch.cuda.is_available() else torch.device("cpu"))
+        acc_I = torch.zeros(sim.m2 * sim.m1, dtype=torch.float32, device=dev)
+        acc_E = torch.zeros(sim.m2 * sim.m1 * 2, dtype=torch.float32, device=dev) if want_exitwave else None
+        sim.set_accumulators(acc_I.data_ptr(), acc_E.data_ptr() if acc_E is not None else 0)
+        image = np.zeros((sim.n3, sim.n2, sim.n1), np.float32)
+        exitwave = np.zeros((sim.n3, sim.m2, sim.m1), np.complex64) if want_exitwave else None
+        for k in range(sim.n3):
+            sim.run_k(k)                       # partial sums of this rank's configurations
+            if world > 1:
+                dist.all_reduce(acc_I, op=dist.ReduceOp.SUM, group=group)
+                if acc_E is not None:
+                    dist.all_reduce(acc_E, op=dist.ReduceOp.SUM, group=group)
+                if dev.type == "cuda":
+                    torch.cuda.synchronize(dev)
+            img, ew = sim.finish_k(k)          # detector tail on the reduced intensity
+            image[k] = img
+            if exitwave is not None:
+                exitwave[k] = ew
+        return image, exitwave
+    finally:
+        sim.close()

@@ -1,0 +1,242 @@
+"""GPU (B200): the CUDA library, called through its C ABI, against
+  * the golden vectors recorded from the unmodified reference (tests/golden/),
+  * the numpy oracle on the same inputs (small cases and the full-size 1024^2 configuration),
+  * the reference itself run live on this box when oracle/_ref/ref_harness travelled with the repo,
+  * size-independent properties at BASELINE.json's full sizes.
+Bit-exact for integer work (bin indices, sort, phonon displacements); exit waves rel-L2 <= 1e-5
+and intensities <= 1e-4 (north_star tolerances)."""
+import ctypes
+import os
+import pathlib
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import CASES, DATA, ROOT, TOL_INTENSITY, TOL_WAVE, golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+HARNESS = ROOT / "oracle" / "_ref" / "ref_harness"
+
+
+# ---------------------------------------------------------------------------------------------
+# building blocks
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048, 4096])
+def test_fft2d_against_numpy(n, fb):
+    rng = np.random.default_rng(n)
+    a = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(np.complex64)
+    ref = np.fft.fft2(a.astype(np.complex128))
+    got = fb.fft2d(a, -1)
+    assert rel_l2(got, ref) < 2e-6
+    back = fb.fft2d(got, +1) / (n * n)
+    assert rel_l2(back, a) < 2e-6
+    # linearity and a delta -> constant (exact)
+    d = np.zeros((n, n), np.complex64)
+    d[0, 0] = 1
+    assert np.array_equal(fb.fft2d(d, -1), np.ones((n, n), np.complex64))
+
+
+@pytest.mark.parametrize("n,nkeys", [(0, 10), (1, 1), (257, 3), (4096, 4096), (100_000, 70_000), (46208, 11 * 1024)])
+def test_sort_records_is_stable_and_exact(n, nkeys, fb):
+    rng = np.random.default_rng(n + nkeys)
+    keys = rng.integers(0, nkeys + 1, n, dtype=np.uint32)      # key == nkeys marks rejected records
+    cols = rng.integers(0, 1 << 20, n, dtype=np.int32)
+    w = rng.standard_normal(n).astype(np.float32)
+    k, c, ww, rp = fb.sort_records(keys, cols, w, nkeys)
+    order = np.argsort(keys, kind="stable")
+    np.testing.assert_array_equal(k, keys[order])
+    np.testing.assert_array_equal(c, cols[order])
+    np.testing.assert_array_equal(ww, w[order])
+    np.testing.assert_array_equal(rp, np.searchsorted(keys[order], np.arange(nkeys + 1), side="left"))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_bins_jitter_and_potential(case, fb, orc):
+    g, meta = golden(case)
+    p, Z, xyz, dwf, occ = orc.read_cnf(str(DATA / f"{case}.cnf"))
+    with fb.Simulation(DATA / f"{case}.cnf") as sim:
+        ps = p.copy()
+        orc.set_sub_slices(ps, orc.sub_slice_ratio(ps.d3, ps.subSlTh))
+        assert (sim.m1, sim.m3, sim.nAt) == (ps.m1, ps.m3, len(Z))
+        assert np.float32(sim.lam) == ps.lam and np.float32(sim.sigma) == ps.sigma
+        # frozen-phonon displacements: same XORWOW streams as the reference -> bit-exact
+        for j in range(max(1, p.frPh)):
+            np.testing.assert_array_equal(sim.jitter_next(0), g["xyz_cfg"][j])
+        xyz0 = g["xyz_cfg"][0]
+        # integer bin tuples: bit-exact against the oracle's restatement of squareAtoms_d
+        bins = sim.bin_atoms(xyz0)
+        i1, i2, i3, _, _, ok = orc.bin_atoms(xyz0, ps)
+        ok = ok & (i3 >= 0) & (i3 < ps.m3)
+        np.testing.assert_array_equal(bins[:, 0] >= 0, ok)
+        np.testing.assert_array_equal(bins[ok, 0], i1[ok])
+        np.testing.assert_array_equal(bins[ok, 1], i2[ok])
+        np.testing.assert_array_equal(bins[ok, 2], i3[ok])
+        Zl = orc.list_of_elements(Z)
+        np.testing.assert_array_equal(bins[:, 3], [Zl.index(z) for z in Z])
+        for s in range(g["V"].shape[0]):
+            V = sim.phase_grating(xyz0, s)
+            if np.linalg.norm(g["V"][s]) > 0:
+                assert rel_l2(V, g["V"][s]) < TOL_WAVE, s
+            else:
+                assert not V.any()
+        psi = sim.exit_wave(xyz0, 0)
+        assert rel_l2(psi, g["psi_exit"][0]) < TOL_WAVE
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_full_run_against_reference_golden_and_oracle(case, fb, oracle_runs):
+    g, meta = golden(case)
+    with fb.Simulation(DATA / f"{case}.cnf", want_exitwave=True) as sim:
+        img, ew = sim.simulate()
+        assert sim.counters()["launches"] > 0
+    assert rel_l2(ew, g["exitwave"]) < TOL_WAVE
+    assert rel_l2(img, g["image"]) < TOL_INTENSITY
+    res, _ = oracle_runs(case)
+    assert rel_l2(ew, res.exitwave) < TOL_WAVE
+    assert rel_l2(img, res.image) < TOL_INTENSITY
+
+
+def test_runs_are_bit_reproducible(fb):
+    """Sorted, segmented deposition instead of float atomics: two runs agree bit for bit (the
+    reference does not, src/crystalMaker.cu:100-119)."""
+    out = []
+    for _ in range(2):
+        with fb.Simulation(DATA / "phonon64.cnf", want_exitwave=True) as sim:
+            out.append(sim.simulate())
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+
+
+@pytest.mark.parametrize("batch", [1, 2, 3])
+def test_batching_does_not_change_results(batch, fb):
+    with fb.Simulation(DATA / "phonon64.cnf", want_exitwave=True, batch=1) as a:
+        ia, ea = a.simulate()
+    with fb.Simulation(DATA / "phonon64.cnf", want_exitwave=True, batch=batch) as b:
+        ib, eb = b.simulate()
+    np.testing.assert_array_equal(ia, ib)
+    np.testing.assert_array_equal(ea, eb)
+
+
+def test_rank_shards_sum_to_the_whole(fb):
+    """rank/world sharding of the phonon configurations incl. the RNG burn-in: the partial sums
+    of (rank 0, rank 1) of 2 add up to the single-rank result."""
+    import torch
+    with fb.Simulation(DATA / "phonon64.cnf", want_exitwave=True) as whole:
+        whole.run_k(0)
+        img_w, ew_w = whole.finish_k(0)
+    n = 64 * 64
+    accI = torch.zeros(n, dtype=torch.float32, device="cuda")
+    accE = torch.zeros(2 * n, dtype=torch.float32, device="cuda")
+    sumI = torch.zeros_like(accI)
+    sumE = torch.zeros_like(accE)
+    for r in range(2):
+        with fb.Simulation(DATA / "phonon64.cnf", want_exitwave=True, rank=r, world=2) as part:
+            part.set_accumulators(accI.data_ptr(), accE.data_ptr())
+            part.run_k(0)
+            torch.cuda.synchronize()
+            sumI += accI
+            sumE += accE
+            if r == 1:
+                accI.copy_(sumI)
+                accE.copy_(sumE)
+                torch.cuda.synchronize()
+                img_s, ew_s = part.finish_k(0)
+    assert rel_l2(ew_s, ew_w) < 1e-6
+    assert rel_l2(img_s, img_w) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# the drop-in boundary
+# ---------------------------------------------------------------------------------------------
+def test_FDES_drop_in_call(fb, orc, tmp_path, monkeypatch):
+    """The exported FDES() with the argument meaning of src/FDESExport.cu:59-178: atoms from the
+    caller's array (occupancy truncated to int, src/paramStructure.cu:323), image into the caller's
+    buffer and into image_name as raw float32 [n3][n2][n1]."""
+    monkeypatch.chdir(tmp_path)
+    cnf = DATA / "tilt64.cnf"
+    p, Z, xyz, dwf, occ = orc.read_cnf(str(cnf))
+    atoms6 = np.column_stack([Z.astype(np.float32), xyz, dwf, occ]).astype(np.float32)
+    dst = np.zeros((p.n3, p.n2, p.n1), np.float32)
+    fb.cuda_FDES(0, 2, str(cnf), str(tmp_path / "M.bin"), str(tmp_path / "r.emd"), atoms6, len(atoms6), dst)
+    res = orc.build_measurements(p, Z, xyz, dwf, np.trunc(occ).astype(np.float32))
+    assert rel_l2(dst, res.image) < TOL_INTENSITY
+    on_disk = np.fromfile(tmp_path / "M.bin", np.float32).reshape(dst.shape)
+    np.testing.assert_array_equal(on_disk, dst)
+    ew = np.fromfile(str(tmp_path / "r.emd") + ".exit_wave.f32", np.float32).view(np.complex64).reshape(p.n3, p.m2, p.m1)
+    assert rel_l2(ew, res.exitwave) < TOL_WAVE
+    assert (tmp_path / "dataFDES_used.cnf").exists()     # side-effect file of getParams (:629-631)
+
+
+def test_cli_binary(orc, tmp_path, oracle_runs):
+    exe = ROOT / "fdes_b200" / "bin" / "FDES"
+    r = subprocess.run([str(exe), "--input_name", str(DATA / "sub128.cnf"), "--image_name", "out.bin",
+                        "--print_level", "2"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-500:]
+    res, _ = oracle_runs("sub128")
+    img = np.fromfile(tmp_path / "out.bin", np.float32).reshape(res.image.shape)
+    assert rel_l2(img, res.image) < TOL_INTENSITY
+    ew = np.fromfile(tmp_path / "results.emd.exit_wave.f32", np.float32).view(np.complex64).reshape(res.exitwave.shape)
+    assert rel_l2(ew, res.exitwave) < TOL_WAVE
+
+
+def test_unsupported_inputs_fail_loudly(fb, tmp_path):
+    from fdes_b200 import specimens
+    specimens.write_cnf(tmp_path / "odd.cnf", image_size=40, border_size=20, slices=2, pixel_size=0.25e-10,
+                        slice_thickness=2e-10, atoms=specimens.au_cuboctahedron(1))
+    with pytest.raises(fb.FdesError, match="power of two"):
+        fb.Simulation(tmp_path / "odd.cnf")
+    with pytest.raises(fb.FdesError, match="cannot read"):
+        fb.Simulation(tmp_path / "missing.cnf")
+
+
+# ---------------------------------------------------------------------------------------------
+# full size (BASELINE.json configs[1]: Si[001] 11k atoms, 1024^2, 2 A slices)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def si1024(tmp_path_factory, fb):
+    from fdes_b200 import specimens
+    d = tmp_path_factory.mktemp("si1024")
+    cnf = d / "si001_1024.cnf"
+    specimens.config_si001_1024(cnf)
+    with fb.Simulation(cnf, want_exitwave=True) as sim:
+        img, ew = sim.simulate()
+    return cnf, img, ew
+
+
+def test_si1024_against_oracle(si1024, orc):
+    cnf, img, ew = si1024
+    p, Z, xyz, dwf, occ = orc.read_cnf(str(cnf))
+    res = orc.build_measurements(p, Z, xyz, dwf, occ)
+    assert rel_l2(ew, res.exitwave) < TOL_WAVE
+    assert rel_l2(img, res.image) < TOL_INTENSITY
+
+
+@pytest.mark.skipif(not HARNESS.exists(), reason="oracle/_ref/ref_harness not built")
+def test_si1024_against_live_reference(si1024, tmp_path):
+    cnf, img, ew = si1024
+    out = tmp_path / "ref"
+    subprocess.run([str(HARNESS), "run", str(cnf), str(out), "2"], check=True, capture_output=True)
+    rimg = np.fromfile(out / "image.f32", np.float32).reshape(img.shape)
+    rew = np.fromfile(out / "exitwave.f32", np.float32).view(np.complex64).reshape(ew.shape)
+    assert rel_l2(ew, rew) < TOL_WAVE
+    assert rel_l2(img, rimg) < TOL_INTENSITY
+
+
+def test_si1024_properties(si1024, fb, orc, tmp_path):
+    cnf, img, ew = si1024
+    # elastic scattering without absorption only loses intensity through the 2/3 band limit
+    n = ew.shape[-1] * ew.shape[-2]
+    total = float(np.sum(np.abs(ew.astype(np.complex128)) ** 2)) / n
+    assert 0.9 < total <= 1.0 + 1e-5
+    # the specimen is mirror-symmetric in x <-> y about the grid centre up to the (fixed) structure
+    # origin; a cheap invariant that needs no such assumption: the image is finite and positive
+    assert np.isfinite(img).all() and img.min() > 0
+    # empty specimen (all atoms outside the slab): the plane wave passes unchanged
+    p, Z, xyz, dwf, occ = orc.read_cnf(str(cnf))
+    atoms6 = np.column_stack([Z.astype(np.float32), xyz, dwf, occ]).astype(np.float32)
+    atoms6[:, 3] = 1e-6
+    with fb.Simulation(cnf, atoms6=atoms6, want_exitwave=True) as sim:
+        img0, ew0 = sim.simulate()
+    assert np.allclose(ew0, 1.0, atol=1e-5)
+    assert np.allclose(img0, 1.0, atol=1e-4)
