@@ -234,13 +234,9 @@ int fdes_b200_fft2d(float* data_host, int N, int dir, int gpu_index)
     const size_t NN = (size_t)N * N;
     cpx *d = nullptr, *tw = nullptr;
     ck(cudaMalloc(&d, NN * sizeof(cpx)), "cudaMalloc");
-    ck(cudaMalloc(&tw, N * sizeof(cpx)), "cudaMalloc");
-    std::vector<cpx> h(N);
-    for (int n = 0; n < N; n++) {
-        const double a = -2.0 * M_PI * (double)n / (double)N;
-        h[n] = make_float2((float)cos(a), (float)sin(a));
-    }
-    ck(cudaMemcpy(tw, h.data(), N * sizeof(cpx), cudaMemcpyHostToDevice), "cudaMemcpy");
+    const std::vector<cpx> h = make_twiddles(N);
+    ck(cudaMalloc(&tw, h.size() * sizeof(cpx)), "cudaMalloc");
+    ck(cudaMemcpy(tw, h.data(), h.size() * sizeof(cpx), cudaMemcpyHostToDevice), "cudaMemcpy");
     ck(cudaMemcpy(d, data_host, NN * sizeof(cpx), cudaMemcpyHostToDevice), "cudaMemcpy");
     SweepGeom g{N, N, N, tw};
     RowOpts ro;

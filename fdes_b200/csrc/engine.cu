@@ -86,7 +86,7 @@ Engine::Engine(const Params& pin, const Atoms& atoms, const EngineOptions& opt) 
     CK(cudaEventCreate(&ev1_));
 
     const size_t NN = (size_t)N_ * N_, Q = (size_t)(N_ / 2 + 1);
-    dmalloc(tw_, N_); dmalloc(Pq_, Q * Q); dmalloc(Gq_, (size_t)nZ_ * Q * Q);
+    dmalloc(Pq_, Q * Q); dmalloc(Gq_, (size_t)nZ_ * Q * Q);
     dmalloc(psi_in_, NN); dmalloc(Psi_, (size_t)B_ * NN); dmalloc(W_, (size_t)B_ * NN);
     dmalloc(A_, (size_t)B_ * nZ_ * NN);
     dmalloc(I_own_, NN); dmalloc(lens_, NN); dmalloc(det_, NN); dmalloc(scratch_, NN);
@@ -137,18 +137,10 @@ Engine::~Engine()
 
 void Engine::setup_tables()
 {
-    // twiddles in double precision
-    std::vector<cpx> tw(N_);
-    for (int n = 0; n < N_; n++) {
-        const double a = -2.0 * M_PI * (double)n / (double)N_;
-        tw[n] = make_float2((float)cos(a), (float)sin(a));
-    }
-    // exact values on the axes
-    tw[0] = make_float2(1.f, 0.f);
-    tw[N_ / 4] = make_float2(0.f, -1.f);
-    tw[N_ / 2] = make_float2(-1.f, 0.f);
-    tw[3 * N_ / 4] = make_float2(0.f, 1.f);
-    CK(cudaMemcpyAsync(tw_, tw.data(), N_ * sizeof(cpx), cudaMemcpyHostToDevice, st_));
+    // pass twiddle tables (double precision on the host)
+    const std::vector<cpx> tw = make_twiddles(N_);
+    dmalloc(tw_, tw.size());
+    CK(cudaMemcpyAsync(tw_, tw.data(), tw.size() * sizeof(cpx), cudaMemcpyHostToDevice, st_));
     CK(cudaStreamSynchronize(st_));
 
     // 2/3 band limit: largest |i1| kept on the axis by zeroHighFreq's float test

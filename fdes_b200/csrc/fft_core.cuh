@@ -1,14 +1,21 @@
 // fdes_b200 -- register/shared-memory Stockham line FFT for sm_100a (complex float32).
 //
 // One "line" (a grid row or a grid column) of N points is transformed by T = N/E threads that
-// each keep E = 16 points in registers at positions theta + m*T (m = 0..E-1).  A transform is a
-// sequence of radix-R passes (R = 16 while it divides what is left, then 8/4/2).  In a pass a
-// thread performs E/R radix-R butterflies on registers; between passes the line is exchanged
+// each keep E points in registers at positions theta + m*T (m = 0..E-1).  A transform is a
+// sequence of radix-R passes (R = E while it divides what is left, then the remainder).  In a
+// pass a thread performs E/R radix-R DFTs on registers; between passes the line is exchanged
 // through padded shared memory (Stockham autosort: natural order in, natural order out).  The
 // register layout before the first pass and after the last pass is the same, so
 //   * global loads/stores are coalesced (consecutive threads <-> consecutive points), and
 //   * transforms can be chained (inverse -> pointwise op -> forward) with the data staying in
 //     registers -- this is what lets a whole multislice sweep touch HBM once.
+// With E = 32 a 1024-point line is 32 x 32: ONE shared-memory exchange per transform and, for a
+// row, one warp per line (warp-level synchronisation only).
+//
+// Arithmetic uses the packed f32x2 instructions of sm_100 (add/mul/fma.rn.f32x2 -> FADD2 / FMUL2 /
+// FFMA2): a complex add is one instruction and a complex multiply two, which halves the issue
+// slots the butterflies need (the FP32 lanes themselves run at the same rate, measured with
+// tools/microbench/f32x2_rate.cu).
 // The index algebra is checked on the CPU by tools/fft_model.py.
 //
 // Replaces the cuFFT C2C calls of the reference hot path (cufftExecC2C at
@@ -20,168 +27,208 @@ namespace fdes {
 
 typedef float2 cpx;
 
-constexpr int FFT_E = 16;  // points per thread
-
-__device__ __forceinline__ cpx cmul(cpx a, cpx b)
+// ---------------------------------------------------------------------------------------------
+// packed f32x2 arithmetic
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ cpx padd(cpx a, cpx b)
 {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+    cpx c;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rc, ra, rb; "
+        "mov.b64 {%0,%1}, rc;}" : "=f"(c.x), "=f"(c.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return c;
 }
-__device__ __forceinline__ cpx cadd(cpx a, cpx b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ cpx csub(cpx a, cpx b) { return make_float2(a.x - b.x, a.y - b.y); }
-// multiply by DIR * i  (DIR = -1: forward transform, W4 = -i)
+__device__ __forceinline__ cpx psub(cpx a, cpx b)
+{
+    cpx c;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; sub.rn.f32x2 rc, ra, rb; "
+        "mov.b64 {%0,%1}, rc;}" : "=f"(c.x), "=f"(c.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return c;
+}
+__device__ __forceinline__ cpx pmul(cpx a, cpx b)
+{
+    cpx c;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rc, ra, rb; "
+        "mov.b64 {%0,%1}, rc;}" : "=f"(c.x), "=f"(c.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return c;
+}
+__device__ __forceinline__ cpx pfma(cpx a, cpx b, cpx c)
+{
+    cpx d;
+    asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; "
+        "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+
+__device__ __forceinline__ cpx cadd(cpx a, cpx b) { return padd(a, b); }
+__device__ __forceinline__ cpx csub(cpx a, cpx b) { return psub(a, b); }
+// a * (c + i s): FMUL2 + FFMA2 (the scalar broadcasts and the pair swap are operand modifiers)
+__device__ __forceinline__ cpx cmul_cs(cpx a, float c, float s)
+{
+    return pfma(make_float2(a.x, a.x), make_float2(c, s), pmul(make_float2(a.y, a.y), make_float2(-s, c)));
+}
+__device__ __forceinline__ cpx cmul(cpx a, cpx b) { return cmul_cs(a, b.x, b.y); }
+// a * conj(b)
+__device__ __forceinline__ cpx cmul_conj(cpx a, cpx b) { return cmul_cs(a, b.x, -b.y); }
+// a + (DIR * i) * d   and   a - (DIR * i) * d      (DIR = -1: forward transform, W4 = -i)
+template <int DIR>
+__device__ __forceinline__ cpx add_di(cpx a, cpx d)
+{
+    return pfma(make_float2(d.y, d.x), DIR < 0 ? make_float2(1.f, -1.f) : make_float2(-1.f, 1.f), a);
+}
+template <int DIR>
+__device__ __forceinline__ cpx sub_di(cpx a, cpx d)
+{
+    return pfma(make_float2(d.y, d.x), DIR < 0 ? make_float2(-1.f, 1.f) : make_float2(1.f, -1.f), a);
+}
+// a * (DIR * i)
 template <int DIR>
 __device__ __forceinline__ cpx mul_di(cpx a)
 {
     return DIR < 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
 }
-// multiply by (c + DIR*i*s)
-template <int DIR>
-__device__ __forceinline__ cpx mul_w(cpx a, float c, float s)
+
+// ---------------------------------------------------------------------------------------------
+// in-register DFTs, natural order in / natural order out
+// ---------------------------------------------------------------------------------------------
+// cos / sin of 2 pi n / 32, n = 0..8
+__device__ __forceinline__ constexpr float cos32(int n)
 {
-    const float sd = DIR < 0 ? -s : s;
-    return make_float2(a.x * c - a.y * sd, a.x * sd + a.y * c);
+    constexpr float c[9] = {1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                            0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f,
+                            0.19509032201612826785f, 0.f};
+    // reduce n (mod 32) to the first octant pair
+    n &= 31;
+    if (n > 16) n = 32 - n;          // cos is even
+    return n <= 8 ? c[n] : -c[16 - n];
+}
+__device__ __forceinline__ constexpr float sin32(int n) { return cos32(n - 8); }
+
+// v *= exp(DIR * 2 pi i * n / 32) with compile-time n
+template <int DIR, int n32>
+__device__ __forceinline__ cpx mul_w32(cpx a)
+{
+    constexpr int n = ((n32 % 32) + 32) % 32;
+    if constexpr (n == 0) return a;
+    else if constexpr (n == 8) return mul_di<DIR>(a);
+    else if constexpr (n == 16) return make_float2(-a.x, -a.y);
+    else if constexpr (n == 24) return mul_di<-DIR>(a);
+    else return cmul_cs(a, cos32(n), DIR < 0 ? -sin32(n) : sin32(n));
 }
 
-template <int DIR>
-__device__ __forceinline__ void bfly2(cpx& a, cpx& b)
-{
-    const cpx t = a;
-    a = cadd(t, b);
-    b = csub(t, b);
-}
-
-// 4-point DFT, natural order in / out.
-template <int DIR>
-__device__ __forceinline__ void bfly4(cpx& x0, cpx& x1, cpx& x2, cpx& x3)
-{
-    const cpx t0 = cadd(x0, x2), t1 = csub(x0, x2);
-    const cpx t2 = cadd(x1, x3), t3 = mul_di<DIR>(csub(x1, x3));
-    x0 = cadd(t0, t2);
-    x2 = csub(t0, t2);
-    x1 = cadd(t1, t3);
-    x3 = csub(t1, t3);
-}
-
-// R-point DFT on v[0..R-1], natural order in / out.
 template <int R, int DIR>
-struct Butterfly;
+struct Dft;
 
 template <int DIR>
-struct Butterfly<2, DIR> {
-    __device__ __forceinline__ static void run(cpx (&v)[2]) { bfly2<DIR>(v[0], v[1]); }
-};
-template <int DIR>
-struct Butterfly<4, DIR> {
-    __device__ __forceinline__ static void run(cpx (&v)[4]) { bfly4<DIR>(v[0], v[1], v[2], v[3]); }
-};
-template <int DIR>
-struct Butterfly<8, DIR> {
-    // t = t1 + 2*t2 (t1<2, t2<4), s = 4*s1 + s2:  W8^{st} = W2^{s1 t1} W8^{s2 t1} W4^{s2 t2}
-    __device__ __forceinline__ static void run(cpx (&v)[8])
+struct Dft<2, DIR> {
+    __device__ __forceinline__ static void run(cpx (&v)[2])
     {
-        constexpr float h = 0.70710678118654752440f;
-        bfly4<DIR>(v[0], v[2], v[4], v[6]);  // Y[0][s2] at v[2*s2]
-        bfly4<DIR>(v[1], v[3], v[5], v[7]);  // Y[1][s2] at v[1+2*s2]
-        v[3] = mul_w<DIR>(v[3], h, h);       // W8^1
-        v[5] = mul_di<DIR>(v[5]);            // W8^2
-        v[7] = mul_w<DIR>(v[7], -h, h);      // W8^3
-        bfly2<DIR>(v[0], v[1]);              // X[s2] , X[4+s2] at v[2 s2], v[1+2 s2]
-        bfly2<DIR>(v[2], v[3]);
-        bfly2<DIR>(v[4], v[5]);
-        bfly2<DIR>(v[6], v[7]);
-        // X[4 s1 + s2] sits at v[s1 + 2 s2] -> natural order
-        const cpx a1 = v[1], a2 = v[2], a3 = v[3], a4 = v[4], a5 = v[5], a6 = v[6];
-        v[1] = a2; v[2] = a4; v[3] = a6; v[4] = a1; v[5] = a3; v[6] = a5;
+        const cpx t = v[0];
+        v[0] = cadd(t, v[1]);
+        v[1] = csub(t, v[1]);
     }
 };
 template <int DIR>
-struct Butterfly<16, DIR> {
-    // t = t1 + 4*t2, s = 4*s1 + s2:  W16^{st} = W4^{s1 t1} W16^{s2 t1} W4^{s2 t2}
-    __device__ __forceinline__ static void run(cpx (&v)[16])
+struct Dft<4, DIR> {
+    __device__ __forceinline__ static void run(cpx (&v)[4])
     {
-        constexpr float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
-        constexpr float h = 0.70710678118654752440f;
-#pragma unroll
-        for (int t1 = 0; t1 < 4; t1++) bfly4<DIR>(v[t1], v[t1 + 4], v[t1 + 8], v[t1 + 12]);
-        // v[t1 + 4 s2] *= W16^{s2 t1}
-        v[5] = mul_w<DIR>(v[5], c1, s1);     // s2=1,t1=1 : n=1
-        v[6] = mul_w<DIR>(v[6], h, h);       // n=2
-        v[7] = mul_w<DIR>(v[7], s1, c1);     // n=3
-        v[9] = mul_w<DIR>(v[9], h, h);       // s2=2,t1=1 : n=2
-        v[10] = mul_di<DIR>(v[10]);          // n=4
-        v[11] = mul_w<DIR>(v[11], -h, h);    // n=6
-        v[13] = mul_w<DIR>(v[13], s1, c1);   // s2=3,t1=1 : n=3
-        v[14] = mul_w<DIR>(v[14], -h, h);    // n=6
-        v[15] = mul_w<DIR>(v[15], -c1, -s1); // n=9: cos=-c1, sin=-s1
-#pragma unroll
-        for (int s2 = 0; s2 < 4; s2++) bfly4<DIR>(v[4 * s2], v[4 * s2 + 1], v[4 * s2 + 2], v[4 * s2 + 3]);
-        // X[4 s1 + s2] sits at v[s1 + 4 s2] -> transpose 4x4
-#pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-            for (int b = a + 1; b < 4; b++) {
-                const cpx t = v[a + 4 * b];
-                v[a + 4 * b] = v[b + 4 * a];
-                v[b + 4 * a] = t;
-            }
+        const cpx t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+        const cpx t2 = cadd(v[1], v[3]), d = csub(v[1], v[3]);
+        v[0] = cadd(t0, t2);
+        v[2] = csub(t0, t2);
+        v[1] = add_di<DIR>(t1, d);
+        v[3] = sub_di<DIR>(t1, d);
     }
 };
-
-// padded shared-memory index (one extra slot per 16) -- conflict-free 64-bit scatter/gather
-__device__ __forceinline__ int smpad(int i) { return i + (i >> 4); }
-__host__ __device__ constexpr int line_smem_elems(int N) { return N + (N >> 4); }
-
-// forward twiddle table tw[n] = exp(-2 pi i n / N), n < N (built in double on the host)
-template <int DIR>
-__device__ __forceinline__ cpx ldtw(const cpx* __restrict__ tw, int idx)
-{
-    cpx w = __ldg(tw + idx);
-    if (DIR > 0) w.y = -w.y;
-    return w;
-}
-
-// twiddle v[t] *= W^(t*kk) for t = 1..R-1, W = exp(DIR 2 pi i / N), kk = k * N/(NS*R)
+// R = R1 * R2, input index t = t1 + R1 t2, output index s = R2 s1 + s2:
+//   X[R2 s1 + s2] = sum_t1 W_R1^{s1 t1} ( W_R^{s2 t1} sum_t2 W_R2^{s2 t2} x[t1 + R1 t2] )
 template <int R, int DIR>
-__device__ __forceinline__ void apply_twiddles(cpx (&v)[R], const cpx* __restrict__ tw, int kk)
-{
-    if (R == 2) {
-        v[1] = cmul(v[1], ldtw<DIR>(tw, kk));
-    } else if (R == 4) {
-        const cpx w1 = ldtw<DIR>(tw, kk), w2 = ldtw<DIR>(tw, 2 * kk);
-        v[1] = cmul(v[1], w1);
-        v[2] = cmul(v[2], w2);
-        v[3] = cmul(v[3], cmul(w1, w2));
-    } else if (R == 8) {
-        const cpx w1 = ldtw<DIR>(tw, kk), w2 = ldtw<DIR>(tw, 2 * kk), w4 = ldtw<DIR>(tw, 4 * kk);
-        const cpx w3 = cmul(w1, w2);
-        v[1] = cmul(v[1], w1);
-        v[2] = cmul(v[2], w2);
-        v[3] = cmul(v[3], w3);
-        v[4] = cmul(v[4], w4);
-        v[5] = cmul(v[5], cmul(w4, w1));
-        v[6] = cmul(v[6], cmul(w4, w2));
-        v[7] = cmul(v[7], cmul(w4, w3));
-    } else {  // 16
-        const cpx w1 = ldtw<DIR>(tw, kk), w2 = ldtw<DIR>(tw, 2 * kk), w4 = ldtw<DIR>(tw, 4 * kk);
-        const cpx w8 = ldtw<DIR>(tw, 8 * kk);
-        const cpx w3 = cmul(w1, w2);
-        cpx lo[8];
-        lo[1] = w1; lo[2] = w2; lo[3] = w3; lo[4] = w4;
-        lo[5] = cmul(w4, w1); lo[6] = cmul(w4, w2); lo[7] = cmul(w4, w3);
+struct Dft {
+    static constexpr int R1 = 4, R2 = R / 4;
+    static_assert(R == 8 || R == 16 || R == 32, "radix 2..32");
+    __device__ __forceinline__ static void run(cpx (&v)[R])
+    {
+        cpx y[R1][R2];
 #pragma unroll
-        for (int t = 1; t < 8; t++) v[t] = cmul(v[t], lo[t]);
-        v[8] = cmul(v[8], w8);
+        for (int t1 = 0; t1 < R1; t1++) {
+            cpx u[R2];
 #pragma unroll
-        for (int t = 1; t < 8; t++) v[8 + t] = cmul(v[8 + t], cmul(w8, lo[t]));
+            for (int t2 = 0; t2 < R2; t2++) u[t2] = v[t1 + R1 * t2];
+            Dft<R2, DIR>::run(u);
+#pragma unroll
+            for (int s2 = 0; s2 < R2; s2++) y[t1][s2] = u[s2];
+        }
+        twiddle_rows<1>(y);
+        twiddle_rows<2>(y);
+        twiddle_rows<3>(y);
+#pragma unroll
+        for (int s2 = 0; s2 < R2; s2++) {
+            cpx z[R1];
+#pragma unroll
+            for (int t1 = 0; t1 < R1; t1++) z[t1] = y[t1][s2];
+            Dft<R1, DIR>::run(z);
+#pragma unroll
+            for (int s1 = 0; s1 < R1; s1++) v[R2 * s1 + s2] = z[s1];
+        }
     }
+    template <int t1, int s2 = 1>
+    __device__ __forceinline__ static void twiddle_rows(cpx (&y)[R1][R2])
+    {
+        if constexpr (s2 < R2) {
+            y[t1][s2] = mul_w32<DIR, (32 / R) * s2 * t1>(y[t1][s2]);
+            twiddle_rows<t1, s2 + 1>(y);
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// line transform
+// ---------------------------------------------------------------------------------------------
+// synchronisation of the threads that share a line buffer
+struct SyncBlock { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
+struct SyncWarp { __device__ __forceinline__ void operator()() const { __syncwarp(); } };
+struct SyncNamed {   // threads [id, count): bar.sync id, count  (count a multiple of 32)
+    int id, count;
+    __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+};
+
+// padded shared-memory index (one extra slot per E) -- conflict-free 64-bit scatter/gather
+template <int E>
+__device__ __forceinline__ int smpad(int i) { return i + (i / E); }
+template <int E>
+__host__ __device__ constexpr int line_smem_elems(int N) { return N + N / E; }
+
+// Twiddle tables (built in double on the host, see make_twiddles in engine.cu), for a line of N
+// points with E points per thread and passes of radix R_1 = E, R_2, ...:
+//   pass p >= 2 with NS = R_1 ... R_{p-1}:  tab_p[t * NS + k] = exp(-2 pi i t k / (NS R_p)), t < R_p, k < NS
+// stored back to back: offsets twiddle_offset<N, E>(p).
+template <int N, int E, int NS>
+struct PassInfo {
+    static constexpr int rem = N / NS;
+    static constexpr int R = rem >= E ? E : rem;
+    static constexpr bool last = (rem == R);
+};
+template <int N, int E, int NS = 1>
+__host__ __device__ constexpr int twiddle_table_elems()
+{
+    using P = PassInfo<N, E, NS>;
+    const int mine = NS > 1 ? P::R * NS : 0;
+    if constexpr (P::last) return mine;
+    else return mine + twiddle_table_elems<N, E, NS * P::R>();
+}
+template <int N, int E, int NS_TARGET, int NS = 1>
+__host__ __device__ constexpr int twiddle_offset()
+{
+    using P = PassInfo<N, E, NS>;
+    if constexpr (NS == NS_TARGET) return 0;
+    else return (NS > 1 ? P::R * NS : 0) + twiddle_offset<N, E, NS_TARGET, NS * P::R>();
 }
 
-// One Stockham pass of radix R with NS = product of previous radices.
-template <int N, int R, int NS, int DIR, bool LAST>
-__device__ __forceinline__ void fft_pass(cpx (&x)[FFT_E], cpx* __restrict__ sm, int theta,
-                                         const cpx* __restrict__ tw)
+template <int N, int E, int R, int NS, int DIR, bool LAST, class Sync>
+__device__ __forceinline__ void fft_pass(cpx (&x)[E], cpx* __restrict__ sm, int theta,
+                                         const cpx* __restrict__ tw, Sync sync)
 {
-    constexpr int E = FFT_E, T = N / E, U = E / R;
+    constexpr int T = N / E, U = E / R;
 #pragma unroll
     for (int u = 0; u < U; u++) {
         const int j = theta + u * T;
@@ -189,44 +236,49 @@ __device__ __forceinline__ void fft_pass(cpx (&x)[FFT_E], cpx* __restrict__ sm, 
         cpx v[R];
 #pragma unroll
         for (int t = 0; t < R; t++) v[t] = x[u + t * U];
-        if (NS > 1) apply_twiddles<R, DIR>(v, tw, k * (N / (NS * R)));
-        Butterfly<R, DIR>::run(v);
-        if (LAST) {
+        if constexpr (NS > 1) {
+            const cpx* tab = tw + twiddle_offset<N, E, NS>() + k;
+#pragma unroll
+            for (int t = 1; t < R; t++) {
+                const cpx w = __ldg(tab + t * NS);
+                v[t] = DIR < 0 ? cmul(v[t], w) : cmul_conj(v[t], w);
+            }
+        }
+        Dft<R, DIR>::run(v);
+        if constexpr (LAST) {
 #pragma unroll
             for (int t = 0; t < R; t++) x[u + t * U] = v[t];
         } else {
             const int base = (j - k) * R + k;
 #pragma unroll
-            for (int t = 0; t < R; t++) sm[smpad(base + t * NS)] = v[t];
+            for (int t = 0; t < R; t++) sm[smpad<E>(base + t * NS)] = v[t];
         }
     }
-    if (!LAST) {
-        __syncthreads();
+    if constexpr (!LAST) {
+        sync();
 #pragma unroll
-        for (int m = 0; m < E; m++) x[m] = sm[smpad(theta + m * T)];
-        __syncthreads();
+        for (int m = 0; m < E; m++) x[m] = sm[smpad<E>(theta + m * T)];
+        sync();
     }
 }
 
-template <int N, int NS, int DIR>
+template <int N, int E, int NS, int DIR, class Sync>
 struct LinePasses {
-    __device__ __forceinline__ static void run(cpx (&x)[FFT_E], cpx* sm, int theta, const cpx* tw)
+    __device__ __forceinline__ static void run(cpx (&x)[E], cpx* sm, int theta, const cpx* tw, Sync sync)
     {
-        constexpr int rem = N / NS;
-        constexpr int R = rem >= FFT_E ? FFT_E : rem;
-        constexpr bool last = (rem == R);
-        fft_pass<N, R, NS, DIR, last>(x, sm, theta, tw);
-        if constexpr (!last) LinePasses<N, NS * R, DIR>::run(x, sm, theta, tw);
+        using P = PassInfo<N, E, NS>;
+        fft_pass<N, E, P::R, NS, DIR, P::last, Sync>(x, sm, theta, tw, sync);
+        if constexpr (!P::last) LinePasses<N, E, NS * P::R, DIR, Sync>::run(x, sm, theta, tw, sync);
     }
 };
 
-// Transform one line held as x[m] = f[theta + m*N/16].  All threads of the CTA must call it
-// together (it contains __syncthreads when N > 16).  sm: this line's line_smem_elems(N) slots.
-template <int N, int DIR>
-__device__ __forceinline__ void fft_line(cpx (&x)[FFT_E], cpx* sm, int theta, const cpx* tw)
+// Transform one line held as x[m] = f[theta + m*N/E].  All threads sharing the line buffer must
+// call it together.  sm: this line's line_smem_elems<E>(N) slots; tw: tables described above.
+template <int N, int E, int DIR, class Sync>
+__device__ __forceinline__ void fft_line(cpx (&x)[E], cpx* sm, int theta, const cpx* tw, Sync sync)
 {
-    static_assert(N >= 16 && (N & (N - 1)) == 0, "power-of-two line length >= 16");
-    LinePasses<N, 1, DIR>::run(x, sm, theta, tw);
+    static_assert(N >= E && (N & (N - 1)) == 0, "power-of-two line length >= E");
+    LinePasses<N, E, 1, DIR, Sync>::run(x, sm, theta, tw, sync);
 }
 
 }  // namespace fdes

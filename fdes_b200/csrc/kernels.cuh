@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstddef>
 #include <cstdint>
+#include <vector>
 
 namespace fdes {
 
@@ -14,8 +15,10 @@ struct SweepGeom {
     int N;              // grid size (power of two, 64..4096)
     int lo_end;         // columns kx in [0, lo_end) or [hi_start, N) can be non-zero after the
     int hi_start;       //   2/3 band limit (bounds rounded outwards to multiples of 32)
-    const cpx* tw;      // forward twiddles exp(-2 pi i n / N), n < N
+    const cpx* tw;      // pass twiddle tables of make_twiddles(N) (layout: fft_core.cuh)
 };
+// host copy of the twiddle tables a SweepGeom of size N must point to (on the device)
+std::vector<cpx> make_twiddles(int N);
 
 bool fft_size_supported(int N);
 int rows_per_block(int N);

@@ -16,8 +16,10 @@
 // stored, loaded nor transformed by S3..S6.
 #include "fft_core.cuh"
 #include "kernels.cuh"
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 namespace fdes {
 
@@ -31,22 +33,42 @@ namespace fdes {
         }                                                                                        \
     } while (0)
 
+// Points per thread for a line of N points (rows and columns use the same split, so one
+// twiddle table per grid size serves both).
+template <int N>
+struct LineCfg {
+    static constexpr int E = N >= 512 ? 32 : (N >= 128 ? 16 : 8);
+    static constexpr int T = N / E;                     // threads per line
+    static constexpr int LS = line_smem_elems<E>(N);    // padded line buffer [elements]
+};
 template <int N>
 struct RowCfg {
-    static constexpr int T = N / FFT_E;
-    static constexpr int RPB = (256 / T) > 0 ? (256 / T) : 1;
+    using L = LineCfg<N>;
+    static constexpr int E = L::E, T = L::T;
+    static constexpr int RPB = (128 / T) > 0 ? (128 / T) : 1;      // lines (rows) per CTA
     static constexpr int THREADS = RPB * T;
-    static constexpr int LSTRIDE = line_smem_elems(N);
+    static constexpr int LSTRIDE = L::LS;
     static constexpr size_t SMEM = (size_t)RPB * LSTRIDE * sizeof(cpx);
+    static constexpr bool WARP_SYNC = (T <= 32);       // a line lives inside one warp
 };
-// HEAVY kernels keep two register sets per thread -> fewer columns per CTA for large N.
+// threads of one row line: warp-level sync when the line fits a warp, else a named barrier
+template <int N>
+struct RowSync {
+    int id;
+    __device__ __forceinline__ explicit RowSync(int line) : id(line + 1) {}
+    __device__ __forceinline__ void operator()() const
+    {
+        if constexpr (RowCfg<N>::WARP_SYNC) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(RowCfg<N>::T) : "memory");
+    }
+};
 template <int N, bool HEAVY>
 struct ColCfg {
-    static constexpr int T = N / FFT_E;
-    static constexpr int CW0 = N <= 256 ? 16 : (N <= 1024 ? 8 : 4);
-    static constexpr int CW = (HEAVY && CW0 * T > 512) ? 512 / T : CW0;
+    using L = LineCfg<N>;
+    static constexpr int E = L::E, T = L::T;
+    static constexpr int CW = (256 / T) >= 16 ? 16 : ((256 / T) >= 2 ? (256 / T) : 2);   // columns per CTA
     static constexpr int THREADS = CW * T;
-    static constexpr int LSTRIDE = line_smem_elems(N) + 16 / CW;  // bank-conflict-free line stride
+    static constexpr int LSTRIDE = L::LS + 16 / CW;   // bank-conflict-free line stride
     static constexpr size_t SMEM = (size_t)CW * LSTRIDE * sizeof(cpx);
 };
 
@@ -54,8 +76,6 @@ bool fft_size_supported(int N)
 {
     return N == 64 || N == 128 || N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096;
 }
-int rows_per_block(int N) { return (256 / (N / FFT_E)) > 0 ? 256 / (N / FFT_E) : 1; }
-int cols_per_block(int N) { return N <= 256 ? 16 : (N <= 1024 ? 8 : 4); }
 
 #define FDES_DISPATCH_N(N_, ...)                                                               \
     switch (N_) {                                                                                \
@@ -94,15 +114,9 @@ static int band_cols(const SweepGeom& g)
     return g.lo_end >= g.hi_start ? g.N : g.lo_end + (g.N - g.hi_start);
 }
 
-// f0 * f1 in the reference's 3-multiply form (multiplyElementwise, src/complexMath.cu:44-62)
-__device__ __forceinline__ cpx mul3(cpx f0, cpx f1)
-{
-    const float a = f0.x, b = f0.y, c = f1.x, d = f1.y;
-    const float k = a * (c + d);
-    const float dd = d * (a + b);
-    const float cc = c * (b - a);
-    return make_float2(k - dd, k + cc);
-}
+// The reference multiplies complex fields with a 3-multiplication form (multiplyElementwise,
+// src/complexMath.cu:44-62); here the plain product is used (FMUL2 + FFMA2).  Both are correctly
+// rounded to within 1-2 ulp of the exact product; the parity bound is 1e-5.
 
 // =============================================================================================
 // S1  density rows
@@ -115,7 +129,9 @@ k_density_rows(cpx* __restrict__ A, const int* __restrict__ rowptr, const int* _
 {
     using C = RowCfg<N>;
     extern __shared__ cpx smem[];
+    constexpr int E = C::E;
     const int line = threadIdx.x / C::T, theta = threadIdx.x % C::T;
+    const RowSync<N> sync(line);
     const int z = blockIdx.y, b = blockIdx.z;
     const int row = blockIdx.x * C::RPB + line;
     const int* rp = rowptr + (size_t)b * rp_stride + (size_t)(slice * nZ + z) * N;
@@ -124,7 +140,7 @@ k_density_rows(cpx* __restrict__ A, const int* __restrict__ rowptr, const int* _
     if (!__syncthreads_or(hi > lo)) return;
     float* dens = reinterpret_cast<float*>(smem + C::RPB * C::LSTRIDE) + line * N;
 #pragma unroll
-    for (int m = 0; m < FFT_E; m++) dens[theta + m * C::T] = 0.f;
+    for (int m = 0; m < E; m++) dens[theta + m * C::T] = 0.f;
     __syncthreads();
     if (theta == 0) {
         // sorted, stable order -> the summation order is fixed (deterministic, unlike the
@@ -134,16 +150,16 @@ k_density_rows(cpx* __restrict__ A, const int* __restrict__ rowptr, const int* _
         for (int i = lo; i < hi; i++) dens[cc[i]] += ww[i];
     }
     __syncthreads();
-    cpx x[FFT_E];
+    cpx x[E];
 #pragma unroll
-    for (int m = 0; m < FFT_E; m++) {
+    for (int m = 0; m < E; m++) {
         const float d = dens[theta + m * C::T];
         x[m] = make_float2(d, d * imPot);
     }
-    fft_line<N, -1>(x, smem + line * C::LSTRIDE, theta, tw);
+    fft_line<N, E, -1>(x, smem + line * C::LSTRIDE, theta, tw, sync);
     cpx* out = A + ((size_t)(b * nZ + z) * N + row) * N;
 #pragma unroll
-    for (int m = 0; m < FFT_E; m++) out[theta + m * C::T] = x[m];
+    for (int m = 0; m < E; m++) out[theta + m * C::T] = x[m];
 }
 
 void launch_density_rows(const SweepGeom& g, cpx* A, const int* rowptr, const int* rec_col,
@@ -173,39 +189,41 @@ k_potential_cols(cpx* __restrict__ B, const cpx* __restrict__ A, const float* __
     using C = ColCfg<N, true>;
     extern __shared__ cpx smem[];
     constexpr int Q = N / 2 + 1;
+    constexpr int E = C::E;
     const int c = threadIdx.x % C::CW, theta = threadIdx.x / C::CW;
+    const SyncBlock sync;
     const int kx = blockIdx.x * C::CW + c, b = blockIdx.y;
     const int ax = min(kx, N - kx);
     cpx* sm = smem + c * C::LSTRIDE;
-    cpx acc[FFT_E];
+    cpx acc[E];
 #pragma unroll
-    for (int m = 0; m < FFT_E; m++) acc[m] = make_float2(0.f, 0.f);
+    for (int m = 0; m < E; m++) acc[m] = make_float2(0.f, 0.f);
     bool any = false;
     for (int z = 0; z < nZ; z++) {
         const int* rp = rowptr + (size_t)b * rp_stride + (size_t)(slice * nZ + z) * N;
         if (rp[N] == rp[0]) continue;  // species absent from this slice (CTA-uniform)
         any = true;
         const cpx* Az = A + (size_t)(b * nZ + z) * N * N + kx;
-        cpx x[FFT_E];
+        cpx x[E];
 #pragma unroll
-        for (int m = 0; m < FFT_E; m++) {
+        for (int m = 0; m < E; m++) {
             const int y = theta + m * C::T;
             x[m] = (rp[y + 1] > rp[y]) ? Az[(size_t)y * N] : make_float2(0.f, 0.f);
         }
-        fft_line<N, -1>(x, sm, theta, tw);
+        fft_line<N, E, -1>(x, sm, theta, tw, sync);
         const float* G = Gq + (size_t)z * Q * Q + ax;
 #pragma unroll
-        for (int m = 0; m < FFT_E; m++) {
+        for (int m = 0; m < E; m++) {
             const int ky = theta + m * C::T;
             const float gz = __ldg(G + min(ky, N - ky) * Q);
             acc[m].x += x[m].x * gz;
             acc[m].y += x[m].y * gz;
         }
     }
-    if (any) fft_line<N, 1>(acc, sm, theta, tw);
+    if (any) fft_line<N, E, 1>(acc, sm, theta, tw, sync);
     cpx* out = B + (size_t)b * N * N + kx;
 #pragma unroll
-    for (int m = 0; m < FFT_E; m++) out[(size_t)(theta + m * C::T) * N] = acc[m];
+    for (int m = 0; m < E; m++) out[(size_t)(theta + m * C::T) * N] = acc[m];
 }
 
 void launch_potential_cols(const SweepGeom& g, cpx* B, const cpx* A, const float* Gq,
@@ -232,27 +250,31 @@ k_transmit_rows(cpx* __restrict__ W, cpx* __restrict__ Vout, int lo_end, int hi_
 {
     using C = RowCfg<N>;
     extern __shared__ cpx smem[];
+    constexpr int E = C::E;
     const int line = threadIdx.x / C::T, theta = threadIdx.x % C::T;
+    const RowSync<N> sync(line);
     const size_t rowoff = ((size_t)blockIdx.y * N + blockIdx.x * C::RPB + line) * N;
     cpx* sm = smem + line * C::LSTRIDE;
-    cpx x[FFT_E];
+    cpx x[E];
 #pragma unroll
-    for (int m = 0; m < FFT_E; m++) x[m] = W[rowoff + theta + m * C::T];
-    fft_line<N, 1>(x, sm, theta, tw);
+    for (int m = 0; m < E; m++) x[m] = W[rowoff + theta + m * C::T];
+    fft_line<N, E, 1>(x, sm, theta, tw, sync);
     if (Vout) {
 #pragma unroll
-        for (int m = 0; m < FFT_E; m++) Vout[rowoff + theta + m * C::T] = x[m];
+        for (int m = 0; m < E; m++) Vout[rowoff + theta + m * C::T] = x[m];
     }
     // potential2Transmission, src/multisliceSimulation.cu:41-52
 #pragma unroll
-    for (int m = 0; m < FFT_E; m++) {
+    for (int m = 0; m < E; m++) {
         const float Vx = x[m].x, Vy = x[m].y;
         const float e = expf(-Vy);
-        x[m] = make_float2(e * cosf(Vx), e * sinf(Vx));
+        float sn, cs;
+        sincosf(Vx, &sn, &cs);
+        x[m] = make_float2(e * cs, e * sn);
     }
-    fft_line<N, -1>(x, sm, theta, tw);
+    fft_line<N, E, -1>(x, sm, theta, tw, sync);
 #pragma unroll
-    for (int m = 0; m < FFT_E; m++) {
+    for (int m = 0; m < E; m++) {
         const int kx = theta + m * C::T;
         if (in_band(kx, lo_end, hi_start)) W[rowoff + kx] = x[m];
     }
@@ -278,28 +300,30 @@ k_bandlimit_cols(cpx* __restrict__ W, int lo_end, int hi_start, const cpx* __res
 {
     using C = ColCfg<N, false>;
     extern __shared__ cpx smem[];
+    constexpr int E = C::E;
     const int c = threadIdx.x % C::CW, theta = threadIdx.x / C::CW;
+    const SyncBlock sync;
     const int kx = band_col0(blockIdx.x * C::CW, lo_end, hi_start) + c;
     cpx* sm = smem + c * C::LSTRIDE;
     cpx* col = W + (size_t)blockIdx.y * N * N + kx;
-    cpx x[FFT_E];
+    cpx x[E];
 #pragma unroll
-    for (int m = 0; m < FFT_E; m++) x[m] = col[(size_t)(theta + m * C::T) * N];
-    fft_line<N, -1>(x, sm, theta, tw);
+    for (int m = 0; m < E; m++) x[m] = col[(size_t)(theta + m * C::T) * N];
+    fft_line<N, E, -1>(x, sm, theta, tw, sync);
     // zeroHighFreq (src/multisliceSimulation.cu:225-250) and the 1/N of bandwidthLimit (:558-559)
     const int i1 = kx > N / 2 ? kx - N : kx;
     const float mind = (float)N;
     const float alpha = 1.f / ((float)(N * N));
 #pragma unroll
-    for (int m = 0; m < FFT_E; m++) {
+    for (int m = 0; m < E; m++) {
         const int ky = theta + m * C::T;
         const int i2 = ky > N / 2 ? ky - N : ky;
         const bool cut = ((float)(i1 * i1 + i2 * i2) * 9.f / (mind * mind)) > 1.f;
         x[m] = cut ? make_float2(0.f, 0.f) : make_float2(x[m].x * alpha, x[m].y * alpha);
     }
-    fft_line<N, 1>(x, sm, theta, tw);
+    fft_line<N, E, 1>(x, sm, theta, tw, sync);
 #pragma unroll
-    for (int m = 0; m < FFT_E; m++) col[(size_t)(theta + m * C::T) * N] = x[m];
+    for (int m = 0; m < E; m++) col[(size_t)(theta + m * C::T) * N] = x[m];
 }
 
 void launch_bandlimit_cols(const SweepGeom& g, cpx* W, int batch, cudaStream_t st)
@@ -318,31 +342,41 @@ void launch_bandlimit_cols(const SweepGeom& g, cpx* W, int batch, cudaStream_t s
 // =============================================================================================
 template <int N>
 __global__ void __launch_bounds__(RowCfg<N>::THREADS)
-k_multiply_rows(cpx* __restrict__ Psi, const cpx* __restrict__ E, size_t e_batch_stride,
+k_multiply_rows(cpx* __restrict__ Psi, const cpx* __restrict__ Tk, size_t e_batch_stride,
                 int lo_end, int hi_start, int psi_full, const cpx* __restrict__ tw)
 {
     using C = RowCfg<N>;
     extern __shared__ cpx smem[];
+    constexpr int E = C::E;
     const int line = threadIdx.x / C::T, theta = threadIdx.x % C::T;
+    const RowSync<N> sync(line);
     const size_t row = (size_t)blockIdx.x * C::RPB + line;
-    const cpx* e = E + (size_t)blockIdx.y * e_batch_stride + row * N;
+    const cpx* e = Tk + (size_t)blockIdx.y * e_batch_stride + row * N;
     cpx* p = Psi + ((size_t)blockIdx.y * N + row) * N;
     cpx* sm = smem + line * C::LSTRIDE;
-    cpx t[FFT_E], x[FFT_E];
+    // t = IFFT_row(Tk) is parked in shared memory while psi is transformed (two register sets of
+    // E points each would not fit)
+    cpx* park = smem + C::RPB * C::LSTRIDE + line * N;
+    cpx x[E];
 #pragma unroll
-    for (int m = 0; m < FFT_E; m++) {
+    for (int m = 0; m < E; m++) {
         const int kx = theta + m * C::T;
-        const bool ib = in_band(kx, lo_end, hi_start);
-        t[m] = ib ? e[kx] : make_float2(0.f, 0.f);
-        x[m] = (ib || psi_full) ? p[kx] : make_float2(0.f, 0.f);
+        x[m] = in_band(kx, lo_end, hi_start) ? e[kx] : make_float2(0.f, 0.f);
     }
-    fft_line<N, 1>(t, sm, theta, tw);
-    fft_line<N, 1>(x, sm, theta, tw);
+    fft_line<N, E, 1>(x, sm, theta, tw, sync);
 #pragma unroll
-    for (int m = 0; m < FFT_E; m++) x[m] = mul3(t[m], x[m]);
-    fft_line<N, -1>(x, sm, theta, tw);
+    for (int m = 0; m < E; m++) park[theta + m * C::T] = x[m];
 #pragma unroll
-    for (int m = 0; m < FFT_E; m++) {
+    for (int m = 0; m < E; m++) {
+        const int kx = theta + m * C::T;
+        x[m] = (in_band(kx, lo_end, hi_start) || psi_full) ? p[kx] : make_float2(0.f, 0.f);
+    }
+    fft_line<N, E, 1>(x, sm, theta, tw, sync);
+#pragma unroll
+    for (int m = 0; m < E; m++) x[m] = cmul(park[theta + m * C::T], x[m]);
+    fft_line<N, E, -1>(x, sm, theta, tw, sync);
+#pragma unroll
+    for (int m = 0; m < E; m++) {
         const int kx = theta + m * C::T;
         if (in_band(kx, lo_end, hi_start)) p[kx] = x[m];
     }
@@ -353,10 +387,11 @@ void launch_multiply_rows(const SweepGeom& g, cpx* Psi, const cpx* E, size_t e_b
 {
     FDES_DISPATCH_N(g.N, {
         using C = RowCfg<NN>;
+        const size_t smem = C::SMEM + (size_t)C::RPB * NN * sizeof(cpx);
         static bool once = false;
-        if (!once) { allow_smem(k_multiply_rows<NN>, C::SMEM); once = true; }
+        if (!once) { allow_smem(k_multiply_rows<NN>, smem); once = true; }
         dim3 grid(NN / C::RPB, batch);
-        k_multiply_rows<NN><<<grid, C::THREADS, C::SMEM, st>>>(Psi, E, e_batch_stride, g.lo_end,
+        k_multiply_rows<NN><<<grid, C::THREADS, smem, st>>>(Psi, E, e_batch_stride, g.lo_end,
                                                               g.hi_start, psi_full ? 1 : 0, g.tw);
     });
 }
@@ -372,23 +407,25 @@ k_propagate_cols(cpx* __restrict__ Psi, const cpx* __restrict__ Pq, int lo_end, 
     using C = ColCfg<N, false>;
     extern __shared__ cpx smem[];
     constexpr int Q = N / 2 + 1;
+    constexpr int E = C::E;
     const int c = threadIdx.x % C::CW, theta = threadIdx.x / C::CW;
+    const SyncBlock sync;
     const int kx = band_col0(blockIdx.x * C::CW, lo_end, hi_start) + c;
     cpx* sm = smem + c * C::LSTRIDE;
     cpx* col = Psi + (size_t)blockIdx.y * N * N + kx;
-    cpx x[FFT_E];
+    cpx x[E];
 #pragma unroll
-    for (int m = 0; m < FFT_E; m++) x[m] = col[(size_t)(theta + m * C::T) * N];
-    fft_line<N, -1>(x, sm, theta, tw);
+    for (int m = 0; m < E; m++) x[m] = col[(size_t)(theta + m * C::T) * N];
+    fft_line<N, E, -1>(x, sm, theta, tw, sync);
     const cpx* P = Pq + min(kx, N - kx);
 #pragma unroll
-    for (int m = 0; m < FFT_E; m++) {
+    for (int m = 0; m < E; m++) {
         const int ky = theta + m * C::T;
-        x[m] = mul3(x[m], __ldg(P + min(ky, N - ky) * Q));
+        x[m] = cmul(x[m], __ldg(P + min(ky, N - ky) * Q));
     }
-    fft_line<N, 1>(x, sm, theta, tw);
+    fft_line<N, E, 1>(x, sm, theta, tw, sync);
 #pragma unroll
-    for (int m = 0; m < FFT_E; m++) col[(size_t)(theta + m * C::T) * N] = x[m];
+    for (int m = 0; m < E; m++) col[(size_t)(theta + m * C::T) * N] = x[m];
 }
 
 void launch_propagate_cols(const SweepGeom& g, cpx* Psi, const cpx* Pq, int batch, cudaStream_t st)
@@ -412,12 +449,14 @@ k_rows_fft(const void* __restrict__ in_, void* __restrict__ out_, RowOpts o, int
 {
     using C = RowCfg<N>;
     extern __shared__ cpx smem[];
+    constexpr int E = C::E;
     const int line = threadIdx.x / C::T, theta = threadIdx.x % C::T;
+    const RowSync<N> sync(line);
     const int y = blockIdx.x * C::RPB + line;
     const size_t rowoff = ((size_t)blockIdx.y * N + y) * N;
-    cpx x[FFT_E];
+    cpx x[E];
 #pragma unroll
-    for (int m = 0; m < FFT_E; m++) {
+    for (int m = 0; m < E; m++) {
         const int kx = theta + m * C::T;
         if (o.in_is_real)
             x[m] = make_float2(static_cast<const float*>(in_)[rowoff + kx], 0.f);
@@ -426,9 +465,9 @@ k_rows_fft(const void* __restrict__ in_, void* __restrict__ out_, RowOpts o, int
         else
             x[m] = make_float2(0.f, 0.f);
     }
-    fft_line<N, DIR>(x, smem + line * C::LSTRIDE, theta, tw);
+    fft_line<N, E, DIR>(x, smem + line * C::LSTRIDE, theta, tw, sync);
 #pragma unroll
-    for (int m = 0; m < FFT_E; m++) {
+    for (int m = 0; m < E; m++) {
         const int xx = theta + m * C::T;
         const cpx v = make_float2(x[m].x * o.scale, x[m].y * o.scale);
         if (EPI == ROW_STORE) {
@@ -494,36 +533,38 @@ k_cols_fft(const cpx* __restrict__ in, void* __restrict__ out_, const void* __re
 {
     using C = ColCfg<N, false>;
     extern __shared__ cpx smem[];
+    constexpr int E = C::E;
     const int c = threadIdx.x % C::CW, theta = threadIdx.x / C::CW;
+    const SyncBlock sync;
     const int kx = blockIdx.x * C::CW + c;
     cpx* sm = smem + c * C::LSTRIDE;
     const size_t boff = (size_t)blockIdx.y * N * N;
-    cpx x[FFT_E];
+    cpx x[E];
 #pragma unroll
-    for (int m = 0; m < FFT_E; m++) x[m] = in[boff + (size_t)(theta + m * C::T) * N + kx];
+    for (int m = 0; m < E; m++) x[m] = in[boff + (size_t)(theta + m * C::T) * N + kx];
     if (OP == COL_PLAIN) {
-        fft_line<N, DIR>(x, sm, theta, tw);
+        fft_line<N, E, DIR>(x, sm, theta, tw, sync);
         cpx* out = static_cast<cpx*>(out_);
 #pragma unroll
-        for (int m = 0; m < FFT_E; m++)
+        for (int m = 0; m < E; m++)
             out[boff + (size_t)(theta + m * C::T) * N + kx] = make_float2(x[m].x * scale, x[m].y * scale);
         return;
     }
-    fft_line<N, -1>(x, sm, theta, tw);
+    fft_line<N, E, -1>(x, sm, theta, tw, sync);
     if (OP == COL_DP_ACCUM) {
         // |fftshift(FFT psi)|^2 / N accumulated with weight (diffractionPattern,
         // src/crystalMaker.cu:714-717; cufftShift2D_h, src/complexMath.cu:510-557)
         float* out = static_cast<float*>(out_);
         const int xs = (kx + N / 2) & (N - 1);
 #pragma unroll
-        for (int m = 0; m < FFT_E; m++) {
+        for (int m = 0; m < E; m++) {
             const int ys = (theta + m * C::T + N / 2) & (N - 1);
             out[boff + (size_t)ys * N + xs] += scale * (x[m].x * x[m].x + x[m].y * x[m].y);
         }
         return;
     }
 #pragma unroll
-    for (int m = 0; m < FFT_E; m++) {
+    for (int m = 0; m < E; m++) {
         const size_t idx = (size_t)(theta + m * C::T) * N + kx;
         if (OP == COL_MUL_CPX_INV) {
             // psi * CTF as in multiplyLensFunction (src/multisliceSimulation.cu:339-340)
@@ -534,10 +575,10 @@ k_cols_fft(const cpx* __restrict__ in, void* __restrict__ out_, const void* __re
             x[m] = make_float2(x[m].x * w, x[m].y * w);
         }
     }
-    fft_line<N, 1>(x, sm, theta, tw);
+    fft_line<N, E, 1>(x, sm, theta, tw, sync);
     cpx* out = static_cast<cpx*>(out_);
 #pragma unroll
-    for (int m = 0; m < FFT_E; m++)
+    for (int m = 0; m < E; m++)
         out[boff + (size_t)(theta + m * C::T) * N + kx] = make_float2(x[m].x * scale, x[m].y * scale);
 }
 
@@ -566,6 +607,56 @@ void launch_cols_fft(const SweepGeom& g, const cpx* in, void* out, int dir, ColO
             case COL_DP_ACCUM: cols_fft_one<NN, -1, COL_DP_ACCUM>(g, in, out, table, scale, batch, st); break;
         }
     });
+}
+
+// ---------------------------------------------------------------------------------------------
+// twiddle tables (layout: fft_core.cuh) and geometry queries
+// ---------------------------------------------------------------------------------------------
+template <int N>
+static std::vector<cpx> make_twiddles_n()
+{
+    constexpr int E = LineCfg<N>::E;
+    std::vector<cpx> tw;
+    int NS = 1;
+    while (NS < N) {
+        const int rem = N / NS, R = rem >= E ? E : rem;
+        if (NS > 1)
+            for (int t = 0; t < R; t++)
+                for (int k = 0; k < NS; k++) {
+                    // exp(-2 pi i t k / (NS R)), exact on the axes
+                    const long long num = (long long)t * k, den = (long long)NS * R;
+                    const long long r = num % den;
+                    cpx w;
+                    if (r == 0) w = make_float2(1.f, 0.f);
+                    else if (4 * r == den) w = make_float2(0.f, -1.f);
+                    else if (2 * r == den) w = make_float2(-1.f, 0.f);
+                    else if (4 * r == 3 * den) w = make_float2(0.f, 1.f);
+                    else {
+                        const double a = -2.0 * 3.14159265358979323846 * (double)r / (double)den;
+                        w = make_float2((float)cos(a), (float)sin(a));
+                    }
+                    tw.push_back(w);
+                }
+        NS *= R;
+    }
+    if ((int)tw.size() != twiddle_table_elems<N, E>()) { fprintf(stderr, "fdes_b200: twiddle table size mismatch\n"); abort(); }
+    if (tw.empty()) tw.push_back(make_float2(1.f, 0.f));
+    return tw;
+}
+std::vector<cpx> make_twiddles(int N)
+{
+    FDES_DISPATCH_N(N, { return make_twiddles_n<NN>(); });
+    return {};
+}
+int rows_per_block(int N)
+{
+    FDES_DISPATCH_N(N, { return RowCfg<NN>::RPB; });
+    return 0;
+}
+int cols_per_block(int N)
+{
+    FDES_DISPATCH_N(N, { return ColCfg<NN, false>::CW; });
+    return 0;
 }
 
 }  // namespace fdes

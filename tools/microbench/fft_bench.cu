@@ -1,0 +1,186 @@
+// Developer microbenchmark for fdes_b200/csrc/fft_core.cuh: a row sweep (IFFT_row -> scale ->
+// FFT_row) and a column sweep (FFT_col -> x table -> IFFT_col) over a batch of N x N complex64
+// grids, checked against cuFFT (test tooling only) and timed with CUDA events.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -I ../../fdes_b200/csrc fft_bench.cu -lcufft -o fft_bench
+#include "fft_core.cuh"
+#include <cufft.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+using namespace fdes;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e_), __LINE__); exit(1);} } while (0)
+
+template <int N, int E>
+std::vector<cpx> make_twiddles()
+{
+    std::vector<cpx> tw;
+    int NS = 1;
+    while (NS < N) {
+        const int rem = N / NS, R = rem >= E ? E : rem;
+        if (NS > 1)
+            for (int t = 0; t < R; t++)
+                for (int k = 0; k < NS; k++) {
+                    const double a = -2.0 * M_PI * (double)t * (double)k / ((double)NS * R);
+                    tw.push_back(make_float2((float)cos(a), (float)sin(a)));
+                }
+        NS *= R;
+    }
+    if (tw.empty()) tw.push_back(make_float2(1.f, 0.f));
+    return tw;
+}
+
+template <int N, int E, int LPB>
+__global__ void __launch_bounds__(LPB * (N / E)) k_rows(cpx* __restrict__ data, const cpx* __restrict__ tw, float scale)
+{
+    constexpr int T = N / E;
+    constexpr int LS = line_smem_elems<E>(N);
+    extern __shared__ cpx smem[];
+    const int line = threadIdx.x / T, theta = threadIdx.x % T;
+    cpx* row = data + ((size_t)blockIdx.x * LPB + line) * N;
+    cpx* sm = smem + line * LS;
+    cpx x[E];
+#pragma unroll
+    for (int m = 0; m < E; m++) x[m] = row[theta + m * T];
+    if constexpr (T <= 32) {
+        fft_line<N, E, 1>(x, sm, theta, tw, SyncWarp());
+#pragma unroll
+        for (int m = 0; m < E; m++) x[m] = make_float2(x[m].x * scale, x[m].y * scale);
+        fft_line<N, E, -1>(x, sm, theta, tw, SyncWarp());
+    } else {
+        SyncNamed s{line + 1, T};
+        fft_line<N, E, 1>(x, sm, theta, tw, s);
+#pragma unroll
+        for (int m = 0; m < E; m++) x[m] = make_float2(x[m].x * scale, x[m].y * scale);
+        fft_line<N, E, -1>(x, sm, theta, tw, s);
+    }
+#pragma unroll
+    for (int m = 0; m < E; m++) row[theta + m * T] = x[m];
+}
+
+template <int N, int E, int CW>
+__global__ void __launch_bounds__(CW * (N / E)) k_cols(cpx* __restrict__ data, const cpx* __restrict__ tw,
+                                                      const cpx* __restrict__ tab)
+{
+    constexpr int T = N / E;
+    constexpr int LS = line_smem_elems<E>(N) + 16 / CW;
+    extern __shared__ cpx smem[];
+    const int c = threadIdx.x % CW, theta = threadIdx.x / CW;
+    const int kx = blockIdx.x * CW + c;
+    cpx* col = data + (size_t)blockIdx.y * N * N + kx;
+    cpx* sm = smem + c * LS;
+    cpx x[E];
+#pragma unroll
+    for (int m = 0; m < E; m++) x[m] = col[(size_t)(theta + m * T) * N];
+    fft_line<N, E, -1>(x, sm, theta, tw, SyncBlock());
+#pragma unroll
+    for (int m = 0; m < E; m++) x[m] = cmul(x[m], __ldg(tab + (size_t)(theta + m * T) * N + kx));
+    fft_line<N, E, 1>(x, sm, theta, tw, SyncBlock());
+#pragma unroll
+    for (int m = 0; m < E; m++) col[(size_t)(theta + m * T) * N] = x[m];
+}
+
+__global__ void k_scale(cpx* d, size_t n, float s) { for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = make_float2(d[i].x * s, d[i].y * s); }
+__global__ void k_mul(cpx* d, const cpx* t, size_t n, size_t nt) { for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) { cpx a = d[i], b = t[i % nt]; d[i] = make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); } }
+
+static double rel_err(const std::vector<cpx>& a, const std::vector<cpx>& b)
+{
+    double num = 0, den = 0;
+    for (size_t i = 0; i < a.size(); i++) {
+        const double dx = (double)a[i].x - b[i].x, dy = (double)a[i].y - b[i].y;
+        num += dx * dx + dy * dy;
+        den += (double)b[i].x * b[i].x + (double)b[i].y * b[i].y;
+    }
+    return sqrt(num / den);
+}
+
+template <int N, int E, int LPB, int CW>
+void run(int batch, int reps)
+{
+    const size_t NN = (size_t)N * N, total = NN * batch;
+    std::vector<cpx> h(total), tabh(NN);
+    srand(1234);
+    for (auto& v : h) v = make_float2(rand() / (float)RAND_MAX - 0.5f, rand() / (float)RAND_MAX - 0.5f);
+    for (size_t i = 0; i < NN; i++) { const float a = 0.001f * (float)(i % 977); tabh[i] = make_float2(cosf(a) / N, sinf(a) / N); }
+    cpx *d, *ref, *tab, *tw;
+    CK(cudaMalloc(&d, total * sizeof(cpx))); CK(cudaMalloc(&ref, total * sizeof(cpx))); CK(cudaMalloc(&tab, NN * sizeof(cpx)));
+    auto twh = make_twiddles<N, E>();
+    CK(cudaMalloc(&tw, twh.size() * sizeof(cpx)));
+    CK(cudaMemcpy(tw, twh.data(), twh.size() * sizeof(cpx), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(tab, tabh.data(), NN * sizeof(cpx), cudaMemcpyHostToDevice));
+    constexpr int T = N / E;
+    const size_t smem_r = (size_t)LPB * line_smem_elems<E>(N) * sizeof(cpx);
+    const size_t smem_c = (size_t)CW * (line_smem_elems<E>(N) + 16 / CW) * sizeof(cpx);
+    CK(cudaFuncSetAttribute(k_rows<N, E, LPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+    CK(cudaFuncSetAttribute(k_cols<N, E, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+    int occ_r = 0, occ_c = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, k_rows<N, E, LPB>, LPB * T, smem_r);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_cols<N, E, CW>, CW * T, smem_c);
+    cudaFuncAttributes fr, fc;
+    cudaFuncGetAttributes(&fr, k_rows<N, E, LPB>); cudaFuncGetAttributes(&fc, k_cols<N, E, CW>);
+    // ---- correctness vs cuFFT
+    cufftHandle plan_r, plan_c;
+    int n1[1] = {N};
+    cufftPlanMany(&plan_r, 1, n1, n1, 1, N, n1, 1, N, CUFFT_C2C, N * batch);          // rows
+    int inembed[1] = {N};
+    cufftPlanMany(&plan_c, 1, n1, inembed, N, 1, inembed, N, 1, CUFFT_C2C, N);          // columns of one grid
+    std::vector<cpx> got(total), want(total);
+    const float scale = 1.f / N;
+    CK(cudaMemcpy(d, h.data(), total * sizeof(cpx), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ref, h.data(), total * sizeof(cpx), cudaMemcpyHostToDevice));
+    k_rows<N, E, LPB><<<N * batch / LPB, LPB * T, smem_r>>>(d, tw, scale);
+    cufftExecC2C(plan_r, ref, ref, CUFFT_INVERSE); k_scale<<<1184, 256>>>(ref, total, scale); cufftExecC2C(plan_r, ref, ref, CUFFT_FORWARD);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(got.data(), d, total * sizeof(cpx), cudaMemcpyDeviceToHost)); CK(cudaMemcpy(want.data(), ref, total * sizeof(cpx), cudaMemcpyDeviceToHost));
+    const double er = rel_err(got, want), er0 = rel_err(got, h);
+    CK(cudaMemcpy(d, h.data(), total * sizeof(cpx), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ref, h.data(), total * sizeof(cpx), cudaMemcpyHostToDevice));
+    k_cols<N, E, CW><<<dim3(N / CW, batch), CW * T, smem_c>>>(d, tw, tab);
+    for (int b = 0; b < batch; b++) cufftExecC2C(plan_c, ref + b * NN, ref + b * NN, CUFFT_FORWARD);
+    k_mul<<<1184, 256>>>(ref, tab, total, NN);
+    for (int b = 0; b < batch; b++) cufftExecC2C(plan_c, ref + b * NN, ref + b * NN, CUFFT_INVERSE);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(got.data(), d, total * sizeof(cpx), cudaMemcpyDeviceToHost)); CK(cudaMemcpy(want.data(), ref, total * sizeof(cpx), cudaMemcpyDeviceToHost));
+    const double ec = rel_err(got, want);
+    // ---- timing
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float ms_r, ms_c;
+    for (int w = 0; w < 2; w++) {
+        cudaEventRecord(e0);
+        for (int r = 0; r < reps; r++) k_rows<N, E, LPB><<<N * batch / LPB, LPB * T, smem_r>>>(d, tw, scale);
+        cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms_r, e0, e1);
+        cudaEventRecord(e0);
+        for (int r = 0; r < reps; r++) k_cols<N, E, CW><<<dim3(N / CW, batch), CW * T, smem_c>>>(d, tw, tab);
+        cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms_c, e0, e1);
+    }
+    CK(cudaDeviceSynchronize());
+    const double gb = 16.0 * total / 1e9;
+    printf("N=%4d E=%2d LPB=%d CW=%d batch=%2d | rows: %7.2f us %6.0f GB/s regs=%3d occ=%d err=%.1e (vs id %.1e) | cols: %7.2f us %6.0f GB/s regs=%3d occ=%d err=%.1e\n",
+           N, E, LPB, CW, batch, ms_r / reps * 1e3, gb / (ms_r / reps * 1e-3), fr.numRegs, occ_r, er, er0,
+           ms_c / reps * 1e3, gb / (ms_c / reps * 1e-3), fc.numRegs, occ_c, ec);
+    cufftDestroy(plan_r); cufftDestroy(plan_c);
+    cudaFree(d); cudaFree(ref); cudaFree(tab); cudaFree(tw);
+}
+
+int main(int argc, char** argv)
+{
+    const int reps = 20;
+    run<1024, 32, 4, 8>(16, reps);
+    run<1024, 32, 8, 8>(16, reps);
+    run<1024, 32, 2, 4>(16, reps);
+    run<1024, 16, 4, 8>(16, reps);
+    run<1024, 16, 4, 4>(16, reps);
+    run<1024, 32, 4, 8>(4, reps);
+    run<1024, 16, 4, 8>(4, reps);
+    run<2048, 32, 2, 4>(4, reps);
+    run<2048, 32, 2, 8>(4, reps);
+    run<2048, 16, 2, 4>(4, reps);
+    run<4096, 32, 1, 4>(1, reps);
+    run<4096, 32, 1, 2>(1, reps);
+    run<512, 32, 8, 8>(16, reps);
+    run<512, 16, 8, 8>(16, reps);
+    run<256, 16, 16, 16>(64, reps);
+    run<64, 8, 32, 16>(256, reps);
+    return 0;
+}
