@@ -16,7 +16,7 @@ from typing import Optional
 import numpy as np
 
 _PKG = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _PKG / "lib" / "libfdes_b200.so"
+LIB_PATH = pathlib.Path(os.environ.get("FDES_B200_LIB", _PKG / "lib" / "libfdes_b200.so"))
 _lib = None
 
 

@@ -60,6 +60,45 @@ __device__ __forceinline__ cpx pfma(cpx a, cpx b, cpx c)
     return d;
 }
 
+// Loads that stay where they are written: the asm is volatile, so the compiler can neither hoist
+// them above a preceding synchronisation nor batch them ahead of the transform before them
+// (invariant / __restrict__ loads get hoisted to the top of the kernel and then pin 2 registers
+// per element across a whole FFT).
+__device__ __forceinline__ cpx ld_nc(const cpx* p)    // read-only data (tables)
+{
+    cpx v;
+    asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+// same with a compile-time element offset folded into the address (one base register for a
+// whole unrolled sequence instead of one 64-bit pointer per load)
+template <int OFF>
+__device__ __forceinline__ cpx ld_nc_at(const cpx* p)
+{
+    cpx v;
+    asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "l"(p), "n"(OFF * 8));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ float ld_nc_at(const float* p)
+{
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1+%2];" : "=f"(v) : "l"(p), "n"(OFF * 4));
+    return v;
+}
+__device__ __forceinline__ float ld_nc(const float* p)
+{
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ cpx ld_g(const cpx* p)     // data written by earlier kernels
+{
+    cpx v;
+    asm volatile("ld.global.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ cpx cadd(cpx a, cpx b) { return padd(a, b); }
 __device__ __forceinline__ cpx csub(cpx a, cpx b) { return psub(a, b); }
 // a * (c + i s): FMUL2 + FFMA2 (the scalar broadcasts and the pair swap are operand modifiers)
@@ -224,6 +263,17 @@ __host__ __device__ constexpr int twiddle_offset()
     else return (NS > 1 ? P::R * NS : 0) + twiddle_offset<N, E, NS_TARGET, NS * P::R>();
 }
 
+// v[t] *= tab[t * NS] (or its conjugate for the inverse transform), t = T0 .. R-1
+template <int R, int NS, int DIR, int T0>
+__device__ __forceinline__ void apply_pass_twiddles(cpx (&v)[R], const cpx* __restrict__ tab)
+{
+    if constexpr (T0 < R) {
+        const cpx w = ld_nc_at<T0 * NS>(tab);
+        v[T0] = DIR < 0 ? cmul(v[T0], w) : cmul_conj(v[T0], w);
+        apply_pass_twiddles<R, NS, DIR, T0 + 1>(v, tab);
+    }
+}
+
 template <int N, int E, int R, int NS, int DIR, bool LAST, class Sync>
 __device__ __forceinline__ void fft_pass(cpx (&x)[E], cpx* __restrict__ sm, int theta,
                                          const cpx* __restrict__ tw, Sync sync)
@@ -236,14 +286,7 @@ __device__ __forceinline__ void fft_pass(cpx (&x)[E], cpx* __restrict__ sm, int 
         cpx v[R];
 #pragma unroll
         for (int t = 0; t < R; t++) v[t] = x[u + t * U];
-        if constexpr (NS > 1) {
-            const cpx* tab = tw + twiddle_offset<N, E, NS>() + k;
-#pragma unroll
-            for (int t = 1; t < R; t++) {
-                const cpx w = __ldg(tab + t * NS);
-                v[t] = DIR < 0 ? cmul(v[t], w) : cmul_conj(v[t], w);
-            }
-        }
+        if constexpr (NS > 1) apply_pass_twiddles<R, NS, DIR, 1>(v, tw + twiddle_offset<N, E, NS>() + k);
         Dft<R, DIR>::run(v);
         if constexpr (LAST) {
 #pragma unroll
@@ -280,5 +323,84 @@ __device__ __forceinline__ void fft_line(cpx (&x)[E], cpx* sm, int theta, const 
     static_assert(N >= E && (N & (N - 1)) == 0, "power-of-two line length >= E");
     LinePasses<N, E, 1, DIR, Sync>::run(x, sm, theta, tw, sync);
 }
+
+// ---------------------------------------------------------------------------------------------
+// column tiles
+// ---------------------------------------------------------------------------------------------
+// Per-thread view of a column sweep: which column line it transforms, and how the CTA's tile
+// travels between global memory and the registers x[m] = f[(theta + m*T)][column].
+template <int N, int E_, int CW_, bool STAGED_>
+struct ColTile {
+    static constexpr int E = E_, T = N / E_, CW = CW_;
+    static constexpr bool STAGED = STAGED_;
+    static constexpr int THREADS = CW * T;
+    static constexpr int LSTRIDE = line_smem_elems<E>(N) + 16 / CW;   // bank-conflict-free line stride
+    static constexpr int RPI = THREADS / CW;                          // tile rows moved per iteration
+    static constexpr size_t SMEM = (size_t)CW * LSTRIDE * sizeof(cpx);
+    using C = ColTile;
+    int line, theta;     // column within the tile, position within the column
+    int lc, lr;          // staged copies: column / first row handled by this thread
+    cpx* smem;           // CTA tile buffer
+    cpx* sm;             // this column's padded line buffer
+
+    __device__ __forceinline__ explicit ColTile(cpx* smem_) : smem(smem_)
+    {
+        if constexpr (C::STAGED) { line = threadIdx.x / T; theta = threadIdx.x % T; }
+        else { line = threadIdx.x % CW; theta = threadIdx.x / CW; }
+        lc = threadIdx.x % CW;
+        lr = threadIdx.x / CW;
+        sm = smem + line * C::LSTRIDE;
+    }
+    // synchronisation among the threads that share a line buffer
+    __device__ __forceinline__ void operator()() const
+    {
+        if constexpr (C::STAGED) __syncwarp();
+        else __syncthreads();
+    }
+    // x[m] <- tile(theta + m*T, line); tile = &array[0][first column of the tile].
+    // keep(row) == false reads as zero without touching memory.  `again`: the tile buffer was
+    // used by a previous load/transform of this CTA.
+    template <class Keep>
+    __device__ __forceinline__ void load(cpx (&x)[E], const cpx* __restrict__ tile, Keep keep, bool again = false) const
+    {
+        if constexpr (C::STAGED) {
+            if (again) __syncthreads();
+            cpx v[E];
+#pragma unroll
+            for (int i = 0; i < E; i++) {
+                const int row = lr + i * C::RPI;
+                v[i] = keep(row) ? tile[(size_t)row * N + lc] : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < E; i++) smem[lc * C::LSTRIDE + smpad<E>(lr + i * C::RPI)] = v[i];
+            __syncthreads();
+#pragma unroll
+            for (int m = 0; m < E; m++) x[m] = sm[smpad<E>(theta + m * T)];
+            __syncwarp();
+        } else {
+#pragma unroll
+            for (int m = 0; m < E; m++) {
+                const int row = theta + m * T;
+                x[m] = keep(row) ? tile[(size_t)row * N + line] : make_float2(0.f, 0.f);
+            }
+        }
+    }
+    __device__ __forceinline__ void store(const cpx (&x)[E], cpx* __restrict__ tile) const
+    {
+        if constexpr (C::STAGED) {
+#pragma unroll
+            for (int m = 0; m < E; m++) sm[smpad<E>(theta + m * T)] = x[m];
+            __syncthreads();
+            cpx v[E];
+#pragma unroll
+            for (int i = 0; i < E; i++) v[i] = smem[lc * C::LSTRIDE + smpad<E>(lr + i * C::RPI)];
+#pragma unroll
+            for (int i = 0; i < E; i++) tile[(size_t)(lr + i * C::RPI) * N + lc] = v[i];
+        } else {
+#pragma unroll
+            for (int m = 0; m < E; m++) tile[(size_t)(theta + m * T) * N + line] = x[m];
+        }
+    }
+};
 
 }  // namespace fdes

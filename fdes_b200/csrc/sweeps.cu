@@ -33,6 +33,11 @@ namespace fdes {
         }                                                                                        \
     } while (0)
 
+// register budget per thread that __launch_bounds__ asks the compiler to respect
+#ifndef FDES_REG_BUDGET
+#define FDES_REG_BUDGET 128
+#endif
+
 // Points per thread for a line of N points (rows and columns use the same split, so one
 // twiddle table per grid size serves both).
 template <int N>
@@ -50,6 +55,7 @@ struct RowCfg {
     static constexpr int LSTRIDE = L::LS;
     static constexpr size_t SMEM = (size_t)RPB * LSTRIDE * sizeof(cpx);
     static constexpr bool WARP_SYNC = (T <= 32);       // a line lives inside one warp
+    static constexpr int MIN_CTAS = (65536 / FDES_REG_BUDGET) / THREADS > 0 ? (65536 / FDES_REG_BUDGET) / THREADS : 1;
 };
 // threads of one row line: warp-level sync when the line fits a warp, else a named barrier
 template <int N>
@@ -70,7 +76,30 @@ struct ColCfg {
     static constexpr int THREADS = CW * T;
     static constexpr int LSTRIDE = L::LS + 16 / CW;   // bank-conflict-free line stride
     static constexpr size_t SMEM = (size_t)CW * LSTRIDE * sizeof(cpx);
+    // Staged tiles: the CTA moves its [N rows][CW columns] tile between global and shared memory
+    // with a column-fastest thread mapping (coalesced CW*8-byte row segments), while each column
+    // is transformed by the threads of ONE warp (warp-level synchronisation inside the FFT).
+    static constexpr bool STAGED = (T <= 32);
+    static constexpr int RPI = THREADS / CW;          // tile rows moved per iteration (= T)
+    static constexpr int MIN_CTAS = (65536 / FDES_REG_BUDGET) / THREADS > 0 ? (65536 / FDES_REG_BUDGET) / THREADS : 1;
 };
+
+template <int N>
+using ColCtx = ColTile<N, LineCfg<N>::E, ColCfg<N, false>::CW, ColCfg<N, false>::STAGED>;
+// Multiply x[m] (ky = theta + m*T) by the quarter table tab[min(ky, N - ky) * Q + ax]: the first
+// half of the points sits at base_lo + m*T*Q, the second at base_hi + (N - m*T)*Q with
+// base_lo = tab + ax + theta*Q and base_hi = tab + ax - theta*Q -- compile-time offsets.
+template <int N, int E, int M, class TabT, class F>
+__device__ __forceinline__ void quarter_table_apply(cpx (&x)[E], const TabT* lo, const TabT* hi, F f)
+{
+    constexpr int T = N / E, Q = N / 2 + 1;
+    if constexpr (M < E) {
+        if constexpr (M < E / 2) x[M] = f(x[M], ld_nc_at<M * T * Q>(lo));
+        else x[M] = f(x[M], ld_nc_at<(N - M * T) * Q>(hi));
+        quarter_table_apply<N, E, M + 1>(x, lo, hi, f);
+    }
+}
+struct KeepAll { __device__ __forceinline__ bool operator()(int) const { return true; } };
 
 bool fft_size_supported(int N)
 {
@@ -122,7 +151,7 @@ static int band_cols(const SweepGeom& g)
 // S1  density rows
 // =============================================================================================
 template <int N>
-__global__ void __launch_bounds__(RowCfg<N>::THREADS)
+__global__ void __launch_bounds__(RowCfg<N>::THREADS, RowCfg<N>::MIN_CTAS)
 k_density_rows(cpx* __restrict__ A, const int* __restrict__ rowptr, const int* __restrict__ rec_col,
                const float* __restrict__ rec_w, int slice, int nZ, size_t rec_stride,
                size_t rp_stride, float imPot, const cpx* __restrict__ tw)
@@ -181,7 +210,7 @@ void launch_density_rows(const SweepGeom& g, cpx* A, const int* rowptr, const in
 // S2  potential columns
 // =============================================================================================
 template <int N>
-__global__ void __launch_bounds__(ColCfg<N, true>::THREADS)
+__global__ void __launch_bounds__(ColCfg<N, true>::THREADS, ColCfg<N, true>::MIN_CTAS)
 k_potential_cols(cpx* __restrict__ B, const cpx* __restrict__ A, const float* __restrict__ Gq,
                  const int* __restrict__ rowptr, int slice, int nZ, size_t rp_stride,
                  const cpx* __restrict__ tw)
@@ -190,11 +219,10 @@ k_potential_cols(cpx* __restrict__ B, const cpx* __restrict__ A, const float* __
     extern __shared__ cpx smem[];
     constexpr int Q = N / 2 + 1;
     constexpr int E = C::E;
-    const int c = threadIdx.x % C::CW, theta = threadIdx.x / C::CW;
-    const SyncBlock sync;
-    const int kx = blockIdx.x * C::CW + c, b = blockIdx.y;
+    const ColCtx<N> ctx(smem);
+    const int theta = ctx.theta;
+    const int kx0 = blockIdx.x * C::CW, kx = kx0 + ctx.line, b = blockIdx.y;
     const int ax = min(kx, N - kx);
-    cpx* sm = smem + c * C::LSTRIDE;
     cpx acc[E];
 #pragma unroll
     for (int m = 0; m < E; m++) acc[m] = make_float2(0.f, 0.f);
@@ -202,28 +230,21 @@ k_potential_cols(cpx* __restrict__ B, const cpx* __restrict__ A, const float* __
     for (int z = 0; z < nZ; z++) {
         const int* rp = rowptr + (size_t)b * rp_stride + (size_t)(slice * nZ + z) * N;
         if (rp[N] == rp[0]) continue;  // species absent from this slice (CTA-uniform)
-        any = true;
-        const cpx* Az = A + (size_t)(b * nZ + z) * N * N + kx;
+        const cpx* Az = A + (size_t)(b * nZ + z) * N * N + kx0;
         cpx x[E];
-#pragma unroll
-        for (int m = 0; m < E; m++) {
-            const int y = theta + m * C::T;
-            x[m] = (rp[y + 1] > rp[y]) ? Az[(size_t)y * N] : make_float2(0.f, 0.f);
-        }
-        fft_line<N, E, -1>(x, sm, theta, tw, sync);
+        // rows without deposits were not written by S1: read them as zero
+        ctx.load(x, Az, [rp](int y) { return rp[y + 1] > rp[y]; }, any);
+        any = true;
+        fft_line<N, E, -1>(x, ctx.sm, theta, tw, ctx);
         const float* G = Gq + (size_t)z * Q * Q + ax;
+        // acc += x * G  (tmp holds x * G; the accumulate stays a separate packed add)
+        quarter_table_apply<N, E, 0>(x, G + theta * Q, G - theta * Q,
+                                     [](cpx v, float gz) { return pmul(v, make_float2(gz, gz)); });
 #pragma unroll
-        for (int m = 0; m < E; m++) {
-            const int ky = theta + m * C::T;
-            const float gz = __ldg(G + min(ky, N - ky) * Q);
-            acc[m].x += x[m].x * gz;
-            acc[m].y += x[m].y * gz;
-        }
+        for (int m = 0; m < E; m++) acc[m] = padd(acc[m], x[m]);
     }
-    if (any) fft_line<N, E, 1>(acc, sm, theta, tw, sync);
-    cpx* out = B + (size_t)b * N * N + kx;
-#pragma unroll
-    for (int m = 0; m < E; m++) out[(size_t)(theta + m * C::T) * N] = acc[m];
+    if (any) fft_line<N, E, 1>(acc, ctx.sm, theta, tw, ctx);
+    ctx.store(acc, B + (size_t)b * N * N + kx0);
 }
 
 void launch_potential_cols(const SweepGeom& g, cpx* B, const cpx* A, const float* Gq,
@@ -244,7 +265,7 @@ void launch_potential_cols(const SweepGeom& g, cpx* B, const cpx* A, const float
 // S3  transmission rows
 // =============================================================================================
 template <int N>
-__global__ void __launch_bounds__(RowCfg<N>::THREADS)
+__global__ void __launch_bounds__(RowCfg<N>::THREADS, RowCfg<N>::MIN_CTAS)
 k_transmit_rows(cpx* __restrict__ W, cpx* __restrict__ Vout, int lo_end, int hi_start,
                 const cpx* __restrict__ tw)
 {
@@ -295,21 +316,19 @@ void launch_transmit_rows(const SweepGeom& g, cpx* W, cpx* Vout, int batch, cuda
 // S4  band-limit columns
 // =============================================================================================
 template <int N>
-__global__ void __launch_bounds__(ColCfg<N, false>::THREADS)
+__global__ void __launch_bounds__(ColCfg<N, false>::THREADS, ColCfg<N, false>::MIN_CTAS)
 k_bandlimit_cols(cpx* __restrict__ W, int lo_end, int hi_start, const cpx* __restrict__ tw)
 {
     using C = ColCfg<N, false>;
     extern __shared__ cpx smem[];
     constexpr int E = C::E;
-    const int c = threadIdx.x % C::CW, theta = threadIdx.x / C::CW;
-    const SyncBlock sync;
-    const int kx = band_col0(blockIdx.x * C::CW, lo_end, hi_start) + c;
-    cpx* sm = smem + c * C::LSTRIDE;
-    cpx* col = W + (size_t)blockIdx.y * N * N + kx;
+    const ColCtx<N> ctx(smem);
+    const int theta = ctx.theta;
+    const int kx0 = band_col0(blockIdx.x * C::CW, lo_end, hi_start), kx = kx0 + ctx.line;
+    cpx* tile = W + (size_t)blockIdx.y * N * N + kx0;
     cpx x[E];
-#pragma unroll
-    for (int m = 0; m < E; m++) x[m] = col[(size_t)(theta + m * C::T) * N];
-    fft_line<N, E, -1>(x, sm, theta, tw, sync);
+    ctx.load(x, tile, KeepAll());
+    fft_line<N, E, -1>(x, ctx.sm, theta, tw, ctx);
     // zeroHighFreq (src/multisliceSimulation.cu:225-250) and the 1/N of bandwidthLimit (:558-559)
     const int i1 = kx > N / 2 ? kx - N : kx;
     const float mind = (float)N;
@@ -321,9 +340,8 @@ k_bandlimit_cols(cpx* __restrict__ W, int lo_end, int hi_start, const cpx* __res
         const bool cut = ((float)(i1 * i1 + i2 * i2) * 9.f / (mind * mind)) > 1.f;
         x[m] = cut ? make_float2(0.f, 0.f) : make_float2(x[m].x * alpha, x[m].y * alpha);
     }
-    fft_line<N, E, 1>(x, sm, theta, tw, sync);
-#pragma unroll
-    for (int m = 0; m < E; m++) col[(size_t)(theta + m * C::T) * N] = x[m];
+    fft_line<N, E, 1>(x, ctx.sm, theta, tw, ctx);
+    ctx.store(x, tile);
 }
 
 void launch_bandlimit_cols(const SweepGeom& g, cpx* W, int batch, cudaStream_t st)
@@ -341,7 +359,7 @@ void launch_bandlimit_cols(const SweepGeom& g, cpx* W, int batch, cudaStream_t s
 // S5  multiply rows
 // =============================================================================================
 template <int N>
-__global__ void __launch_bounds__(RowCfg<N>::THREADS)
+__global__ void __launch_bounds__(RowCfg<N>::THREADS, RowCfg<N>::MIN_CTAS)
 k_multiply_rows(cpx* __restrict__ Psi, const cpx* __restrict__ Tk, size_t e_batch_stride,
                 int lo_end, int hi_start, int psi_full, const cpx* __restrict__ tw)
 {
@@ -369,7 +387,7 @@ k_multiply_rows(cpx* __restrict__ Psi, const cpx* __restrict__ Tk, size_t e_batc
 #pragma unroll
     for (int m = 0; m < E; m++) {
         const int kx = theta + m * C::T;
-        x[m] = (in_band(kx, lo_end, hi_start) || psi_full) ? p[kx] : make_float2(0.f, 0.f);
+        x[m] = (in_band(kx, lo_end, hi_start) || psi_full) ? ld_g(p + kx) : make_float2(0.f, 0.f);
     }
     fft_line<N, E, 1>(x, sm, theta, tw, sync);
 #pragma unroll
@@ -400,7 +418,7 @@ void launch_multiply_rows(const SweepGeom& g, cpx* Psi, const cpx* E, size_t e_b
 // S6  propagate columns
 // =============================================================================================
 template <int N>
-__global__ void __launch_bounds__(ColCfg<N, false>::THREADS)
+__global__ void __launch_bounds__(ColCfg<N, false>::THREADS, ColCfg<N, false>::MIN_CTAS)
 k_propagate_cols(cpx* __restrict__ Psi, const cpx* __restrict__ Pq, int lo_end, int hi_start,
                  const cpx* __restrict__ tw)
 {
@@ -408,24 +426,17 @@ k_propagate_cols(cpx* __restrict__ Psi, const cpx* __restrict__ Pq, int lo_end, 
     extern __shared__ cpx smem[];
     constexpr int Q = N / 2 + 1;
     constexpr int E = C::E;
-    const int c = threadIdx.x % C::CW, theta = threadIdx.x / C::CW;
-    const SyncBlock sync;
-    const int kx = band_col0(blockIdx.x * C::CW, lo_end, hi_start) + c;
-    cpx* sm = smem + c * C::LSTRIDE;
-    cpx* col = Psi + (size_t)blockIdx.y * N * N + kx;
+    const ColCtx<N> ctx(smem);
+    const int theta = ctx.theta;
+    const int kx0 = band_col0(blockIdx.x * C::CW, lo_end, hi_start), kx = kx0 + ctx.line;
+    cpx* tile = Psi + (size_t)blockIdx.y * N * N + kx0;
     cpx x[E];
-#pragma unroll
-    for (int m = 0; m < E; m++) x[m] = col[(size_t)(theta + m * C::T) * N];
-    fft_line<N, E, -1>(x, sm, theta, tw, sync);
+    ctx.load(x, tile, KeepAll());
+    fft_line<N, E, -1>(x, ctx.sm, theta, tw, ctx);
     const cpx* P = Pq + min(kx, N - kx);
-#pragma unroll
-    for (int m = 0; m < E; m++) {
-        const int ky = theta + m * C::T;
-        x[m] = cmul(x[m], __ldg(P + min(ky, N - ky) * Q));
-    }
-    fft_line<N, E, 1>(x, sm, theta, tw, sync);
-#pragma unroll
-    for (int m = 0; m < E; m++) col[(size_t)(theta + m * C::T) * N] = x[m];
+    quarter_table_apply<N, E, 0>(x, P + theta * Q, P - theta * Q, [](cpx v, cpx p) { return cmul(v, p); });
+    fft_line<N, E, 1>(x, ctx.sm, theta, tw, ctx);
+    ctx.store(x, tile);
 }
 
 void launch_propagate_cols(const SweepGeom& g, cpx* Psi, const cpx* Pq, int batch, cudaStream_t st)
@@ -443,7 +454,7 @@ void launch_propagate_cols(const SweepGeom& g, cpx* Psi, const cpx* Pq, int batc
 // generic row sweep
 // =============================================================================================
 template <int N, int DIR, int EPI>
-__global__ void __launch_bounds__(RowCfg<N>::THREADS)
+__global__ void __launch_bounds__(RowCfg<N>::THREADS, RowCfg<N>::MIN_CTAS)
 k_rows_fft(const void* __restrict__ in_, void* __restrict__ out_, RowOpts o, int lo_end,
            int hi_start, const cpx* __restrict__ tw)
 {
@@ -527,30 +538,27 @@ void launch_rows_fft(const SweepGeom& g, const void* in, void* out, int dir, Row
 // generic column sweep
 // =============================================================================================
 template <int N, int DIR, int OP>
-__global__ void __launch_bounds__(ColCfg<N, false>::THREADS)
+__global__ void __launch_bounds__(ColCfg<N, false>::THREADS, ColCfg<N, false>::MIN_CTAS)
 k_cols_fft(const cpx* __restrict__ in, void* __restrict__ out_, const void* __restrict__ table,
            float scale, const cpx* __restrict__ tw)
 {
     using C = ColCfg<N, false>;
     extern __shared__ cpx smem[];
     constexpr int E = C::E;
-    const int c = threadIdx.x % C::CW, theta = threadIdx.x / C::CW;
-    const SyncBlock sync;
-    const int kx = blockIdx.x * C::CW + c;
-    cpx* sm = smem + c * C::LSTRIDE;
+    const ColCtx<N> ctx(smem);
+    const int theta = ctx.theta;
+    const int kx0 = blockIdx.x * C::CW, kx = kx0 + ctx.line;
     const size_t boff = (size_t)blockIdx.y * N * N;
     cpx x[E];
-#pragma unroll
-    for (int m = 0; m < E; m++) x[m] = in[boff + (size_t)(theta + m * C::T) * N + kx];
+    ctx.load(x, in + boff + kx0, KeepAll());
     if (OP == COL_PLAIN) {
-        fft_line<N, E, DIR>(x, sm, theta, tw, sync);
-        cpx* out = static_cast<cpx*>(out_);
+        fft_line<N, E, DIR>(x, ctx.sm, theta, tw, ctx);
 #pragma unroll
-        for (int m = 0; m < E; m++)
-            out[boff + (size_t)(theta + m * C::T) * N + kx] = make_float2(x[m].x * scale, x[m].y * scale);
+        for (int m = 0; m < E; m++) x[m] = make_float2(x[m].x * scale, x[m].y * scale);
+        ctx.store(x, static_cast<cpx*>(out_) + boff + kx0);
         return;
     }
-    fft_line<N, E, -1>(x, sm, theta, tw, sync);
+    fft_line<N, E, -1>(x, ctx.sm, theta, tw, ctx);
     if (OP == COL_DP_ACCUM) {
         // |fftshift(FFT psi)|^2 / N accumulated with weight (diffractionPattern,
         // src/crystalMaker.cu:714-717; cufftShift2D_h, src/complexMath.cu:510-557)
@@ -568,18 +576,17 @@ k_cols_fft(const cpx* __restrict__ in, void* __restrict__ out_, const void* __re
         const size_t idx = (size_t)(theta + m * C::T) * N + kx;
         if (OP == COL_MUL_CPX_INV) {
             // psi * CTF as in multiplyLensFunction (src/multisliceSimulation.cu:339-340)
-            const cpx w = __ldg(static_cast<const cpx*>(table) + idx);
+            const cpx w = ld_nc(static_cast<const cpx*>(table) + idx);
             x[m] = make_float2(w.x * x[m].x - w.y * x[m].y, w.x * x[m].y + w.y * x[m].x);
         } else {
-            const float w = __ldg(static_cast<const float*>(table) + idx);
+            const float w = ld_nc(static_cast<const float*>(table) + idx);
             x[m] = make_float2(x[m].x * w, x[m].y * w);
         }
     }
-    fft_line<N, E, 1>(x, sm, theta, tw, sync);
-    cpx* out = static_cast<cpx*>(out_);
+    fft_line<N, E, 1>(x, ctx.sm, theta, tw, ctx);
 #pragma unroll
-    for (int m = 0; m < E; m++)
-        out[boff + (size_t)(theta + m * C::T) * N + kx] = make_float2(x[m].x * scale, x[m].y * scale);
+    for (int m = 0; m < E; m++) x[m] = make_float2(x[m].x * scale, x[m].y * scale);
+    ctx.store(x, static_cast<cpx*>(out_) + boff + kx0);
 }
 
 template <int N, int DIR, int OP>

@@ -31,8 +31,8 @@ std::vector<cpx> make_twiddles()
     return tw;
 }
 
-template <int N, int E, int LPB>
-__global__ void __launch_bounds__(LPB * (N / E)) k_rows(cpx* __restrict__ data, const cpx* __restrict__ tw, float scale)
+template <int N, int E, int LPB, int MINB>
+__global__ void __launch_bounds__(LPB * (N / E), MINB) k_rows(cpx* __restrict__ data, const cpx* __restrict__ tw, float scale)
 {
     constexpr int T = N / E;
     constexpr int LS = line_smem_elems<E>(N);
@@ -59,31 +59,52 @@ __global__ void __launch_bounds__(LPB * (N / E)) k_rows(cpx* __restrict__ data, 
     for (int m = 0; m < E; m++) row[theta + m * T] = x[m];
 }
 
-template <int N, int E, int CW>
-__global__ void __launch_bounds__(CW * (N / E)) k_cols(cpx* __restrict__ data, const cpx* __restrict__ tw,
-                                                      const cpx* __restrict__ tab)
+// quad layout: 4 adjacent lines interleaved element-wise (32-byte sectors hold one position of 4 lines)
+template <int N> __device__ __forceinline__ size_t addr_quad(int line, int pos) { return (size_t)(line >> 2) * (4 * N) + 4 * pos + (line & 3); }
+template <int N, int E, int LPB, int MINB>
+__global__ void __launch_bounds__(LPB * (N / E), MINB) k_quad(const cpx* __restrict__ in, cpx* __restrict__ out, const cpx* __restrict__ tw, float scale)
 {
     constexpr int T = N / E;
-    constexpr int LS = line_smem_elems<E>(N) + 16 / CW;
+    constexpr int LS = line_smem_elems<E>(N);
     extern __shared__ cpx smem[];
-    const int c = threadIdx.x % CW, theta = threadIdx.x / CW;
-    const int kx = blockIdx.x * CW + c;
-    cpx* col = data + (size_t)blockIdx.y * N * N + kx;
-    cpx* sm = smem + c * LS;
+    const int line = threadIdx.x / T, theta = threadIdx.x % T;
+    const int l = blockIdx.x * LPB + line;
+    const size_t boff = (size_t)blockIdx.y * N * N;
+    cpx* sm = smem + line * LS;
     cpx x[E];
 #pragma unroll
-    for (int m = 0; m < E; m++) x[m] = col[(size_t)(theta + m * T) * N];
-    fft_line<N, E, -1>(x, sm, theta, tw, SyncBlock());
+    for (int m = 0; m < E; m++) x[m] = in[boff + addr_quad<N>(l, theta + m * T)];
+    fft_line<N, E, 1>(x, sm, theta, tw, SyncWarp());
 #pragma unroll
-    for (int m = 0; m < E; m++) x[m] = cmul(x[m], __ldg(tab + (size_t)(theta + m * T) * N + kx));
-    fft_line<N, E, 1>(x, sm, theta, tw, SyncBlock());
+    for (int m = 0; m < E; m++) x[m] = make_float2(x[m].x * scale, x[m].y * scale);
+    fft_line<N, E, -1>(x, sm, theta, tw, SyncWarp());
 #pragma unroll
-    for (int m = 0; m < E; m++) col[(size_t)(theta + m * T) * N] = x[m];
+    for (int m = 0; m < E; m++) out[boff + addr_quad<N>(theta + m * T, l)] = x[m];
+}
+struct KeepAll { __device__ __forceinline__ bool operator()(int) const { return true; } };
+template <int N, int E, int CW, bool STAGED, int MINB>
+__global__ void __launch_bounds__(CW * (N / E), MINB) k_cols(cpx* __restrict__ data, const cpx* __restrict__ tw,
+                                                            const cpx* __restrict__ tab)
+{
+    using Tile = ColTile<N, E, CW, STAGED>;
+    extern __shared__ cpx smem[];
+    const Tile ctx(smem);
+    const int theta = ctx.theta;
+    const int kx0 = blockIdx.x * CW, kx = kx0 + ctx.line;
+    cpx* tile = data + (size_t)blockIdx.y * N * N + kx0;
+    cpx x[E];
+    ctx.load(x, tile, KeepAll());
+    fft_line<N, E, -1>(x, ctx.sm, theta, tw, ctx);
+#pragma unroll
+    for (int m = 0; m < E; m++) x[m] = cmul(x[m], ld_nc(tab + (theta + m * Tile::T)));   // column-independent table
+    fft_line<N, E, 1>(x, ctx.sm, theta, tw, ctx);
+    ctx.store(x, tile);
 }
 
 __global__ void k_scale(cpx* d, size_t n, float s) { for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = make_float2(d[i].x * s, d[i].y * s); }
 __global__ void k_mul(cpx* d, const cpx* t, size_t n, size_t nt) { for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) { cpx a = d[i], b = t[i % nt]; d[i] = make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); } }
 
+__global__ void k_mul_rows(cpx* d, const cpx* t, size_t n, int N) { for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) { cpx a = d[i], b = t[(i / N) % N]; d[i] = make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); } }
 static double rel_err(const std::vector<cpx>& a, const std::vector<cpx>& b)
 {
     double num = 0, den = 0;
@@ -95,7 +116,7 @@ static double rel_err(const std::vector<cpx>& a, const std::vector<cpx>& b)
     return sqrt(num / den);
 }
 
-template <int N, int E, int LPB, int CW>
+template <int N, int E, int LPB, int MINBR, int CW, bool STAGED, int MINBC>
 void run(int batch, int reps)
 {
     const size_t NN = (size_t)N * N, total = NN * batch;
@@ -111,14 +132,14 @@ void run(int batch, int reps)
     CK(cudaMemcpy(tab, tabh.data(), NN * sizeof(cpx), cudaMemcpyHostToDevice));
     constexpr int T = N / E;
     const size_t smem_r = (size_t)LPB * line_smem_elems<E>(N) * sizeof(cpx);
-    const size_t smem_c = (size_t)CW * (line_smem_elems<E>(N) + 16 / CW) * sizeof(cpx);
-    CK(cudaFuncSetAttribute(k_rows<N, E, LPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
-    CK(cudaFuncSetAttribute(k_cols<N, E, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+    const size_t smem_c = ColTile<N, E, CW, STAGED>::SMEM;
+    CK(cudaFuncSetAttribute(k_rows<N, E, LPB, MINBR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+    CK(cudaFuncSetAttribute(k_cols<N, E, CW, STAGED, MINBC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
     int occ_r = 0, occ_c = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, k_rows<N, E, LPB>, LPB * T, smem_r);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_cols<N, E, CW>, CW * T, smem_c);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, k_rows<N, E, LPB, MINBR>, LPB * T, smem_r);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_cols<N, E, CW, STAGED, MINBC>, CW * T, smem_c);
     cudaFuncAttributes fr, fc;
-    cudaFuncGetAttributes(&fr, k_rows<N, E, LPB>); cudaFuncGetAttributes(&fc, k_cols<N, E, CW>);
+    cudaFuncGetAttributes(&fr, k_rows<N, E, LPB, MINBR>); cudaFuncGetAttributes(&fc, k_cols<N, E, CW, STAGED, MINBC>);
     // ---- correctness vs cuFFT
     cufftHandle plan_r, plan_c;
     int n1[1] = {N};
@@ -129,16 +150,16 @@ void run(int batch, int reps)
     const float scale = 1.f / N;
     CK(cudaMemcpy(d, h.data(), total * sizeof(cpx), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ref, h.data(), total * sizeof(cpx), cudaMemcpyHostToDevice));
-    k_rows<N, E, LPB><<<N * batch / LPB, LPB * T, smem_r>>>(d, tw, scale);
+    k_rows<N, E, LPB, MINBR><<<N * batch / LPB, LPB * T, smem_r>>>(d, tw, scale);
     cufftExecC2C(plan_r, ref, ref, CUFFT_INVERSE); k_scale<<<1184, 256>>>(ref, total, scale); cufftExecC2C(plan_r, ref, ref, CUFFT_FORWARD);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(got.data(), d, total * sizeof(cpx), cudaMemcpyDeviceToHost)); CK(cudaMemcpy(want.data(), ref, total * sizeof(cpx), cudaMemcpyDeviceToHost));
     const double er = rel_err(got, want), er0 = rel_err(got, h);
     CK(cudaMemcpy(d, h.data(), total * sizeof(cpx), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ref, h.data(), total * sizeof(cpx), cudaMemcpyHostToDevice));
-    k_cols<N, E, CW><<<dim3(N / CW, batch), CW * T, smem_c>>>(d, tw, tab);
+    k_cols<N, E, CW, STAGED, MINBC><<<dim3(N / CW, batch), CW * T, smem_c>>>(d, tw, tab);
     for (int b = 0; b < batch; b++) cufftExecC2C(plan_c, ref + b * NN, ref + b * NN, CUFFT_FORWARD);
-    k_mul<<<1184, 256>>>(ref, tab, total, NN);
+    k_mul_rows<<<1184, 256>>>(ref, tab, total, N);
     for (int b = 0; b < batch; b++) cufftExecC2C(plan_c, ref + b * NN, ref + b * NN, CUFFT_INVERSE);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(got.data(), d, total * sizeof(cpx), cudaMemcpyDeviceToHost)); CK(cudaMemcpy(want.data(), ref, total * sizeof(cpx), cudaMemcpyDeviceToHost));
@@ -148,39 +169,67 @@ void run(int batch, int reps)
     float ms_r, ms_c;
     for (int w = 0; w < 2; w++) {
         cudaEventRecord(e0);
-        for (int r = 0; r < reps; r++) k_rows<N, E, LPB><<<N * batch / LPB, LPB * T, smem_r>>>(d, tw, scale);
+        for (int r = 0; r < reps; r++) k_rows<N, E, LPB, MINBR><<<N * batch / LPB, LPB * T, smem_r>>>(d, tw, scale);
         cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms_r, e0, e1);
         cudaEventRecord(e0);
-        for (int r = 0; r < reps; r++) k_cols<N, E, CW><<<dim3(N / CW, batch), CW * T, smem_c>>>(d, tw, tab);
+        for (int r = 0; r < reps; r++) k_cols<N, E, CW, STAGED, MINBC><<<dim3(N / CW, batch), CW * T, smem_c>>>(d, tw, tab);
         cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms_c, e0, e1);
     }
     CK(cudaDeviceSynchronize());
     const double gb = 16.0 * total / 1e9;
-    printf("N=%4d E=%2d LPB=%d CW=%d batch=%2d | rows: %7.2f us %6.0f GB/s regs=%3d occ=%d err=%.1e (vs id %.1e) | cols: %7.2f us %6.0f GB/s regs=%3d occ=%d err=%.1e\n",
-           N, E, LPB, CW, batch, ms_r / reps * 1e3, gb / (ms_r / reps * 1e-3), fr.numRegs, occ_r, er, er0,
+    printf("N=%4d E=%2d LPB=%d/%d CW=%d%s/%d batch=%2d | rows: %7.2f us %6.0f GB/s regs=%3d occ=%d err=%.1e (vs id %.1e) | cols: %7.2f us %6.0f GB/s regs=%3d occ=%d err=%.1e\n",
+           N, E, LPB, MINBR, CW, STAGED ? "s" : "u", MINBC, batch, ms_r / reps * 1e3, gb / (ms_r / reps * 1e-3), fr.numRegs, occ_r, er, er0,
            ms_c / reps * 1e3, gb / (ms_c / reps * 1e-3), fc.numRegs, occ_c, ec);
     cufftDestroy(plan_r); cufftDestroy(plan_c);
     cudaFree(d); cudaFree(ref); cudaFree(tab); cudaFree(tw);
 }
 
+template <int N, int E, int LPB, int MINB>
+void run_quad(int batch, int reps)
+{
+    const size_t NN = (size_t)N * N, total = NN * batch;
+    std::vector<cpx> h(total), got(total);
+    srand(99);
+    for (auto& v : h) v = make_float2(rand() / (float)RAND_MAX - 0.5f, rand() / (float)RAND_MAX - 0.5f);
+    cpx *a, *b, *tw;
+    CK(cudaMalloc(&a, total * sizeof(cpx))); CK(cudaMalloc(&b, total * sizeof(cpx)));
+    auto twh = make_twiddles<N, E>();
+    CK(cudaMalloc(&tw, twh.size() * sizeof(cpx)));
+    CK(cudaMemcpy(tw, twh.data(), twh.size() * sizeof(cpx), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(a, h.data(), total * sizeof(cpx), cudaMemcpyHostToDevice));
+    constexpr int T = N / E;
+    const size_t smem = (size_t)LPB * line_smem_elems<E>(N) * sizeof(cpx);
+    CK(cudaFuncSetAttribute(k_quad<N, E, LPB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_quad<N, E, LPB, MINB>, LPB * T, smem);
+    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k_quad<N, E, LPB, MINB>);
+    dim3 grid(N / LPB, batch);
+    k_quad<N, E, LPB, MINB><<<grid, LPB * T, smem>>>(a, b, tw, 1.f / N);
+    k_quad<N, E, LPB, MINB><<<grid, LPB * T, smem>>>(b, a, tw, 1.f / N);   // transposed twice = identity
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(got.data(), a, total * sizeof(cpx), cudaMemcpyDeviceToHost));
+    const double err = rel_err(got, h);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float ms = 0;
+    for (int w = 0; w < 2; w++) {
+        cudaEventRecord(e0);
+        for (int r = 0; r < reps; r++) k_quad<N, E, LPB, MINB><<<grid, LPB * T, smem>>>((r & 1) ? b : a, (r & 1) ? a : b, tw, 1.f / N);
+        cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
+    }
+    printf("N=%4d E=%2d LPB=%d/%d batch=%2d | quad-transposing: %7.2f us %6.0f GB/s regs=%3d occ=%d roundtrip err=%.1e\n", N, E, LPB, MINB, batch,
+           ms / reps * 1e3, 16.0 * total / 1e9 / (ms / reps * 1e-3), fa.numRegs, occ, err);
+    cudaFree(a); cudaFree(b); cudaFree(tw);
+}
+
 int main(int argc, char** argv)
 {
     const int reps = 20;
-    run<1024, 32, 4, 8>(16, reps);
-    run<1024, 32, 8, 8>(16, reps);
-    run<1024, 32, 2, 4>(16, reps);
-    run<1024, 16, 4, 8>(16, reps);
-    run<1024, 16, 4, 4>(16, reps);
-    run<1024, 32, 4, 8>(4, reps);
-    run<1024, 16, 4, 8>(4, reps);
-    run<2048, 32, 2, 4>(4, reps);
-    run<2048, 32, 2, 8>(4, reps);
-    run<2048, 16, 2, 4>(4, reps);
-    run<4096, 32, 1, 4>(1, reps);
-    run<4096, 32, 1, 2>(1, reps);
-    run<512, 32, 8, 8>(16, reps);
-    run<512, 16, 8, 8>(16, reps);
-    run<256, 16, 16, 16>(64, reps);
-    run<64, 8, 32, 16>(256, reps);
+    run<1024, 32, 4, 1, 8, false, 1>(16, reps);
+    run_quad<1024, 32, 4, 1>(16, reps);
+    run_quad<1024, 32, 4, 4>(16, reps);
+    run_quad<1024, 32, 8, 1>(16, reps);
+    run_quad<1024, 32, 4, 1>(4, reps);
+    run_quad<1024, 32, 4, 4>(4, reps);
+    run_quad<2048, 32, 4, 1>(4, reps);
+    run_quad<512, 32, 8, 1>(16, reps);
     return 0;
 }
