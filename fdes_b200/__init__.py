@@ -38,6 +38,7 @@ def load_library() -> ctypes.CDLL:
     vp = ctypes.c_void_p
     lib.fdes_b200_last_error.restype = ctypes.c_char_p
     lib.fdes_b200_version.restype = ctypes.c_int
+    lib.fdes_b200_release_cache.restype = None
     lib.fdes_b200_open_cnf.restype = vp
     lib.fdes_b200_open_cnf.argtypes = [ctypes.c_char_p, c_f, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_int, ctypes.c_int, ctypes.c_int]

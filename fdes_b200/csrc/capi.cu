@@ -11,6 +11,8 @@
 #include <vector>
 #include <algorithm>
 #include <string>
+#include <chrono>
+#include <thread>
 
 using namespace fdes;
 
@@ -304,41 +306,58 @@ void FDES(int gpu_Index, int print_Level, char* input_name, char* image_name, ch
         fprintf(stderr, " \n printLevel error %s  \n", input_name);
         exit(EXIT_FAILURE);
     }
+    using clk = std::chrono::steady_clock;
+    const bool timing = getenv("FDES_B200_TIMING") != nullptr;
+    const auto t0 = clk::now();
     fdes_b200_sim* sim = fdes_b200_open_cnf(input_name, atomsArray, numAtoms, gpu_Index, 0, 0, 1,
                                             print_Level > 1);
     if (!sim) {
         fprintf(stderr, " \n fdes_b200: %s \n", fdes_b200_last_error());
         exit(EXIT_FAILURE);
     }
-    // side-effect file of getParams (src/paramStructure.cu:629-631)
-    write_cnf("dataFDES_used.cnf", sim->eng->params(), sim->atoms, gpu_Index);
+    const auto t1 = clk::now();
+    // side-effect file of getParams (src/paramStructure.cu:629-631), written by a helper thread
+    // while the GPU works (formatting tens of thousands of atom lines takes milliseconds)
+    std::thread cnf_writer([sim, gpu_Index] { write_cnf("dataFDES_used.cnf", sim->eng->params(), sim->atoms, gpu_Index); });
     fprintf(stderr, "  Number of atoms %d \n", sim->atoms.size());
     const Params& p = sim->eng->params();
     const size_t n123 = (size_t)p.n1 * p.n2 * p.n3, m12 = (size_t)p.m1 * p.m2;
-    std::vector<float> image(n123), ew, pot;
+    // the caller's buffer receives the images directly (exportFormedimage, src/FDESExport.cu:162)
+    std::vector<float> image_own, ew, pot;
+    float* image = dstImage;
+    if (!image) { image_own.resize(n123); image = image_own.data(); }
     if (print_Level > 1) ew.resize(2 * m12 * p.n3);
-    if (fdes_b200_simulate(sim, image.data(), ew.empty() ? nullptr : ew.data()) != 0) {
+    auto fail = [&](void) {
         fprintf(stderr, " \n fdes_b200: %s \n", fdes_b200_last_error());
+        cnf_writer.join();
         exit(EXIT_FAILURE);
-    }
+    };
+    if (fdes_b200_simulate(sim, image, ew.empty() ? nullptr : ew.data()) != 0) fail();
+    const auto t2 = clk::now();
     if (print_Level > 0) {
         pot.resize(2 * m12 * (size_t)sim->m3_orig);
-        if (fdes_b200_potential(sim, pot.data()) != 0) {
-            fprintf(stderr, " \n fdes_b200: %s \n", fdes_b200_last_error());
-            exit(EXIT_FAILURE);
-        }
+        if (fdes_b200_potential(sim, pot.data()) != 0) fail();
     }
-    if (image_name && image_name[0]) write_binary(image_name, image.data(), n123);
+    if (image_name && image_name[0]) write_binary(image_name, image, n123);
     if (emd_save_name && emd_save_name[0]) {
         // libhdf5 is not available in this build: the EMD payload is written as raw float32
         // side files next to the requested name (layout: INTEGRATION.md).
         std::string base(emd_save_name);
-        write_binary((base + ".images.f32").c_str(), image.data(), n123);
+        write_binary((base + ".images.f32").c_str(), image, n123);
         if (!ew.empty()) write_binary((base + ".exit_wave.f32").c_str(), ew.data(), ew.size());
         if (!pot.empty()) write_binary((base + ".potential_slices.f32").c_str(), pot.data(), pot.size());
     }
-    if (dstImage) memcpy(dstImage, image.data(), n123 * sizeof(float));   // exportFormedimage
+    const auto t3 = clk::now();
+    cnf_writer.join();
     fdes_b200_close(sim);
+    const auto t4 = clk::now();
+    if (timing) {
+        auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "  fdes_b200 timing [ms]: open %.2f  simulate %.2f  outputs %.2f  close %.2f  total %.2f\n",
+                ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t0, t4));
+    }
 }
+
+void fdes_b200_release_cache(void) { release_device_cache(); }
 
 }  // extern "C"

@@ -14,7 +14,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <stdexcept>
+#include <vector>
 
 namespace fdes {
 
@@ -30,10 +32,90 @@ static const KirklandRow kKirkland[103] = {
                                      " at " + __FILE__ + ":" + std::to_string(__LINE__));        \
     } while (0)
 
-template <typename T>
-static void dmalloc(T*& p, size_t n)
+// ---------------------------------------------------------------------------------------------
+// Device memory: every buffer of an Engine is a slice of ONE block, and blocks are cached per
+// process between simulations (the reference cudaMalloc/cudaFree's its buffers per call and
+// even per slice, src/crystalMaker.cu:255-265, 516-535; cudaMalloc/cudaFree of ~30 buffers cost
+// tens of milliseconds and a device synchronisation each, which would dominate a drop-in FDES()
+// call whose multislice work is a few milliseconds).
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct PoolBlock { void* ptr; size_t bytes; int device; bool in_use; };
+std::mutex g_pool_mutex;
+std::vector<PoolBlock> g_pool;
+constexpr size_t kPoolKeepBytes = (size_t)8 << 30;   // free cached blocks beyond this total
+
+void* pool_acquire(size_t bytes, int device)
 {
-    CK(cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(n, 1) * sizeof(T)));
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    int best = -1;
+    for (int i = 0; i < (int)g_pool.size(); i++) {
+        const PoolBlock& b = g_pool[i];
+        if (!b.in_use && b.device == device && b.bytes >= bytes && (best < 0 || b.bytes < g_pool[best].bytes)) best = i;
+    }
+    if (best >= 0 && g_pool[best].bytes <= 2 * bytes + ((size_t)64 << 20)) {
+        g_pool[best].in_use = true;
+        return g_pool[best].ptr;
+    }
+    const size_t granule = (size_t)32 << 20;
+    const size_t want = (bytes + granule - 1) / granule * granule;
+    void* p = nullptr;
+    cudaError_t err = cudaMalloc(&p, want);
+    if (err != cudaSuccess) {
+        // drop every cached free block of this device and retry once
+        for (auto it = g_pool.begin(); it != g_pool.end();) {
+            if (!it->in_use && it->device == device) { cudaFree(it->ptr); it = g_pool.erase(it); }
+            else ++it;
+        }
+        cudaGetLastError();
+        err = cudaMalloc(&p, want);
+    }
+    if (err != cudaSuccess)
+        throw std::runtime_error(std::string("cudaMalloc of ") + std::to_string(want >> 20) + " MiB failed: " + cudaGetErrorString(err));
+    g_pool.push_back({p, want, device, true});
+    return p;
+}
+void pool_release(void* ptr)
+{
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    size_t free_bytes = 0;
+    for (PoolBlock& b : g_pool) {
+        if (b.ptr == ptr) b.in_use = false;
+        if (!b.in_use) free_bytes += b.bytes;
+    }
+    // keep the cache bounded: free the largest idle blocks first
+    while (free_bytes > kPoolKeepBytes) {
+        int big = -1;
+        for (int i = 0; i < (int)g_pool.size(); i++)
+            if (!g_pool[i].in_use && (big < 0 || g_pool[i].bytes > g_pool[big].bytes)) big = i;
+        if (big < 0) break;
+        cudaFree(g_pool[big].ptr);
+        free_bytes -= g_pool[big].bytes;
+        g_pool.erase(g_pool.begin() + big);
+    }
+}
+// buffers are registered first, then carved out of one block
+struct ArenaPlan {
+    std::vector<std::pair<void**, size_t>> reqs;
+    template <typename T>
+    void add(T*& p, size_t n) { reqs.push_back({reinterpret_cast<void**>(&p), std::max<size_t>(n, 1) * sizeof(T)}); }
+    static size_t align(size_t b) { return (b + 255) & ~(size_t)255; }
+    size_t total() const { size_t t = 0; for (auto& r : reqs) t += align(r.second); return t; }
+    void assign(void* base) const
+    {
+        char* q = static_cast<char*>(base);
+        for (auto& r : reqs) { *r.first = q; q += align(r.second); }
+    }
+};
+}  // namespace
+
+void release_device_cache()
+{
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    for (auto it = g_pool.begin(); it != g_pool.end();) {
+        if (!it->in_use) { cudaFree(it->ptr); it = g_pool.erase(it); }
+        else ++it;
+    }
 }
 
 Engine::Engine(const Params& pin, const Atoms& atoms, const EngineOptions& opt) : p_(pin), opt_(opt)
@@ -86,22 +168,28 @@ Engine::Engine(const Params& pin, const Atoms& atoms, const EngineOptions& opt) 
     CK(cudaEventCreate(&ev1_));
 
     const size_t NN = (size_t)N_ * N_, Q = (size_t)(N_ / 2 + 1);
-    dmalloc(Pq_, Q * Q); dmalloc(Gq_, (size_t)nZ_ * Q * Q);
-    dmalloc(psi_in_, NN); dmalloc(Psi_, (size_t)B_ * NN); dmalloc(W_, (size_t)B_ * NN);
-    dmalloc(A_, (size_t)B_ * nZ_ * NN);
-    dmalloc(I_own_, NN); dmalloc(lens_, NN); dmalloc(det_, NN); dmalloc(scratch_, NN);
-    dmalloc(J_, (size_t)p_.n1 * p_.n2);
-    if (opt_.want_exitwave) dmalloc(ew_own_, NN);
+    tw_host_ = make_twiddles(N_);
+    ArenaPlan plan;
+    plan.add(tw_, tw_host_.size());
+    plan.add(Pq_, Q * Q); plan.add(Gq_, (size_t)nZ_ * Q * Q);
+    plan.add(psi_in_, NN); plan.add(Psi_, (size_t)B_ * NN); plan.add(W_, (size_t)B_ * NN);
+    plan.add(A_, (size_t)B_ * nZ_ * NN);
+    plan.add(I_own_, NN); plan.add(lens_, NN); plan.add(det_, NN); plan.add(scratch_, NN);
+    plan.add(J_, (size_t)p_.n1 * p_.n2);
+    if (opt_.want_exitwave) plan.add(ew_own_, NN);
+    plan.add(xyz0_, 3 * (size_t)nAt_); plan.add(xyzTO_, 3 * (size_t)nAt_); plan.add(xyzK_, 3 * (size_t)nAt_);
+    plan.add(xyzFP_, (size_t)B_ * 3 * nAt_); plan.add(dwf_, nAt_); plan.add(occ_, nAt_); plan.add(zidx_, nAt_);
+    plan.add(keys_, (size_t)B_ * nrec_); plan.add(cols_, (size_t)B_ * nrec_); plan.add(w_, (size_t)B_ * nrec_);
+    plan.add(keys_tmp_, nrec_); plan.add(cols_tmp_, nrec_); plan.add(w_tmp_, nrec_);
+    plan.add(rowptr_, (size_t)B_ * rp_stride_);
+    plan.add(bins_, 4 * (size_t)nAt_);
+    plan.add(hist_, 256 * (size_t)sort_num_blocks(nrec_));
+    plan.add(norm_partial_, 256); plan.add(norm_result_, 1);
+    if (p_.frPh > 0) plan.add(rng_bytes_, rng_state_bytes() * 3 * (size_t)nAt_);
+    arena_ = pool_acquire(plan.total(), opt_.gpu_index);
+    plan.assign(arena_);
+    rng_ = rng_bytes_;
     I_ = I_own_; ew_ = ew_own_;
-    dmalloc(xyz0_, 3 * (size_t)nAt_); dmalloc(xyzTO_, 3 * (size_t)nAt_); dmalloc(xyzK_, 3 * (size_t)nAt_);
-    dmalloc(xyzFP_, (size_t)B_ * 3 * nAt_); dmalloc(dwf_, nAt_); dmalloc(occ_, nAt_); dmalloc(zidx_, nAt_);
-    dmalloc(keys_, (size_t)B_ * nrec_); dmalloc(cols_, (size_t)B_ * nrec_); dmalloc(w_, (size_t)B_ * nrec_);
-    dmalloc(keys_tmp_, nrec_); dmalloc(cols_tmp_, nrec_); dmalloc(w_tmp_, nrec_);
-    dmalloc(rowptr_, (size_t)B_ * rp_stride_);
-    dmalloc(bins_, 4 * (size_t)nAt_);
-    dmalloc(hist_, 256 * (size_t)sort_num_blocks(nrec_));
-    dmalloc(norm_partial_, 256); dmalloc(norm_result_, 1);
-
     std::vector<int> zidx(nAt_);
     for (int i = 0; i < nAt_; i++)
         zidx[i] = (int)(std::find(Zlist_.begin(), Zlist_.end(), atoms.Z[i]) - Zlist_.begin());
@@ -116,7 +204,6 @@ Engine::Engine(const Params& pin, const Atoms& atoms, const EngineOptions& opt) 
     tilt(xyzTO_, p_.tilt_off[0], p_.tilt_off[1], p_.tilt_off[2]);
 
     if (p_.frPh > 0) {
-        CK(cudaMalloc(&rng_, rng_state_bytes() * 3 * (size_t)nAt_));
         launch_rng_init(rng_, 3 * nAt_, 1ULL, st_);   // seed 1, src/crystalMaker.cu:292
     }
     setup_tables();
@@ -126,10 +213,8 @@ Engine::Engine(const Params& pin, const Atoms& atoms, const EngineOptions& opt) 
 Engine::~Engine()
 {
     if (graph_) cudaGraphExecDestroy(graph_);
-    void* ptrs[] = {tw_, Pq_, Gq_, psi_in_, Psi_, W_, A_, I_own_, ew_own_, lens_, det_, scratch_, J_,
-                    xyz0_, xyzTO_, xyzK_, xyzFP_, dwf_, occ_, zidx_, rng_, keys_, keys_tmp_, cols_,
-                    cols_tmp_, w_, w_tmp_, rowptr_, bins_, hist_, norm_partial_, norm_result_};
-    for (void* q : ptrs) if (q) cudaFree(q);
+    if (st_) cudaStreamSynchronize(st_);
+    if (arena_) pool_release(arena_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
     if (st_) cudaStreamDestroy(st_);
@@ -138,10 +223,7 @@ Engine::~Engine()
 void Engine::setup_tables()
 {
     // pass twiddle tables (double precision on the host)
-    const std::vector<cpx> tw = make_twiddles(N_);
-    dmalloc(tw_, tw.size());
-    CK(cudaMemcpyAsync(tw_, tw.data(), tw.size() * sizeof(cpx), cudaMemcpyHostToDevice, st_));
-    CK(cudaStreamSynchronize(st_));
+    CK(cudaMemcpyAsync(tw_, tw_host_.data(), tw_host_.size() * sizeof(cpx), cudaMemcpyHostToDevice, st_));
 
     // 2/3 band limit: largest |i1| kept on the axis by zeroHighFreq's float test
     int kb = 0;

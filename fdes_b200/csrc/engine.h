@@ -102,6 +102,9 @@ private:
     float *xyz0_ = nullptr, *xyzTO_ = nullptr, *xyzK_ = nullptr, *xyzFP_ = nullptr, *dwf_ = nullptr, *occ_ = nullptr;
     int* zidx_ = nullptr;
     void* rng_ = nullptr;
+    unsigned char* rng_bytes_ = nullptr;
+    void* arena_ = nullptr;           // the one device block all buffers above are carved from
+    std::vector<cpx> tw_host_;
     int rng_burn_ = 0;          // normals to discard before this rank's first configuration
     uint32_t *keys_ = nullptr, *keys_tmp_ = nullptr;
     int *cols_ = nullptr, *cols_tmp_ = nullptr, *rowptr_ = nullptr, *bins_ = nullptr;
@@ -116,5 +119,8 @@ private:
     bool warmed_ = false;
     EngineTimings tm_;
 };
+
+// frees the device blocks cached between simulations (idle ones)
+void release_device_cache();
 
 }  // namespace fdes

@@ -43,6 +43,9 @@ void FDES(int gpu_Index, int print_Level, char* input_name, char* image_name, ch
 typedef struct fdes_b200_sim fdes_b200_sim;
 
 const char* fdes_b200_last_error(void);
+/* Device memory blocks are cached per process between simulations (FDES() calls included) so that
+ * repeated calls do not pay cudaMalloc/cudaFree; this returns the idle ones to the driver. */
+void fdes_b200_release_cache(void);
 int fdes_b200_version(void);
 
 /* Host-only (no CUDA call): parse a .cnf exactly as fdes_b200_open_cnf does and report what the
