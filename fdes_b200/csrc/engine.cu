@@ -172,7 +172,7 @@ Engine::Engine(const Params& pin, const Atoms& atoms, const EngineOptions& opt) 
     ArenaPlan plan;
     plan.add(tw_, tw_host_.size());
     plan.add(Pq_, Q * Q); plan.add(Gq_, (size_t)nZ_ * Q * Q);
-    plan.add(psi_in_, NN); plan.add(Psi_, (size_t)B_ * NN); plan.add(W_, (size_t)B_ * NN);
+    plan.add(psi_in_, NN); plan.add(Psi_, (size_t)B_ * NN); plan.add(W_, (size_t)B_ * NN); plan.add(D_, 2 * (size_t)B_ * NN);
     plan.add(A_, (size_t)B_ * nZ_ * NN);
     plan.add(I_own_, NN); plan.add(lens_, NN); plan.add(det_, NN); plan.add(scratch_, NN);
     plan.add(J_, (size_t)p_.n1 * p_.n2);
@@ -288,7 +288,7 @@ void Engine::make_incident(int k)
         // bandwidthLimit (:552-560): FFT2, 2/3 mask, IFFT2, 1/N -- left in row space
         ro.band_only_out = true;
         launch_rows_fft(g_, psi_in_, psi_in_, -1, ROW_STORE, ro, 1, st_);
-        launch_bandlimit_cols(g_, psi_in_, 1, st_);
+        launch_bandlimit_cols(g_, psi_in_, 1, 0, st_);
         // normalise to n1*n2 total intensity; psi = IFFT_row(Psi) => sum |psi|^2 = N * sum |Psi|^2
         launch_norm2(psi_in_, NN, norm_partial_, norm_result_, st_);
         double s = 0.0;
@@ -314,7 +314,7 @@ void Engine::make_incident(int k)
             launch_tukey_window(scratch_, N_, p_.dn1, p_.dn2, p_.cst_pi, st_);
             r3.band_only_out = true;
             launch_rows_fft(g_, scratch_, psi_in_, -1, ROW_STORE, r3, 1, st_);
-            launch_bandlimit_cols(g_, psi_in_, 1, st_);
+            launch_bandlimit_cols(g_, psi_in_, 1, 0, st_);
         } else {
             r3.scale = 1.f / (float)N_;   // row-space convention: Psi = FFT_row(psi) / N
             launch_rows_fft(g_, scratch_, psi_in_, -1, ROW_STORE, r3, 1, st_);
@@ -351,33 +351,39 @@ void Engine::prepare_config(int b, const float* xyz_k)
     bin_and_sort(b, fp);
 }
 
-void Engine::run_slices_plain(int nb, cpx* Vtrace)
+void Engine::run_slices_plain(int nb)
 {
     const size_t NN = (size_t)N_ * N_;
     const bool first_full = p_.doBeamTilt && p_.mode == 2;
-    for (int s = 0; s < p_.m3; s++) {
-        launch_density_rows(g_, A_, rowptr_, cols_, w_, s, nZ_, nb, rec_stride_, rp_stride_, p_.imPot, st_);
-        launch_potential_cols(g_, W_, A_, Gq_, rowptr_, s, nZ_, nb, rp_stride_, st_);
-        launch_transmit_rows(g_, W_, Vtrace ? Vtrace + (size_t)s * NN : nullptr, nb, st_);
-        launch_bandlimit_cols(g_, W_, nb, st_);
-        launch_multiply_rows(g_, Psi_, W_, NN, nb, first_full && s == 0, st_);
-        launch_propagate_cols(g_, Psi_, Pq_, nb, st_);
+    // The potential / transmission sweeps S1..S4 run once per PAIR of slices (the two densities
+    // share one complex transform); S5/S6 then advance the wave through the two slices in turn.
+    for (int s = 0; s < p_.m3; s += 2) {
+        const int npair = std::min(2, p_.m3 - s);
+        const int s2 = npair > 1 ? s + 1 : -1;
+        launch_density_rows(g_, A_, rowptr_, cols_, w_, s, s2, nZ_, nb, rec_stride_, rp_stride_, st_);
+        launch_potential_cols(g_, W_, A_, Gq_, rowptr_, s, s2, nZ_, nb, rp_stride_, st_);
+        launch_transmit_rows(g_, W_, D_, npair, p_.imPot, nb, st_);
+        launch_bandlimit_cols(g_, D_, nb, npair, st_);
+        for (int p = 0; p < npair; p++) {
+            launch_multiply_rows(g_, Psi_, D_ + (size_t)p * NN, 2 * NN, nb, first_full && s + p == 0, st_);
+            launch_propagate_cols(g_, Psi_, Pq_, nb, st_);
+        }
     }
     if (first_full) launch_zero_outband(Psi_, N_, g_.lo_end, g_.hi_start, nb, st_);
 }
 
-void Engine::slice_loop(int nb, cpx* Vtrace)
+void Engine::slice_loop(int nb)
 {
     tm_.slices_executed += (long long)p_.m3 * nb;
-    tm_.kernel_launches += 6LL * p_.m3;
-    if (!opt_.use_graph || Vtrace) { run_slices_plain(nb, Vtrace); return; }
+    tm_.kernel_launches += 4LL * ((p_.m3 + 1) / 2) + 2LL * p_.m3;
+    if (!opt_.use_graph) { run_slices_plain(nb); return; }
     if (!graph_ || graph_nb_ != nb) {
         if (graph_) { cudaGraphExecDestroy(graph_); graph_ = nullptr; }
         // first use of each kernel must happen outside capture (function attributes are set there)
-        if (!warmed_) { run_slices_plain(nb, nullptr); warmed_ = true; graph_nb_ = -1; return; }
+        if (!warmed_) { run_slices_plain(nb); warmed_ = true; graph_nb_ = -1; return; }
         cudaGraph_t g = nullptr;
         CK(cudaStreamBeginCapture(st_, cudaStreamCaptureModeThreadLocal));
-        run_slices_plain(nb, nullptr);
+        run_slices_plain(nb);
         CK(cudaStreamEndCapture(st_, &g));
         CK(cudaGraphInstantiate(&graph_, g, 0));
         CK(cudaGraphDestroy(g));
@@ -424,7 +430,7 @@ void Engine::accumulate_outputs(int k, int nb)
                     launch_area_mask_blend(scratch_, N_, p_.dn1, p_.dn2, st_);
                     r2.band_only_out = true;
                     launch_rows_fft(g_, scratch_, scratch_, -1, ROW_STORE, r2, 1, st_);
-                    launch_bandlimit_cols(g_, scratch_, 1, st_);
+                    launch_bandlimit_cols(g_, scratch_, 1, 0, st_);
                 } else {
                     r2.scale = 1.f / (float)N_;
                     launch_rows_fft(g_, scratch_, scratch_, -1, ROW_STORE, r2, 1, st_);
@@ -493,13 +499,14 @@ void Engine::potential_slices(float* out_host)
     bin_and_sort(0, xyzTO_);
     RowOpts ro; ro.scale = 1.f;
     for (int s = 0; s < m3_orig_; s++) {
-        launch_density_rows(g_, A_, rowptr_, cols_, w_, s, nZ_, 1, rec_stride_, rp_stride_, p_.imPot, st_);
-        launch_potential_cols(g_, W_, A_, Gq_, rowptr_, s, nZ_, 1, rp_stride_, st_);
+        launch_density_rows(g_, A_, rowptr_, cols_, w_, s, -1, nZ_, 1, rec_stride_, rp_stride_, st_);
+        launch_potential_cols(g_, W_, A_, Gq_, rowptr_, s, -1, nZ_, 1, rp_stride_, st_);
         launch_rows_fft(g_, W_, scratch_, +1, ROW_STORE, ro, 1, st_);
+        launch_absorptive_factor(scratch_, NN, p_.imPot, st_);
         CK(cudaMemcpyAsync(out_host + (size_t)s * 2 * NN, scratch_, NN * sizeof(cpx), cudaMemcpyDeviceToHost, st_));
         CK(cudaStreamSynchronize(st_));
     }
-    tm_.kernel_launches += 3LL * m3_orig_;
+    tm_.kernel_launches += 4LL * m3_orig_;
     p_ = save; nkeys_ = nkeys_save; key_bits_ = bits_save;
 }
 
@@ -530,10 +537,11 @@ void Engine::phase_grating(const float* xyz_host, int s, float* V_host)
     const size_t NN = (size_t)N_ * N_;
     CK(cudaMemcpyAsync(xyzFP_, xyz_host, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyHostToDevice, st_));
     bin_and_sort(0, xyzFP_);
-    launch_density_rows(g_, A_, rowptr_, cols_, w_, s, nZ_, 1, rec_stride_, rp_stride_, p_.imPot, st_);
-    launch_potential_cols(g_, W_, A_, Gq_, rowptr_, s, nZ_, 1, rp_stride_, st_);
+    launch_density_rows(g_, A_, rowptr_, cols_, w_, s, -1, nZ_, 1, rec_stride_, rp_stride_, st_);
+    launch_potential_cols(g_, W_, A_, Gq_, rowptr_, s, -1, nZ_, 1, rp_stride_, st_);
     RowOpts ro;
     launch_rows_fft(g_, W_, scratch_, +1, ROW_STORE, ro, 1, st_);
+    launch_absorptive_factor(scratch_, NN, p_.imPot, st_);
     CK(cudaMemcpyAsync(V_host, scratch_, NN * sizeof(cpx), cudaMemcpyDeviceToHost, st_));
     CK(cudaStreamSynchronize(st_));
 }
@@ -596,16 +604,20 @@ void Engine::time_sweeps(int k, int nb, int reps, float* ms6)
         bin_and_sort(b, fp);
         CK(cudaMemcpyAsync(Psi_ + (size_t)b * NN, psi_in_, NN * sizeof(cpx), cudaMemcpyDeviceToDevice, st_));
     }
-    const int s = p_.m3 / 2;
+    // a slice pair in the middle of the specimen; S1..S4 are timed on the pair and reported per
+    // slice (half), S5/S6 on one slice
+    const int s = std::max(0, (p_.m3 / 2) & ~1);
+    const int npair = std::min(2, p_.m3 - s);
+    const int s2 = npair > 1 ? s + 1 : -1;
     for (int i = 0; i < 6; i++) {
         for (int r = -1; r < reps; r++) {   // r = -1: untimed warm-up launch
             if (r == 0) CK(cudaEventRecord(ev0_, st_));
             switch (i) {
-                case 0: launch_density_rows(g_, A_, rowptr_, cols_, w_, s, nZ_, nb, rec_stride_, rp_stride_, p_.imPot, st_); break;
-                case 1: launch_potential_cols(g_, W_, A_, Gq_, rowptr_, s, nZ_, nb, rp_stride_, st_); break;
-                case 2: launch_transmit_rows(g_, W_, nullptr, nb, st_); break;
-                case 3: launch_bandlimit_cols(g_, W_, nb, st_); break;
-                case 4: launch_multiply_rows(g_, Psi_, W_, NN, nb, false, st_); break;
+                case 0: launch_density_rows(g_, A_, rowptr_, cols_, w_, s, s2, nZ_, nb, rec_stride_, rp_stride_, st_); break;
+                case 1: launch_potential_cols(g_, W_, A_, Gq_, rowptr_, s, s2, nZ_, nb, rp_stride_, st_); break;
+                case 2: launch_transmit_rows(g_, W_, D_, npair, p_.imPot, nb, st_); break;
+                case 3: launch_bandlimit_cols(g_, D_, nb, npair, st_); break;
+                case 4: launch_multiply_rows(g_, Psi_, D_, 2 * NN, nb, false, st_); break;
                 case 5: launch_propagate_cols(g_, Psi_, Pq_, nb, st_); break;
             }
         }
@@ -613,7 +625,7 @@ void Engine::time_sweeps(int k, int nb, int reps, float* ms6)
         CK(cudaEventSynchronize(ev1_));
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, ev0_, ev1_));
-        ms6[i] = ms / (float)reps;
+        ms6[i] = ms / (float)reps / (i < 4 ? (float)npair : 1.f);   // per slice
         tm_.kernel_launches += reps + 1;
     }
 }

@@ -82,8 +82,8 @@ private:
     void make_incident(int k);                      // psi_in_ (row space) for index k
     void prepare_config(int b, const float* xyz_k); // jitter + bin + sort + rowptr into slot b
     void bin_and_sort(int b, const float* xyz_dev);
-    void slice_loop(int nb, cpx* Vtrace = nullptr); // S1..S6 for all slices, batch nb
-    void run_slices_plain(int nb, cpx* Vtrace);
+    void slice_loop(int nb);                        // S1..S6 for all slices, batch nb
+    void run_slices_plain(int nb);
     void accumulate_outputs(int k, int nb);
     void tilt(float* xyz_dev, float t0, float t1, float t2);
 
@@ -96,7 +96,7 @@ private:
     cudaStream_t st_ = nullptr;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     // device memory
-    cpx *tw_ = nullptr, *Pq_ = nullptr, *psi_in_ = nullptr, *Psi_ = nullptr, *W_ = nullptr, *A_ = nullptr;
+    cpx *tw_ = nullptr, *Pq_ = nullptr, *psi_in_ = nullptr, *Psi_ = nullptr, *W_ = nullptr, *D_ = nullptr, *A_ = nullptr;
     cpx *ew_ = nullptr, *ew_own_ = nullptr, *lens_ = nullptr, *scratch_ = nullptr;
     float *Gq_ = nullptr, *I_ = nullptr, *I_own_ = nullptr, *det_ = nullptr, *J_ = nullptr;
     float *xyz0_ = nullptr, *xyzTO_ = nullptr, *xyzK_ = nullptr, *xyzFP_ = nullptr, *dwf_ = nullptr, *occ_ = nullptr;

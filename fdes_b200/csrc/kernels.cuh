@@ -25,18 +25,23 @@ int rows_per_block(int N);
 int cols_per_block(int N);
 
 // ---- per-slice sweeps (S1..S6) -------------------------------------------
+// The potential sweeps S1..S3 work on slice PAIRS: the densities of slice and slice2 travel as the
+// real and imaginary part of one complex field (slice2 < 0: no partner).
 // S1: per-species density rows from the sorted deposit records -> row FFT -> A
 void launch_density_rows(const SweepGeom& g, cpx* A, const int* rowptr, const int* rec_col,
-                         const float* rec_w, int slice, int nZ, int batch, size_t rec_stride,
-                         size_t rowptr_stride, float imPot, cudaStream_t st);
+                         const float* rec_w, int slice, int slice2, int nZ, int batch, size_t rec_stride,
+                         size_t rowptr_stride, cudaStream_t st);
 // S2: column FFT of every species, x scattering factor, species sum, inverse column FFT -> B
 void launch_potential_cols(const SweepGeom& g, cpx* B, const cpx* A, const float* Gq,
-                           const int* rowptr, int slice, int nZ, int batch, size_t rowptr_stride,
+                           const int* rowptr, int slice, int slice2, int nZ, int batch, size_t rowptr_stride,
                            cudaStream_t st);
-// S3: inverse row FFT -> V -> exp(iV) -> row FFT (in place on W).  Vout (may be null) receives V.
-void launch_transmit_rows(const SweepGeom& g, cpx* W, cpx* Vout, int batch, cudaStream_t st);
-// S4: column FFT -> 2/3 mask and 1/N -> inverse column FFT (in place, band columns only)
-void launch_bandlimit_cols(const SweepGeom& g, cpx* W, int batch, cudaStream_t st);
+// S3: inverse row FFT of W -> V_a + i V_b; per slice p < npair: exp(i V_p (1 + i imPot)) -> row FFT
+//     -> D[2 b + p] (band columns only)
+void launch_transmit_rows(const SweepGeom& g, const cpx* W, cpx* D, int npair, float imPot, int batch,
+                          cudaStream_t st);
+// S4: column FFT -> 2/3 mask and 1/N -> inverse column FFT (in place, band columns only) on the
+//     entries (b, p < npair) of a [batch][2] stack, or on a plain [batch] stack when npair == 0
+void launch_bandlimit_cols(const SweepGeom& g, cpx* W, int batch, int npair, cudaStream_t st);
 // S5: t = IFFT_row(E), psi = IFFT_row(Psi); Psi <- FFT_row(t * psi).  E batch stride may be 0
 //     (shared transmission stack).  psi_full: Psi may have out-of-band columns (first slice).
 void launch_multiply_rows(const SweepGeom& g, cpx* Psi, const cpx* E, size_t e_batch_stride,
@@ -104,6 +109,9 @@ void launch_fill_f32(float* p, size_t n, float v, cudaStream_t st);
 // plane wave psi = 1 in the (kx, y) domain (Psi = FFT_row(psi)/N): Psi[y][0] = 1, rest 0
 void launch_plane_wave_rowspace(cpx* Psi, int N, int batch, cudaStream_t st);
 void launch_scale_cpx(cpx* p, size_t n, float s, cudaStream_t st);
+// V <- V.x * (1 + i imPot): the absorptive factor of squareAtoms_d (src/crystalMaker.cu:100-119)
+// applied to a potential that was computed from the real density
+void launch_absorptive_factor(cpx* V, size_t n, float imPot, cudaStream_t st);
 // Psi[y][kx] = 0 for the columns outside the band (kx in [lo_end, hi_start))
 void launch_zero_outband(cpx* Psi, int N, int lo_end, int hi_start, int batch, cudaStream_t st);
 // deterministic sum of |p|^2 in double (two-stage tree); result[0] on device

@@ -205,6 +205,16 @@ __global__ void k_scale_cpx(cpx* p, size_t n, float s)
 }
 void launch_scale_cpx(cpx* p, size_t n, float s, cudaStream_t st) { k_scale_cpx<<<grid_for(n), 256, 0, st>>>(p, n, s); }
 
+__global__ void k_absorptive_factor(cpx* V, size_t n, float imPot)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        V[i] = make_float2(V[i].x, V[i].x * imPot);
+}
+void launch_absorptive_factor(cpx* V, size_t n, float imPot, cudaStream_t st)
+{
+    k_absorptive_factor<<<grid_for(n), 256, 0, st>>>(V, n, imPot);
+}
+
 __global__ void k_zero_outband(cpx* Psi, int N, int lo_end, int hi_start, size_t n)
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {

@@ -35,7 +35,7 @@ namespace fdes {
 
 // register budget per thread that __launch_bounds__ asks the compiler to respect
 #ifndef FDES_REG_BUDGET
-#define FDES_REG_BUDGET 128
+#define FDES_REG_BUDGET 255
 #endif
 
 // Points per thread for a line of N points (rows and columns use the same split, so one
@@ -150,11 +150,17 @@ static int band_cols(const SweepGeom& g)
 // =============================================================================================
 // S1  density rows
 // =============================================================================================
+// Two slices share one complex transform: the density of `slice` goes to the real part and the
+// density of `slice2` (or nothing, slice2 < 0) to the imaginary part.  The scattering-factor
+// multiplier of S2 is real and even, so the two potentials come out of S3's inverse transform as
+// the real and the imaginary part -- half the potential work per slice.  (The absorptive factor
+// (1 + i*imPot) of squareAtoms_d, src/crystalMaker.cu:100-119, is a constant complex scale of a
+// real field and is applied in S3.)
 template <int N>
 __global__ void __launch_bounds__(RowCfg<N>::THREADS, RowCfg<N>::MIN_CTAS)
 k_density_rows(cpx* __restrict__ A, const int* __restrict__ rowptr, const int* __restrict__ rec_col,
-               const float* __restrict__ rec_w, int slice, int nZ, size_t rec_stride,
-               size_t rp_stride, float imPot, const cpx* __restrict__ tw)
+               const float* __restrict__ rec_w, int slice, int slice2, int nZ, size_t rec_stride,
+               size_t rp_stride, const cpx* __restrict__ tw)
 {
     using C = RowCfg<N>;
     extern __shared__ cpx smem[];
@@ -165,26 +171,29 @@ k_density_rows(cpx* __restrict__ A, const int* __restrict__ rowptr, const int* _
     const int row = blockIdx.x * C::RPB + line;
     const int* rp = rowptr + (size_t)b * rp_stride + (size_t)(slice * nZ + z) * N;
     const int lo = rp[row], hi = rp[row + 1];
+    int lo2 = 0, hi2 = 0;
+    if (slice2 >= 0) {
+        const int* rp2 = rowptr + (size_t)b * rp_stride + (size_t)(slice2 * nZ + z) * N;
+        lo2 = rp2[row]; hi2 = rp2[row + 1];
+    }
     // rows without deposits are never read by S2 (it consults the same row pointers)
-    if (!__syncthreads_or(hi > lo)) return;
-    float* dens = reinterpret_cast<float*>(smem + C::RPB * C::LSTRIDE) + line * N;
+    if (!__syncthreads_or(hi > lo || hi2 > lo2)) return;
+    cpx* dens = smem + C::RPB * C::LSTRIDE + line * N;
 #pragma unroll
-    for (int m = 0; m < E; m++) dens[theta + m * C::T] = 0.f;
+    for (int m = 0; m < E; m++) dens[theta + m * C::T] = make_float2(0.f, 0.f);
     __syncthreads();
     if (theta == 0) {
         // sorted, stable order -> the summation order is fixed (deterministic, unlike the
         // float atomicAdd of squareAtoms_d, src/crystalMaker.cu:100-119)
         const int* cc = rec_col + (size_t)b * rec_stride;
         const float* ww = rec_w + (size_t)b * rec_stride;
-        for (int i = lo; i < hi; i++) dens[cc[i]] += ww[i];
+        for (int i = lo; i < hi; i++) dens[cc[i]].x += ww[i];
+        for (int i = lo2; i < hi2; i++) dens[cc[i]].y += ww[i];
     }
     __syncthreads();
     cpx x[E];
 #pragma unroll
-    for (int m = 0; m < E; m++) {
-        const float d = dens[theta + m * C::T];
-        x[m] = make_float2(d, d * imPot);
-    }
+    for (int m = 0; m < E; m++) x[m] = dens[theta + m * C::T];
     fft_line<N, E, -1>(x, smem + line * C::LSTRIDE, theta, tw, sync);
     cpx* out = A + ((size_t)(b * nZ + z) * N + row) * N;
 #pragma unroll
@@ -192,17 +201,17 @@ k_density_rows(cpx* __restrict__ A, const int* __restrict__ rowptr, const int* _
 }
 
 void launch_density_rows(const SweepGeom& g, cpx* A, const int* rowptr, const int* rec_col,
-                         const float* rec_w, int slice, int nZ, int batch, size_t rec_stride,
-                         size_t rowptr_stride, float imPot, cudaStream_t st)
+                         const float* rec_w, int slice, int slice2, int nZ, int batch, size_t rec_stride,
+                         size_t rowptr_stride, cudaStream_t st)
 {
     FDES_DISPATCH_N(g.N, {
         using C = RowCfg<NN>;
-        const size_t smem = C::SMEM + (size_t)C::RPB * NN * sizeof(float);
+        const size_t smem = C::SMEM + (size_t)C::RPB * NN * sizeof(cpx);
         static bool once = false;
         if (!once) { allow_smem(k_density_rows<NN>, smem); once = true; }
         dim3 grid(NN / C::RPB, nZ, batch);
-        k_density_rows<NN><<<grid, C::THREADS, smem, st>>>(A, rowptr, rec_col, rec_w, slice, nZ,
-                                                          rec_stride, rowptr_stride, imPot, g.tw);
+        k_density_rows<NN><<<grid, C::THREADS, smem, st>>>(A, rowptr, rec_col, rec_w, slice, slice2, nZ,
+                                                          rec_stride, rowptr_stride, g.tw);
     });
 }
 
@@ -212,7 +221,7 @@ void launch_density_rows(const SweepGeom& g, cpx* A, const int* rowptr, const in
 template <int N>
 __global__ void __launch_bounds__(ColCfg<N, true>::THREADS, ColCfg<N, true>::MIN_CTAS)
 k_potential_cols(cpx* __restrict__ B, const cpx* __restrict__ A, const float* __restrict__ Gq,
-                 const int* __restrict__ rowptr, int slice, int nZ, size_t rp_stride,
+                 const int* __restrict__ rowptr, int slice, int slice2, int nZ, size_t rp_stride,
                  const cpx* __restrict__ tw)
 {
     using C = ColCfg<N, true>;
@@ -229,11 +238,14 @@ k_potential_cols(cpx* __restrict__ B, const cpx* __restrict__ A, const float* __
     bool any = false;
     for (int z = 0; z < nZ; z++) {
         const int* rp = rowptr + (size_t)b * rp_stride + (size_t)(slice * nZ + z) * N;
-        if (rp[N] == rp[0]) continue;  // species absent from this slice (CTA-uniform)
+        // second slice of the pair (imaginary part); the same slice again when there is none
+        const int* rp2 = slice2 >= 0 ? rowptr + (size_t)b * rp_stride + (size_t)(slice2 * nZ + z) * N : rp;
+        if (rp[N] == rp[0] && rp2[N] == rp2[0]) continue;  // species absent from both slices (CTA-uniform)
         const cpx* Az = A + (size_t)(b * nZ + z) * N * N + kx0;
         cpx x[E];
-        // rows without deposits were not written by S1: read them as zero
-        ctx.load(x, Az, [rp](int y) { return rp[y + 1] > rp[y]; }, any);
+        // rows without deposits were not written by S1: read them as zero (branch-free test so the
+        // tile loads stay batched)
+        ctx.load(x, Az, [rp, rp2](int y) { return (rp[y + 1] > rp[y]) | (rp2[y + 1] > rp2[y]); }, any);
         any = true;
         fft_line<N, E, -1>(x, ctx.sm, theta, tw, ctx);
         const float* G = Gq + (size_t)z * Q * Q + ax;
@@ -248,7 +260,7 @@ k_potential_cols(cpx* __restrict__ B, const cpx* __restrict__ A, const float* __
 }
 
 void launch_potential_cols(const SweepGeom& g, cpx* B, const cpx* A, const float* Gq,
-                           const int* rowptr, int slice, int nZ, int batch, size_t rowptr_stride,
+                           const int* rowptr, int slice, int slice2, int nZ, int batch, size_t rowptr_stride,
                            cudaStream_t st)
 {
     FDES_DISPATCH_N(g.N, {
@@ -256,7 +268,7 @@ void launch_potential_cols(const SweepGeom& g, cpx* B, const cpx* A, const float
         static bool once = false;
         if (!once) { allow_smem(k_potential_cols<NN>, C::SMEM); once = true; }
         dim3 grid(NN / C::CW, batch);
-        k_potential_cols<NN><<<grid, C::THREADS, C::SMEM, st>>>(B, A, Gq, rowptr, slice, nZ,
+        k_potential_cols<NN><<<grid, C::THREADS, C::SMEM, st>>>(B, A, Gq, rowptr, slice, slice2, nZ,
                                                                rowptr_stride, g.tw);
     });
 }
@@ -264,51 +276,97 @@ void launch_potential_cols(const SweepGeom& g, cpx* B, const cpx* A, const float
 // =============================================================================================
 // S3  transmission rows
 // =============================================================================================
+// W holds the packed potential spectrum of a slice pair in the (kx, y) domain (S2); its inverse
+// row transform is V_a + i V_b.  For each slice of the pair: t0 = exp(i V (1 + i imPot)) and its
+// row transform goes to D[(2 b + p)], band columns only.
+// sin and cos of one argument with a compact code footprint: Cody-Waite reduction to
+// [-pi/4, pi/4] (three-term pi/2, exact products through FMA) and the Cephes single-precision
+// minimax polynomials, ~1 ulp for |x| < 1e5.  The library sincosf() inlines its Payne-Hanek slow
+// path at every call site; 64 call sites made this kernel 180 KB of code and instruction-cache
+// bound.  Arguments beyond 1e5 rad (no physical potential gets there) take one shared out-of-line
+// copy of the library routine.
+__device__ __noinline__ void sincos_large(float x, float* s, float* c) { sincosf(x, s, c); }
+__device__ __forceinline__ void sincos_compact(float x, float& sn, float& cs)
+{
+    if (fabsf(x) > 1.0e5f) { sincos_large(x, &sn, &cs); return; }
+    const float kf = rintf(x * 0.636619772f);
+    const int k = (int)kf;
+    float r = fmaf(kf, -1.57079601e+00f, x);
+    r = fmaf(kf, -3.13916473e-07f, r);
+    r = fmaf(kf, -5.39030253e-15f, r);
+    const float r2 = r * r;
+    float ps = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+    ps = fmaf(ps, r2, -1.6666654611e-1f);
+    ps = fmaf(ps * r2, r, r);                                   // sin(r)
+    float pc = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    pc = fmaf(pc, r2, 4.166664568298827e-2f);
+    pc = fmaf(pc * r2, r2, fmaf(r2, -0.5f, 1.0f));              // cos(r)
+    const float a = (k & 1) ? pc : ps;                          // quadrant rotation
+    const float b = (k & 1) ? ps : pc;
+    sn = (k & 2) ? -a : a;
+    cs = ((k + 1) & 2) ? -b : b;
+}
+template <int N>
+__device__ __forceinline__ cpx transmission(float V, float imPot)
+{
+    // potential2Transmission, src/multisliceSimulation.cu:41-52, with V.x = V and V.y = imPot * V
+    float sn, cs;
+    sincos_compact(V, sn, cs);
+    if (imPot != 0.f) {
+        const float e = __expf(-(V * imPot));
+        return make_float2(e * cs, e * sn);
+    }
+    return make_float2(cs, sn);
+}
 template <int N>
 __global__ void __launch_bounds__(RowCfg<N>::THREADS, RowCfg<N>::MIN_CTAS)
-k_transmit_rows(cpx* __restrict__ W, cpx* __restrict__ Vout, int lo_end, int hi_start,
-                const cpx* __restrict__ tw)
+k_transmit_rows(const cpx* __restrict__ W, cpx* __restrict__ D, int npair, float imPot, int lo_end,
+                int hi_start, const cpx* __restrict__ tw)
 {
     using C = RowCfg<N>;
     extern __shared__ cpx smem[];
     constexpr int E = C::E;
     const int line = threadIdx.x / C::T, theta = threadIdx.x % C::T;
     const RowSync<N> sync(line);
-    const size_t rowoff = ((size_t)blockIdx.y * N + blockIdx.x * C::RPB + line) * N;
+    const size_t row = (size_t)blockIdx.x * C::RPB + line;
+    const size_t in_off = ((size_t)blockIdx.y * N + row) * N;
     cpx* sm = smem + line * C::LSTRIDE;
+    float* park = reinterpret_cast<float*>(smem + C::RPB * C::LSTRIDE) + line * (2 * N);   // V_a | V_b
     cpx x[E];
 #pragma unroll
-    for (int m = 0; m < E; m++) x[m] = W[rowoff + theta + m * C::T];
+    for (int m = 0; m < E; m++) x[m] = W[in_off + theta + m * C::T];
     fft_line<N, E, 1>(x, sm, theta, tw, sync);
-    if (Vout) {
-#pragma unroll
-        for (int m = 0; m < E; m++) Vout[rowoff + theta + m * C::T] = x[m];
-    }
-    // potential2Transmission, src/multisliceSimulation.cu:41-52
 #pragma unroll
     for (int m = 0; m < E; m++) {
-        const float Vx = x[m].x, Vy = x[m].y;
-        const float e = expf(-Vy);
-        float sn, cs;
-        sincosf(Vx, &sn, &cs);
-        x[m] = make_float2(e * cs, e * sn);
+        park[theta + m * C::T] = x[m].x;
+        park[N + theta + m * C::T] = x[m].y;
     }
-    fft_line<N, E, -1>(x, sm, theta, tw, sync);
+    // one copy of the exp / forward-transform code for both slices of the pair
+#pragma unroll 1
+    for (int p = 0; p < npair; p++) {
+        const float* V = park + p * N;
 #pragma unroll
-    for (int m = 0; m < E; m++) {
-        const int kx = theta + m * C::T;
-        if (in_band(kx, lo_end, hi_start)) W[rowoff + kx] = x[m];
+        for (int m = 0; m < E; m++) x[m] = transmission<N>(V[theta + m * C::T], imPot);
+        fft_line<N, E, -1>(x, sm, theta, tw, sync);
+        cpx* out = D + ((size_t)(blockIdx.y * 2 + p) * N + row) * N;
+#pragma unroll
+        for (int m = 0; m < E; m++) {
+            const int kx = theta + m * C::T;
+            if (in_band(kx, lo_end, hi_start)) out[kx] = x[m];
+        }
     }
 }
 
-void launch_transmit_rows(const SweepGeom& g, cpx* W, cpx* Vout, int batch, cudaStream_t st)
+void launch_transmit_rows(const SweepGeom& g, const cpx* W, cpx* D, int npair, float imPot, int batch,
+                          cudaStream_t st)
 {
     FDES_DISPATCH_N(g.N, {
         using C = RowCfg<NN>;
+        const size_t smem = C::SMEM + (size_t)C::RPB * NN * 2 * sizeof(float);
         static bool once = false;
-        if (!once) { allow_smem(k_transmit_rows<NN>, C::SMEM); once = true; }
+        if (!once) { allow_smem(k_transmit_rows<NN>, smem); once = true; }
         dim3 grid(NN / C::RPB, batch);
-        k_transmit_rows<NN><<<grid, C::THREADS, C::SMEM, st>>>(W, Vout, g.lo_end, g.hi_start, g.tw);
+        k_transmit_rows<NN><<<grid, C::THREADS, smem, st>>>(W, D, npair, imPot, g.lo_end, g.hi_start, g.tw);
     });
 }
 
@@ -317,7 +375,7 @@ void launch_transmit_rows(const SweepGeom& g, cpx* W, cpx* Vout, int batch, cuda
 // =============================================================================================
 template <int N>
 __global__ void __launch_bounds__(ColCfg<N, false>::THREADS, ColCfg<N, false>::MIN_CTAS)
-k_bandlimit_cols(cpx* __restrict__ W, int lo_end, int hi_start, const cpx* __restrict__ tw)
+k_bandlimit_cols(cpx* __restrict__ W, int npair, int lo_end, int hi_start, const cpx* __restrict__ tw)
 {
     using C = ColCfg<N, false>;
     extern __shared__ cpx smem[];
@@ -325,7 +383,9 @@ k_bandlimit_cols(cpx* __restrict__ W, int lo_end, int hi_start, const cpx* __res
     const ColCtx<N> ctx(smem);
     const int theta = ctx.theta;
     const int kx0 = band_col0(blockIdx.x * C::CW, lo_end, hi_start), kx = kx0 + ctx.line;
-    cpx* tile = W + (size_t)blockIdx.y * N * N + kx0;
+    // entry (b, p) of a [batch][2] stack; npair = 1 uses p = 0 only, npair = 0: plain [batch]
+    const size_t entry = npair == 0 ? blockIdx.y : (size_t)(blockIdx.y / npair) * 2 + blockIdx.y % npair;
+    cpx* tile = W + entry * N * N + kx0;
     cpx x[E];
     ctx.load(x, tile, KeepAll());
     fft_line<N, E, -1>(x, ctx.sm, theta, tw, ctx);
@@ -344,14 +404,14 @@ k_bandlimit_cols(cpx* __restrict__ W, int lo_end, int hi_start, const cpx* __res
     ctx.store(x, tile);
 }
 
-void launch_bandlimit_cols(const SweepGeom& g, cpx* W, int batch, cudaStream_t st)
+void launch_bandlimit_cols(const SweepGeom& g, cpx* W, int batch, int npair, cudaStream_t st)
 {
     FDES_DISPATCH_N(g.N, {
         using C = ColCfg<NN, false>;
         static bool once = false;
         if (!once) { allow_smem(k_bandlimit_cols<NN>, C::SMEM); once = true; }
-        dim3 grid(band_cols(g) / C::CW, batch);
-        k_bandlimit_cols<NN><<<grid, C::THREADS, C::SMEM, st>>>(W, g.lo_end, g.hi_start, g.tw);
+        dim3 grid(band_cols(g) / C::CW, npair == 0 ? batch : batch * npair);
+        k_bandlimit_cols<NN><<<grid, C::THREADS, C::SMEM, st>>>(W, npair, g.lo_end, g.hi_start, g.tw);
     });
 }
 

@@ -81,6 +81,37 @@ __global__ void __launch_bounds__(LPB * (N / E), MINB) k_quad(const cpx* __restr
 #pragma unroll
     for (int m = 0; m < E; m++) out[boff + addr_quad<N>(theta + m * T, l)] = x[m];
 }
+// row lines in, transposed out through a shared-memory tile that aliases the exchange buffers
+template <int N, int E, int G, int MINB>
+__global__ void __launch_bounds__(G * (N / E), MINB) k_rowsT(const cpx* __restrict__ in, cpx* __restrict__ out, const cpx* __restrict__ tw, float scale)
+{
+    constexpr int T = N / E, THREADS = G * T;
+    constexpr int LS = line_smem_elems<E>(N);
+    constexpr int TS = G + 1;                       // tile row stride (odd: conflict-free scatter)
+    extern __shared__ cpx smem[];
+    const int line = threadIdx.x / T, theta = threadIdx.x % T;
+    const int l0 = blockIdx.x * G;
+    const size_t boff = (size_t)blockIdx.y * N * N;
+    cpx* sm = smem + line * LS;
+    cpx x[E];
+#pragma unroll
+    for (int m = 0; m < E; m++) x[m] = in[boff + (size_t)(l0 + line) * N + theta + m * T];
+    fft_line<N, E, 1>(x, sm, theta, tw, SyncWarp());
+#pragma unroll
+    for (int m = 0; m < E; m++) x[m] = make_float2(x[m].x * scale, x[m].y * scale);
+    fft_line<N, E, -1>(x, sm, theta, tw, SyncWarp());
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < E; m++) smem[(theta + m * T) * TS + line] = x[m];
+    __syncthreads();
+    const int c = threadIdx.x % G, q0 = threadIdx.x / G;
+    constexpr int QPI = THREADS / G;
+#pragma unroll 8
+    for (int i = 0; i < N / QPI; i++) {
+        const int q = q0 + i * QPI;
+        out[boff + (size_t)q * N + l0 + c] = smem[q * TS + c];
+    }
+}
 struct KeepAll { __device__ __forceinline__ bool operator()(int) const { return true; } };
 template <int N, int E, int CW, bool STAGED, int MINB>
 __global__ void __launch_bounds__(CW * (N / E), MINB) k_cols(cpx* __restrict__ data, const cpx* __restrict__ tw,
@@ -220,16 +251,55 @@ void run_quad(int batch, int reps)
     cudaFree(a); cudaFree(b); cudaFree(tw);
 }
 
+template <int N, int E, int G, int MINB>
+void run_rowsT(int batch, int reps)
+{
+    const size_t NN = (size_t)N * N, total = NN * batch;
+    std::vector<cpx> h(total), got(total);
+    srand(99);
+    for (auto& v : h) v = make_float2(rand() / (float)RAND_MAX - 0.5f, rand() / (float)RAND_MAX - 0.5f);
+    cpx *a, *b, *tw;
+    CK(cudaMalloc(&a, total * sizeof(cpx))); CK(cudaMalloc(&b, total * sizeof(cpx)));
+    auto twh = make_twiddles<N, E>();
+    CK(cudaMalloc(&tw, twh.size() * sizeof(cpx)));
+    CK(cudaMemcpy(tw, twh.data(), twh.size() * sizeof(cpx), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(a, h.data(), total * sizeof(cpx), cudaMemcpyHostToDevice));
+    constexpr int T = N / E;
+    const size_t s1 = (size_t)G * line_smem_elems<E>(N) * sizeof(cpx), s2 = (size_t)N * (G + 1) * sizeof(cpx);
+    const size_t smem = s1 > s2 ? s1 : s2;
+    CK(cudaFuncSetAttribute(k_rowsT<N, E, G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rowsT<N, E, G, MINB>, G * T, smem);
+    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k_rowsT<N, E, G, MINB>);
+    dim3 grid(N / G, batch);
+    k_rowsT<N, E, G, MINB><<<grid, G * T, smem>>>(a, b, tw, 1.f / N);
+    k_rowsT<N, E, G, MINB><<<grid, G * T, smem>>>(b, a, tw, 1.f / N);   // transposed twice = identity
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(got.data(), a, total * sizeof(cpx), cudaMemcpyDeviceToHost));
+    const double err = rel_err(got, h);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float ms = 0;
+    for (int w = 0; w < 2; w++) {
+        cudaEventRecord(e0);
+        for (int r = 0; r < reps; r++) k_rowsT<N, E, G, MINB><<<grid, G * T, smem>>>((r & 1) ? b : a, (r & 1) ? a : b, tw, 1.f / N);
+        cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
+    }
+    printf("N=%4d E=%2d G=%d/%d batch=%2d | rows-transposing: %7.2f us %6.0f GB/s regs=%3d occ=%d roundtrip err=%.1e\n", N, E, G, MINB, batch,
+           ms / reps * 1e3, 16.0 * total / 1e9 / (ms / reps * 1e-3), fa.numRegs, occ, err);
+    cudaFree(a); cudaFree(b); cudaFree(tw);
+}
+
 int main(int argc, char** argv)
 {
     const int reps = 20;
     run<1024, 32, 4, 1, 8, false, 1>(16, reps);
     run_quad<1024, 32, 4, 1>(16, reps);
-    run_quad<1024, 32, 4, 4>(16, reps);
-    run_quad<1024, 32, 8, 1>(16, reps);
-    run_quad<1024, 32, 4, 1>(4, reps);
-    run_quad<1024, 32, 4, 4>(4, reps);
-    run_quad<2048, 32, 4, 1>(4, reps);
-    run_quad<512, 32, 8, 1>(16, reps);
+    run_rowsT<1024, 32, 8, 1>(16, reps);
+    run_rowsT<1024, 32, 8, 2>(16, reps);
+    run_rowsT<1024, 32, 4, 1>(16, reps);
+    run_rowsT<1024, 32, 4, 4>(16, reps);
+    run_rowsT<1024, 32, 16, 1>(16, reps);
+    run_rowsT<1024, 32, 8, 2>(4, reps);
+    run_rowsT<1024, 32, 4, 4>(4, reps);
+    run_rowsT<512, 32, 16, 2>(16, reps);
     return 0;
 }
