@@ -37,25 +37,31 @@ void launch_rng_init(void* states, int n, unsigned long long seed, cudaStream_t 
     k_rng_init<<<(n + 127) / 128, 128, 0, st>>>(static_cast<curandState*>(states), n, seed);
 }
 
-// atomJitter_d, src/crystalMaker.cu:37-48 (out-of-place so the equilibrium copy stays intact)
+// atomJitter_d, src/crystalMaker.cu:37-48 (out-of-place so the equilibrium copy stays intact).
+// One launch draws the displacements of `nconf` consecutive configurations: thread i advances its
+// XORWOW stream by one normal per configuration, exactly like nconf successive reference launches.
 __global__ void k_atom_jitter(float* __restrict__ out, const float* __restrict__ in,
-                              const float* __restrict__ dwf, int nAt, curandState* state, int burn)
+                              const float* __restrict__ dwf, int nAt, curandState* state, int burn,
+                              int nconf)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 3 * nAt) return;
     curandState local = state[i];
     for (int b = 0; b < burn; b++) (void)curand_normal(&local);
-    float x = curand_normal(&local);
-    float v = in[i];
-    v += x * 0.112539540f * sqrtf(dwf[i / 3]);
-    out[i] = v;
+    const float base = in[i];
+    for (int c = 0; c < nconf; c++) {
+        float x = curand_normal(&local);
+        float v = base;
+        v += x * 0.112539540f * sqrtf(dwf[i / 3]);
+        out[(size_t)c * 3 * nAt + i] = v;
+    }
     state[i] = local;
 }
 void launch_atom_jitter(float* xyz_out, const float* xyz_in, const float* dwf, int nAt,
-                        void* states, int burn, cudaStream_t st)
+                        void* states, int burn, int nconf, cudaStream_t st)
 {
     k_atom_jitter<<<(3 * nAt + 127) / 128, 128, 0, st>>>(xyz_out, xyz_in, dwf, nAt,
-                                                        static_cast<curandState*>(states), burn);
+                                                        static_cast<curandState*>(states), burn, nconf);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -70,6 +76,11 @@ __global__ void k_bin_atoms(const float* __restrict__ xyz, const int* __restrict
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nAt) return;
+    // configuration blockIdx.y of a batch: coordinates [conf][nAt][3], records [conf][4 nAt]
+    xyz += (size_t)blockIdx.y * 3 * nAt;
+    keys += (size_t)blockIdx.y * 4 * nAt;
+    cols += (size_t)blockIdx.y * 4 * nAt;
+    w += (size_t)blockIdx.y * 4 * nAt;
     const int m1 = bg.m1, m2 = bg.m2, m3 = bg.m3;
     const uint32_t invalid = (uint32_t)m3 * (uint32_t)bg.nZ * (uint32_t)m2;
     const float x1 = xyz[i * 3 + 0] / bg.d1 + ((float)m1) * 0.5f - 0.5f;
@@ -110,9 +121,9 @@ __global__ void k_bin_atoms(const float* __restrict__ xyz, const int* __restrict
 
 void launch_bin_atoms(const float* xyz, const int* zidx, const float* occ, int nAt,
                       const BinGeom& bg, uint32_t* keys, int* cols, float* w, int* bins_out,
-                      cudaStream_t st)
+                      int nconf, cudaStream_t st)
 {
-    k_bin_atoms<<<(nAt + 255) / 256, 256, 0, st>>>(xyz, zidx, occ, nAt, bg, keys, cols, w, bins_out);
+    k_bin_atoms<<<dim3((nAt + 255) / 256, nconf), 256, 0, st>>>(xyz, zidx, occ, nAt, bg, keys, cols, w, bins_out);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -128,6 +139,8 @@ __global__ void __launch_bounds__(SORT_THREADS)
 k_sort_hist(const uint32_t* __restrict__ keys, int n, int shift, unsigned int* __restrict__ hist, int nb)
 {
     __shared__ unsigned int h[256];
+    keys += (size_t)blockIdx.y * n;
+    hist += (size_t)blockIdx.y * 256 * nb;
     h[threadIdx.x] = 0;
     __syncthreads();
     const int base = blockIdx.x * SORT_CHUNK;
@@ -143,6 +156,7 @@ k_sort_hist(const uint32_t* __restrict__ keys, int n, int shift, unsigned int* _
 __global__ void __launch_bounds__(1024) k_sort_scan(unsigned int* hist, int total)
 {
     __shared__ unsigned int sh[1024];
+    hist += (size_t)blockIdx.y * total;
     const int per = (total + 1023) / 1024;
     const int lo = threadIdx.x * per, hi = min(lo + per, total);
     unsigned int s = 0;
@@ -168,6 +182,11 @@ k_sort_scatter(const uint32_t* __restrict__ keys, const int* __restrict__ cols,
     constexpr int NW = SORT_THREADS / 32;
     __shared__ unsigned int base[256];
     __shared__ unsigned int wcount[NW][256];
+    {
+        const size_t off = (size_t)blockIdx.y * n;
+        keys += off; cols += off; w += off; keys_o += off; cols_o += off; w_o += off;
+        hist += (size_t)blockIdx.y * 256 * nb;
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     base[threadIdx.x] = hist[threadIdx.x * nb + blockIdx.x];
     const int cbase = blockIdx.x * SORT_CHUNK;
@@ -199,7 +218,7 @@ k_sort_scatter(const uint32_t* __restrict__ keys, const int* __restrict__ cols,
     }
 }
 
-void launch_radix_sort(const SortBuffers& sb, int n, int key_bits, cudaStream_t st)
+void launch_radix_sort(const SortBuffers& sb, int n, int key_bits, int nconf, cudaStream_t st)
 {
     if (n <= 0) return;
     const int nb = sort_num_blocks(n);
@@ -211,9 +230,9 @@ void launch_radix_sort(const SortBuffers& sb, int n, int key_bits, cudaStream_t 
     if (passes == 0) passes = 2;
     for (int p = 0; p < passes; p++) {
         const int shift = 8 * p;
-        k_sort_hist<<<nb, SORT_THREADS, 0, st>>>(ki, n, shift, sb.hist, nb);
-        k_sort_scan<<<1, 1024, 0, st>>>(sb.hist, 256 * nb);
-        k_sort_scatter<<<nb, SORT_THREADS, 0, st>>>(ki, ci, wi, ko, co, wo, n, shift, sb.hist, nb);
+        k_sort_hist<<<dim3(nb, nconf), SORT_THREADS, 0, st>>>(ki, n, shift, sb.hist, nb);
+        k_sort_scan<<<dim3(1, nconf), 1024, 0, st>>>(sb.hist, 256 * nb);
+        k_sort_scatter<<<dim3(nb, nconf), SORT_THREADS, 0, st>>>(ki, ci, wi, ko, co, wo, n, shift, sb.hist, nb);
         uint32_t* tk = ki; ki = ko; ko = tk;
         int* tc = ci; ci = co; co = tc;
         float* tw2 = wi; wi = wo; wo = tw2;
@@ -225,6 +244,8 @@ __global__ void k_row_pointers(const uint32_t* __restrict__ keys, int n, int* __
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > nkeys) return;
+    keys += (size_t)blockIdx.y * n;
+    rowptr += (size_t)blockIdx.y * ((size_t)nkeys + 1);
     int lo = 0, hi = n;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
@@ -232,9 +253,9 @@ __global__ void k_row_pointers(const uint32_t* __restrict__ keys, int n, int* __
     }
     rowptr[k] = lo;
 }
-void launch_row_pointers(const uint32_t* keys_sorted, int n, int* rowptr, int nkeys, cudaStream_t st)
+void launch_row_pointers(const uint32_t* keys_sorted, int n, int* rowptr, int nkeys, int nconf, cudaStream_t st)
 {
-    k_row_pointers<<<(nkeys + 1 + 255) / 256, 256, 0, st>>>(keys_sorted, n, rowptr, nkeys);
+    k_row_pointers<<<dim3((nkeys + 1 + 255) / 256, nconf), 256, 0, st>>>(keys_sorted, n, rowptr, nkeys);
 }
 
 }  // namespace fdes

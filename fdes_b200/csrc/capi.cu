@@ -271,8 +271,8 @@ int fdes_b200_sort_records(unsigned int* keys, int* cols, float* w, int n, int n
     ck(cudaMemcpy(sb.w, w, (size_t)n * 4, cudaMemcpyHostToDevice), "cudaMemcpy");
     int bits = 0;
     while ((1LL << bits) <= (long long)nkeys) bits++;
-    launch_radix_sort(sb, n, bits, 0);
-    launch_row_pointers(sb.keys, n, rp, nkeys, 0);
+    launch_radix_sort(sb, n, bits, 1, 0);
+    launch_row_pointers(sb.keys, n, rp, nkeys, 1, 0);
     ck(cudaDeviceSynchronize(), "sort kernels");
     ck(cudaMemcpy(keys, sb.keys, (size_t)n * 4, cudaMemcpyDeviceToHost), "cudaMemcpy");
     ck(cudaMemcpy(cols, sb.cols, (size_t)n * 4, cudaMemcpyDeviceToHost), "cudaMemcpy");

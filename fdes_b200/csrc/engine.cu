@@ -14,11 +14,26 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <mutex>
 #include <stdexcept>
 #include <vector>
 
 namespace fdes {
+
+namespace {
+struct PhaseTimer {
+    bool on = getenv("FDES_B200_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void mark(const char* what)
+    {
+        if (!on) return;
+        const auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "    [engine] %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
+}  // namespace
 
 static const KirklandRow kKirkland[103] = {
 #include "kirkland_table.inc"
@@ -120,6 +135,7 @@ void release_device_cache()
 
 Engine::Engine(const Params& pin, const Atoms& atoms, const EngineOptions& opt) : p_(pin), opt_(opt)
 {
+    PhaseTimer pt;
     if (atoms.size() <= 0) throw std::runtime_error("no atoms in the specimen");
     if (p_.mode < 0 || p_.mode > 2) throw std::runtime_error("mode must be 0 (imaging), 1 (DP) or 2 (CBED)");
     if (p_.m1 != p_.m2)
@@ -152,7 +168,10 @@ Engine::Engine(const Params& pin, const Atoms& atoms, const EngineOptions& opt) 
     j1_ = (int)(((long long)count_ * (rank + 1)) / world);
     rng_burn_ = j0_;
     const int mine = std::max(1, j1_ - j0_);
-    B_ = opt_.batch > 0 ? opt_.batch : std::max(1, (2048 * 2048) / (N_ * N_));
+    // configurations advanced together: 8 fills the GPU at every supported grid size and keeps the
+    // batch buffers ((4 + nZ) complex grids per configuration) far below the 180 GB of HBM
+    B_ = opt_.batch > 0 ? opt_.batch : 8;
+    while (B_ > 1 && (size_t)B_ * (4 + nZ_) * (size_t)N_ * N_ * sizeof(cpx) > ((size_t)48 << 30)) B_ /= 2;
     B_ = std::min(B_, mine);
     const long long nk = (long long)p_.m3 * nZ_ * N_;
     if (nk >= (1LL << 31) - 2) throw std::runtime_error("slices * species * rows too large for 32-bit row keys");
@@ -163,6 +182,7 @@ Engine::Engine(const Params& pin, const Atoms& atoms, const EngineOptions& opt) 
     rec_stride_ = (size_t)nrec_;
     rp_stride_ = (size_t)nkeys_ + 1;
 
+    pt.mark("ctor: host prep");
     CK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
     CK(cudaEventCreate(&ev0_));
     CK(cudaEventCreate(&ev1_));
@@ -180,13 +200,15 @@ Engine::Engine(const Params& pin, const Atoms& atoms, const EngineOptions& opt) 
     plan.add(xyz0_, 3 * (size_t)nAt_); plan.add(xyzTO_, 3 * (size_t)nAt_); plan.add(xyzK_, 3 * (size_t)nAt_);
     plan.add(xyzFP_, (size_t)B_ * 3 * nAt_); plan.add(dwf_, nAt_); plan.add(occ_, nAt_); plan.add(zidx_, nAt_);
     plan.add(keys_, (size_t)B_ * nrec_); plan.add(cols_, (size_t)B_ * nrec_); plan.add(w_, (size_t)B_ * nrec_);
-    plan.add(keys_tmp_, nrec_); plan.add(cols_tmp_, nrec_); plan.add(w_tmp_, nrec_);
+    plan.add(keys_tmp_, (size_t)B_ * nrec_); plan.add(cols_tmp_, (size_t)B_ * nrec_); plan.add(w_tmp_, (size_t)B_ * nrec_);
     plan.add(rowptr_, (size_t)B_ * rp_stride_);
     plan.add(bins_, 4 * (size_t)nAt_);
-    plan.add(hist_, 256 * (size_t)sort_num_blocks(nrec_));
+    plan.add(hist_, (size_t)B_ * 256 * sort_num_blocks(nrec_));
     plan.add(norm_partial_, 256); plan.add(norm_result_, 1);
     if (p_.frPh > 0) plan.add(rng_bytes_, rng_state_bytes() * 3 * (size_t)nAt_);
+    pt.mark("ctor: stream+twiddles");
     arena_ = pool_acquire(plan.total(), opt_.gpu_index);
+    pt.mark("ctor: arena");
     plan.assign(arena_);
     rng_ = rng_bytes_;
     I_ = I_own_; ew_ = ew_own_;
@@ -198,6 +220,7 @@ Engine::Engine(const Params& pin, const Atoms& atoms, const EngineOptions& opt) 
     CK(cudaMemcpyAsync(dwf_, atoms.dwf.data(), nAt_ * sizeof(float), cudaMemcpyHostToDevice, st_));
     CK(cudaMemcpyAsync(occ_, atoms.occ.data(), nAt_ * sizeof(float), cudaMemcpyHostToDevice, st_));
     CK(cudaStreamSynchronize(st_));   // host vectors above go out of scope
+    pt.mark("ctor: uploads");
 
     // coordinates with the tilt offset (src/crystalMaker.cu:282-283)
     CK(cudaMemcpyAsync(xyzTO_, xyz0_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
@@ -208,6 +231,7 @@ Engine::Engine(const Params& pin, const Atoms& atoms, const EngineOptions& opt) 
     }
     setup_tables();
     CK(cudaStreamSynchronize(st_));
+    pt.mark("ctor: rng+tables");
 }
 
 Engine::~Engine()
@@ -324,31 +348,33 @@ void Engine::make_incident(int k)
     incident_k_ = k;
 }
 
-void Engine::bin_and_sort(int b, const float* xyz_dev)
+// records of `nconf` configurations (slots b0 .. b0+nconf-1) from coordinates [nconf][nAt][3]
+void Engine::bin_and_sort(int b0, int nconf, const float* xyz_dev)
 {
     BinGeom bg{N_, N_, p_.m3, nZ_, p_.d1, p_.d2, p_.d3};
-    uint32_t* keys = keys_ + (size_t)b * nrec_;
-    int* cols = cols_ + (size_t)b * nrec_;
-    float* w = w_ + (size_t)b * nrec_;
-    launch_bin_atoms(xyz_dev, zidx_, occ_, nAt_, bg, keys, cols, w, nullptr, st_);
+    uint32_t* keys = keys_ + (size_t)b0 * nrec_;
+    int* cols = cols_ + (size_t)b0 * nrec_;
+    float* w = w_ + (size_t)b0 * nrec_;
+    launch_bin_atoms(xyz_dev, zidx_, occ_, nAt_, bg, keys, cols, w, nullptr, nconf, st_);
     SortBuffers sb{keys, keys_tmp_, cols, cols_tmp_, w, w_tmp_, hist_};
-    launch_radix_sort(sb, nrec_, key_bits_, st_);
-    launch_row_pointers(keys, nrec_, rowptr_ + (size_t)b * rp_stride_, nkeys_, st_);
+    launch_radix_sort(sb, nrec_, key_bits_, nconf, st_);
+    launch_row_pointers(keys, nrec_, rowptr_ + (size_t)b0 * rp_stride_, nkeys_, nconf, st_);
     int passes = (key_bits_ + 7) / 8; if (passes & 1) passes++; if (!passes) passes = 2;
     tm_.kernel_launches += 2 + 3 * passes;
 }
 
-void Engine::prepare_config(int b, const float* xyz_k)
+// jitter + bin + sort + row pointers for the configurations of one batch (slots 0 .. nb-1)
+void Engine::prepare_batch(int nb, const float* xyz_k)
 {
-    float* fp = xyzFP_ + (size_t)b * 3 * nAt_;
     if (p_.frPh > 0) {
-        launch_atom_jitter(fp, xyz_k, dwf_, nAt_, rng_, rng_burn_, st_);
+        launch_atom_jitter(xyzFP_, xyz_k, dwf_, nAt_, rng_, rng_burn_, nb, st_);
         rng_burn_ = 0;
         tm_.kernel_launches += 1;
     } else {
-        CK(cudaMemcpyAsync(fp, xyz_k, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
+        for (int b = 0; b < nb; b++)
+            CK(cudaMemcpyAsync(xyzFP_ + (size_t)b * 3 * nAt_, xyz_k, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
     }
-    bin_and_sort(b, fp);
+    bin_and_sort(0, nb, xyzFP_);
 }
 
 void Engine::run_slices_plain(int nb)
@@ -376,7 +402,9 @@ void Engine::slice_loop(int nb)
 {
     tm_.slices_executed += (long long)p_.m3 * nb;
     tm_.kernel_launches += 4LL * ((p_.m3 + 1) / 2) + 2LL * p_.m3;
-    if (!opt_.use_graph) { run_slices_plain(nb); return; }
+    // a CUDA graph pays off when the sweeps are launch-bound (small grids, small batches); its
+    // capture + instantiation costs about a millisecond, more than it saves on large launches
+    if (!opt_.use_graph || (size_t)nb * N_ * N_ > ((size_t)1 << 21)) { run_slices_plain(nb); return; }
     if (!graph_ || graph_nb_ != nb) {
         if (graph_) { cudaGraphExecDestroy(graph_); graph_ = nullptr; }
         // first use of each kernel must happen outside capture (function attributes are set there)
@@ -446,6 +474,7 @@ void Engine::accumulate_outputs(int k, int nb)
 
 void Engine::run_k(int k)
 {
+    PhaseTimer pt;
     if (k < 0 || k >= p_.n3) throw std::runtime_error("measurement index out of range");
     const size_t NN = (size_t)N_ * N_;
     launch_fill_f32(I_, NN, 0.f, st_);
@@ -455,18 +484,20 @@ void Engine::run_k(int k)
     make_incident(k);
     for (int j = j0_; j < j1_; j += B_) {
         const int nb = std::min(B_, j1_ - j);
-        for (int b = 0; b < nb; b++) {
-            prepare_config(b, xyzK_);
+        prepare_batch(nb, xyzK_);
+        for (int b = 0; b < nb; b++)
             CK(cudaMemcpyAsync(Psi_ + (size_t)b * NN, psi_in_, NN * sizeof(cpx), cudaMemcpyDeviceToDevice, st_));
-        }
         slice_loop(nb);
         accumulate_outputs(k, nb);
     }
+    pt.mark("run_k: enqueue");
     CK(cudaStreamSynchronize(st_));
+    pt.mark("run_k: wait");
 }
 
 void Engine::finish_k(int k, float* image_host, float* exitwave_host)
 {
+    PhaseTimer pt;
     const size_t NN = (size_t)N_ * N_;
     // addNoiseAndMtf (src/crystalMaker.cu:579-613) without the noise branch + copyMiddleOut
     DetectorParams dp{p_.mtfa, p_.mtfb, p_.mtfc, p_.mtfd, p_.illangle, p_.defoci[k], p_.lambda,
@@ -483,6 +514,7 @@ void Engine::finish_k(int k, float* image_host, float* exitwave_host)
     if (exitwave_host && ew_)
         CK(cudaMemcpyAsync(exitwave_host, ew_, NN * sizeof(cpx), cudaMemcpyDeviceToHost, st_));
     CK(cudaStreamSynchronize(st_));
+    pt.mark("finish_k");
 }
 
 void Engine::potential_slices(float* out_host)
@@ -496,7 +528,7 @@ void Engine::potential_slices(float* out_host)
     const int nkeys_save = nkeys_, bits_save = key_bits_;
     nkeys_ = m3_orig_ * nZ_ * N_;
     key_bits_ = 0; while ((1LL << key_bits_) <= nkeys_) key_bits_++;
-    bin_and_sort(0, xyzTO_);
+    bin_and_sort(0, 1, xyzTO_);
     RowOpts ro; ro.scale = 1.f;
     for (int s = 0; s < m3_orig_; s++) {
         launch_density_rows(g_, A_, rowptr_, cols_, w_, s, -1, nZ_, 1, rec_stride_, rp_stride_, st_);
@@ -517,7 +549,7 @@ void Engine::next_jittered_coords(int k, float* xyz_host)
 {
     CK(cudaMemcpyAsync(xyzK_, xyzTO_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
     tilt(xyzK_, p_.tiltspec[2 * k], p_.tiltspec[2 * k + 1], 0.f);
-    if (p_.frPh > 0) { launch_atom_jitter(xyzFP_, xyzK_, dwf_, nAt_, rng_, rng_burn_, st_); rng_burn_ = 0; }
+    if (p_.frPh > 0) { launch_atom_jitter(xyzFP_, xyzK_, dwf_, nAt_, rng_, rng_burn_, 1, st_); rng_burn_ = 0; }
     else CK(cudaMemcpyAsync(xyzFP_, xyzK_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
     CK(cudaMemcpyAsync(xyz_host, xyzFP_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToHost, st_));
     CK(cudaStreamSynchronize(st_));
@@ -527,7 +559,7 @@ void Engine::bin_tuples(const float* xyz_host, int* bins_host)
 {
     CK(cudaMemcpyAsync(xyzFP_, xyz_host, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyHostToDevice, st_));
     BinGeom bg{N_, N_, p_.m3, nZ_, p_.d1, p_.d2, p_.d3};
-    launch_bin_atoms(xyzFP_, zidx_, occ_, nAt_, bg, keys_, cols_, w_, bins_, st_);
+    launch_bin_atoms(xyzFP_, zidx_, occ_, nAt_, bg, keys_, cols_, w_, bins_, 1, st_);
     CK(cudaMemcpyAsync(bins_host, bins_, 4 * (size_t)nAt_ * sizeof(int), cudaMemcpyDeviceToHost, st_));
     CK(cudaStreamSynchronize(st_));
 }
@@ -536,7 +568,7 @@ void Engine::phase_grating(const float* xyz_host, int s, float* V_host)
 {
     const size_t NN = (size_t)N_ * N_;
     CK(cudaMemcpyAsync(xyzFP_, xyz_host, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyHostToDevice, st_));
-    bin_and_sort(0, xyzFP_);
+    bin_and_sort(0, 1, xyzFP_);
     launch_density_rows(g_, A_, rowptr_, cols_, w_, s, -1, nZ_, 1, rec_stride_, rp_stride_, st_);
     launch_potential_cols(g_, W_, A_, Gq_, rowptr_, s, -1, nZ_, 1, rp_stride_, st_);
     RowOpts ro;
@@ -550,7 +582,7 @@ void Engine::exit_wave(const float* xyz_host, int k, float* psi_host)
 {
     const size_t NN = (size_t)N_ * N_;
     CK(cudaMemcpyAsync(xyzFP_, xyz_host, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyHostToDevice, st_));
-    bin_and_sort(0, xyzFP_);
+    bin_and_sort(0, 1, xyzFP_);
     make_incident(k);
     CK(cudaMemcpyAsync(Psi_, psi_in_, NN * sizeof(cpx), cudaMemcpyDeviceToDevice, st_));
     const bool ug = opt_.use_graph;
@@ -575,10 +607,9 @@ double Engine::bench_configs(int k, int configs)
     CK(cudaEventRecord(ev0_, st_));
     for (int j = 0; j < configs; j += B_) {
         const int nb = std::min(B_, configs - j);
-        for (int b = 0; b < nb; b++) {
-            prepare_config(b, xyzK_);
+        prepare_batch(nb, xyzK_);
+        for (int b = 0; b < nb; b++)
             CK(cudaMemcpyAsync(Psi_ + (size_t)b * NN, psi_in_, NN * sizeof(cpx), cudaMemcpyDeviceToDevice, st_));
-        }
         slice_loop(nb);
         accumulate_outputs(k, nb);
     }
@@ -601,7 +632,7 @@ void Engine::time_sweeps(int k, int nb, int reps, float* ms6)
     for (int b = 0; b < nb; b++) {
         float* fp = xyzFP_ + (size_t)b * 3 * nAt_;
         CK(cudaMemcpyAsync(fp, xyzK_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
-        bin_and_sort(b, fp);
+        bin_and_sort(b, 1, fp);
         CK(cudaMemcpyAsync(Psi_ + (size_t)b * NN, psi_in_, NN * sizeof(cpx), cudaMemcpyDeviceToDevice, st_));
     }
     // a slice pair in the middle of the specimen; S1..S4 are timed on the pair and reported per

@@ -80,8 +80,8 @@ public:
 private:
     void setup_tables();
     void make_incident(int k);                      // psi_in_ (row space) for index k
-    void prepare_config(int b, const float* xyz_k); // jitter + bin + sort + rowptr into slot b
-    void bin_and_sort(int b, const float* xyz_dev);
+    void prepare_batch(int nb, const float* xyz_k);  // jitter + bin + sort + rowptr of a batch
+    void bin_and_sort(int b0, int nconf, const float* xyz_dev);
     void slice_loop(int nb);                        // S1..S6 for all slices, batch nb
     void run_slices_plain(int nb);
     void accumulate_outputs(int k, int nb);

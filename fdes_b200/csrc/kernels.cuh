@@ -132,25 +132,28 @@ void launch_rot(float* xyz, int nAt, int axA, int axB, float c, float s, cudaStr
 size_t rng_state_bytes();
 void launch_rng_init(void* states, int n, unsigned long long seed, cudaStream_t st);
 // xyz_out[i] = xyz_in[i] + N(0,1) * 0.112539540f * sqrtf(dwf[i/3]); burn: draws to discard first
+// for nconf consecutive configurations: xyz_out [nconf][nAt][3]
 void launch_atom_jitter(float* xyz_out, const float* xyz_in, const float* dwf, int nAt,
-                        void* states, int burn, cudaStream_t st);
+                        void* states, int burn, int nconf, cudaStream_t st);
 // per atom: 4 deposit records (key = (i3*nZ + zidx)*m2 + row, col, weight) and the integer bin
 // tuple (i1, i2, i3, zidx; -1 when rejected) -- squareAtoms_d, src/crystalMaker.cu:73-134
+// nconf configurations per launch: xyz [nconf][nAt][3], records [nconf][4 nAt] (bins_out: nconf = 1)
 void launch_bin_atoms(const float* xyz, const int* zidx, const float* occ, int nAt,
                       const BinGeom& bg, uint32_t* keys, int* cols, float* w, int* bins_out,
-                      cudaStream_t st);
+                      int nconf, cudaStream_t st);
 // stable LSD radix sort of (key, col, w) by key; tmp buffers same sizes; hist: 256*nblocks ints
 struct SortBuffers {
     uint32_t *keys, *keys_tmp;
     int *cols, *cols_tmp;
     float *w, *w_tmp;
-    unsigned int* hist;   // 256 * sort_num_blocks(n) entries
+    unsigned int* hist;   // 256 * sort_num_blocks(n) entries per configuration
 };
 int sort_num_blocks(int n);
-void launch_radix_sort(const SortBuffers& sb, int n, int key_bits, cudaStream_t st);
+// nconf independent arrays of n records each, stored back to back (tmp and hist likewise)
+void launch_radix_sort(const SortBuffers& sb, int n, int key_bits, int nconf, cudaStream_t st);
 // rowptr[k] = first sorted record with key >= k, k in [0, nkeys]; records with key >= nkeys
 // (rejected atoms) stay beyond rowptr[nkeys]
-void launch_row_pointers(const uint32_t* keys_sorted, int n, int* rowptr, int nkeys,
+void launch_row_pointers(const uint32_t* keys_sorted, int n, int* rowptr, int nkeys, int nconf,
                          cudaStream_t st);
 
 }  // namespace fdes

@@ -13,6 +13,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <string>
+#include <thread>
+#include <vector>
 
 namespace fdes {
 
@@ -60,6 +64,9 @@ const StrKey kStrKeys[] = {
 
 void dispatch_line(const char* field, const char* line, Params& p, int& ts_i, int& tb_i, int& df_i)
 {
+    // atom lines carry no parameter key (none of the keys below starts with "atom:"); skipping
+    // them up front keeps large specimen files from costing ~60 string compares per atom
+    if (!strncmp(field, "atom:", 5)) return;
     for (const FloatKey& k : kFloatKeys)
         if (!strncmp(field, k.key, k.cmp)) sscanf(line, "%*s %g", &(p.*(k.dst)));
     for (int a = 0; a < AB_COUNT; a++) {
@@ -280,9 +287,28 @@ bool write_cnf(const char* file, const Params& p, const Atoms& atoms, int gpu_in
     fprintf(fw, "Number of atoms: %d\n", atoms.size());
     fprintf(fw, "\n# List of atoms. Quantities in each row:\n");
     fprintf(fw, "# Atomic no.; x-, y- and z-coordinate [m]; Debeye-Waller factor [m^2]; occupancy.\n");
-    for (int j = 0; j < atoms.size(); j++)
-        fprintf(fw, "%i %14.8g %14.8g %14.8g %14.8g %14.8g \n", atoms.Z[j], atoms.xyz[3 * j + 0],
-                atoms.xyz[3 * j + 1], atoms.xyz[3 * j + 2], atoms.dwf[j], atoms.occ[j]);
+    // the atom table is formatted by a few threads into memory and written in one go (tens of
+    // thousands of %14.8g conversions otherwise take longer than the simulation itself)
+    const int nAt = atoms.size();
+    const int nthreads = std::max(1, std::min(8, nAt / 2048));
+    std::vector<std::string> chunks(nthreads);
+    auto format_range = [&](int t) {
+        const int lo = (int)((long long)nAt * t / nthreads), hi = (int)((long long)nAt * (t + 1) / nthreads);
+        std::string& s = chunks[t];
+        s.reserve((size_t)(hi - lo) * 90);
+        char buf[160];
+        for (int j = lo; j < hi; j++) {
+            const int n = snprintf(buf, sizeof buf, "%i %14.8g %14.8g %14.8g %14.8g %14.8g \n", atoms.Z[j],
+                                   atoms.xyz[3 * j + 0], atoms.xyz[3 * j + 1], atoms.xyz[3 * j + 2], atoms.dwf[j],
+                                   atoms.occ[j]);
+            s.append(buf, (size_t)n);
+        }
+    };
+    std::vector<std::thread> workers;
+    for (int t = 1; t < nthreads; t++) workers.emplace_back(format_range, t);
+    format_range(0);
+    for (auto& w : workers) w.join();
+    for (const std::string& s : chunks) fwrite(s.data(), 1, s.size(), fw);
     fclose(fw);
     return true;
 }
