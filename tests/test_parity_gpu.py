@@ -240,3 +240,45 @@ def test_si1024_properties(si1024, fb, orc, tmp_path):
         img0, ew0 = sim.simulate()
     assert np.allclose(ew0, 1.0, atol=1e-5)
     assert np.allclose(img0, 1.0, atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------
+# the other grid sizes of BASELINE.json: 2048^2 (Au cuboctahedron), 4096^2 (random slab, 3 species),
+# 512^2 CBED probe (the per-probe unit of the STEM configuration)
+# ---------------------------------------------------------------------------------------------
+def _oracle_vs_library(cnf, fb, orc, atoms6=None):
+    p, Z, xyz, dwf, occ = orc.read_cnf(str(cnf))
+    if atoms6 is not None:
+        Z, xyz, dwf, occ = atoms6[:, 0].astype(np.int32), atoms6[:, 1:4].copy(), atoms6[:, 4].copy(), atoms6[:, 5].copy()
+    with fb.Simulation(cnf, atoms6=atoms6, want_exitwave=True) as sim:
+        img, ew = sim.simulate()
+    res = orc.build_measurements(p, Z, xyz, dwf, occ)
+    assert rel_l2(ew, res.exitwave) < TOL_WAVE
+    assert rel_l2(img, res.image) < TOL_INTENSITY
+    return img, ew
+
+
+def test_au_2048_against_oracle(fb, orc, tmp_path):
+    from fdes_b200 import specimens
+    cnf = tmp_path / "au.cnf"
+    specimens.config_au_2048(cnf, frozen_phonons=0)
+    _oracle_vs_library(cnf, fb, orc)
+
+
+def test_random_4096_against_oracle(fb, orc, tmp_path):
+    from fdes_b200 import specimens
+    cnf = tmp_path / "slab.cnf"
+    atoms = specimens.random_slab(3000, 4096 * 0.1e-10, 5 * 2e-10)
+    specimens.write_cnf(cnf, image_size=2048, border_size=1024, slices=5, pixel_size=0.1e-10, slice_thickness=2e-10,
+                        atoms=atoms, voltage=200e3, absorptive=0.05)
+    _oracle_vs_library(cnf, fb, orc)
+
+
+def test_srtio3_512_probe_against_oracle(fb, orc, tmp_path):
+    """mode 2 (CBED probe at the grid centre): the per-probe unit of the STEM configuration."""
+    from fdes_b200 import specimens
+    cnf = tmp_path / "sto.cnf"
+    atoms = specimens.srtio3_slab(4, 4, 8)
+    specimens.write_cnf(cnf, image_size=512, border_size=0, slices=16, pixel_size=19.525e-10 / 512,
+                        slice_thickness=1.9525e-10, atoms=atoms, voltage=200e3, mode=2, objective_aperture=20e-3)
+    _oracle_vs_library(cnf, fb, orc)
