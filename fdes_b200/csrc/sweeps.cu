@@ -34,8 +34,11 @@ namespace fdes {
     } while (0)
 
 // register budget per thread that __launch_bounds__ asks the compiler to respect
-#ifndef FDES_REG_BUDGET
-#define FDES_REG_BUDGET 255
+#ifndef FDES_ROW_MIN_CTAS
+#define FDES_ROW_MIN_CTAS 3
+#endif
+#ifndef FDES_COL_MIN_CTAS
+#define FDES_COL_MIN_CTAS 1
 #endif
 
 // Points per thread for a line of N points (rows and columns use the same split, so one
@@ -55,7 +58,7 @@ struct RowCfg {
     static constexpr int LSTRIDE = L::LS;
     static constexpr size_t SMEM = (size_t)RPB * LSTRIDE * sizeof(cpx);
     static constexpr bool WARP_SYNC = (T <= 32);       // a line lives inside one warp
-    static constexpr int MIN_CTAS = (65536 / FDES_REG_BUDGET) / THREADS > 0 ? (65536 / FDES_REG_BUDGET) / THREADS : 1;
+    static constexpr int MIN_CTAS = FDES_ROW_MIN_CTAS;
 };
 // threads of one row line: warp-level sync when the line fits a warp, else a named barrier
 template <int N>
@@ -81,7 +84,7 @@ struct ColCfg {
     // is transformed by the threads of ONE warp (warp-level synchronisation inside the FFT).
     static constexpr bool STAGED = (T <= 32);
     static constexpr int RPI = THREADS / CW;          // tile rows moved per iteration (= T)
-    static constexpr int MIN_CTAS = (65536 / FDES_REG_BUDGET) / THREADS > 0 ? (65536 / FDES_REG_BUDGET) / THREADS : 1;
+    static constexpr int MIN_CTAS = FDES_COL_MIN_CTAS;
 };
 
 template <int N>
