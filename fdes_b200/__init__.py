@@ -59,6 +59,8 @@ def load_library() -> ctypes.CDLL:
     lib.fdes_b200_exit_wave.argtypes = [vp, c_f, ctypes.c_int, c_f]
     lib.fdes_b200_bench_configs.argtypes = [vp, ctypes.c_int, ctypes.c_int]
     lib.fdes_b200_bench_configs.restype = ctypes.c_double
+    lib.fdes_b200_stem_scan.argtypes = [vp, ctypes.c_int, ctypes.c_int, c_f, ctypes.c_int, c_f, c_f]
+    lib.fdes_b200_stem_scan.restype = ctypes.c_double
     lib.fdes_b200_time_sweeps.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f]
     lib.fdes_b200_get_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
     lib.fdes_b200_fft2d.argtypes = [c_f, ctypes.c_int, ctypes.c_int, ctypes.c_int]
@@ -231,6 +233,17 @@ class Simulation:
         c = (ctypes.c_longlong * 4)()
         self._ck(self._lib.fdes_b200_get_counters(self._h, c, 1 if reset else 0))
         return {"slices": int(c[0]), "launches": int(c[1]), "band_columns": int(c[2])}
+
+    def stem_scan(self, positions: np.ndarray, detectors_mrad: np.ndarray, k: int = 0):
+        """STEM scan (mode 2 .cnf): positions [n, 2] in metres relative to the grid centre,
+        detectors_mrad [ndet, 2] = (inner, outer).  Returns (signals [n, ndet], device ms)."""
+        pos = np.ascontiguousarray(positions, np.float32).reshape(-1, 2)
+        det = np.ascontiguousarray(detectors_mrad, np.float32).reshape(-1, 2)
+        out = np.zeros((pos.shape[0], det.shape[0]), np.float32)
+        ms = self._lib.fdes_b200_stem_scan(self._h, k, pos.shape[0], _fp(pos), det.shape[0], _fp(det), _fp(out))
+        if ms < 0:
+            raise FdesError(self._lib.fdes_b200_last_error().decode())
+        return out, float(ms)
 
     def time_sweeps(self, k: int = 0, batch: int = 0, reps: int = 20):
         """Average launch duration [ms] of the six per-slice sweeps S1..S6."""

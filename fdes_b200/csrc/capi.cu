@@ -202,6 +202,16 @@ double fdes_b200_bench_configs(fdes_b200_sim* sim, int k, int configs)
     API_CATCH(-1.0)
 }
 
+double fdes_b200_stem_scan(fdes_b200_sim* sim, int k, int nprobes, const float* xy_host, int ndet,
+                           const float* det_mrad_host, float* out_host)
+{
+    API_TRY
+    double ms = 0.0;
+    sim->eng->stem_scan(k, nprobes, xy_host, ndet, det_mrad_host, out_host, &ms);
+    return ms;
+    API_CATCH(-1.0)
+}
+
 int fdes_b200_time_sweeps(fdes_b200_sim* sim, int k, int batch, int reps, float* ms6)
 {
     API_TRY

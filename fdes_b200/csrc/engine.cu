@@ -621,6 +621,92 @@ double Engine::bench_configs(int k, int configs)
     return (double)ms;
 }
 
+// ---------------------------------------------------------------------------------------------
+// STEM probe scan.  FDES itself has no scan (mode 2 = one CBED probe at the grid centre,
+// src/multisliceSimulation.cu:572-581); a scan position r_p is that probe shifted periodically by
+// a phase ramp in Fourier space, the specimen fixed.  Per frozen-phonon configuration the
+// transmission functions of all slices are computed once (S1..S4) and kept in HBM; the probes
+// then advance in batches through S5/S6 only, and annular detectors integrate the diffraction
+// intensity |FFT2 psi|^2 / N^2 (diffractionPattern, src/crystalMaker.cu:700-718).
+// ---------------------------------------------------------------------------------------------
+void Engine::stem_scan(int k, int nprobes, const float* xy_host, int ndet, const float* det_mrad_host,
+                       float* out_host, double* loop_ms)
+{
+    if (p_.mode != 2) throw std::runtime_error("STEM scan needs mode 2 (convergent probe)");
+    if (k < 0 || k >= p_.n3) throw std::runtime_error("measurement index out of range");
+    if (nprobes <= 0) throw std::runtime_error("no probe positions");
+    if (ndet <= 0 || ndet > MAX_DETECTORS) throw std::runtime_error("1..8 detectors supported");
+    if (p_.doBeamTilt) throw std::runtime_error("STEM scan with beam tilt is not supported");
+    const size_t NN = (size_t)N_ * N_;
+    DetectorRings rings{};
+    rings.n = ndet;
+    for (int d = 0; d < ndet; d++) {
+        // k^2 = (sin(theta[mrad] * 1e-3) / lambda)^2, the detector convention of src/rwQsc.cu:723-730
+        const float a = sinf(det_mrad_host[2 * d] * 1e-3f) / p_.lambda, b = sinf(det_mrad_host[2 * d + 1] * 1e-3f) / p_.lambda;
+        rings.in2[d] = a * a;
+        rings.out2[d] = b * b;
+    }
+    // device scratch of this call: transmission stack, probe shifts, detector sums
+    const int tiles = detector_tiles(g_);
+    cpx* tstack = nullptr; float *shifts = nullptr, *out = nullptr, *partial = nullptr;
+    ArenaPlan plan;
+    plan.add(tstack, ((size_t)p_.m3 + 1) * NN);
+    plan.add(shifts, 2 * (size_t)nprobes);
+    plan.add(out, (size_t)nprobes * ndet);
+    plan.add(partial, (size_t)B_ * tiles * MAX_DETECTORS);
+    void* block = pool_acquire(plan.total(), opt_.gpu_index);
+    plan.assign(block);
+    try {
+        std::vector<float> sh(2 * (size_t)nprobes);
+        for (int i = 0; i < nprobes; i++) {
+            sh[2 * i] = xy_host[2 * i] / ((float)N_ * p_.d1);
+            sh[2 * i + 1] = xy_host[2 * i + 1] / ((float)N_ * p_.d2);
+        }
+        CK(cudaMemcpyAsync(shifts, sh.data(), sh.size() * sizeof(float), cudaMemcpyHostToDevice, st_));
+        launch_fill_f32(out, (size_t)nprobes * ndet, 0.f, st_);
+        CK(cudaMemcpyAsync(xyzK_, xyzTO_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
+        tilt(xyzK_, p_.tiltspec[2 * k], p_.tiltspec[2 * k + 1], 0.f);
+        make_incident(k);
+        // spectrum of the centred probe: PSI0 = FFT_col(psi_in) (scratch_ is free after make_incident)
+        launch_cols_fft(g_, psi_in_, scratch_, -1, COL_PLAIN, nullptr, 1.f, 1, st_);
+        CK(cudaStreamSynchronize(st_));    // sh goes out of scope below
+        CK(cudaEventRecord(ev0_, st_));
+        const float weight = 1.f / (float)count_;
+        for (int j = j0_; j < j1_; j++) {
+            prepare_batch(1, xyzK_);
+            for (int s = 0; s < p_.m3; s += 2) {   // transmission stack of this configuration
+                const int npair = std::min(2, p_.m3 - s);
+                const int s2 = npair > 1 ? s + 1 : -1;
+                launch_density_rows(g_, A_, rowptr_, cols_, w_, s, s2, nZ_, 1, rec_stride_, rp_stride_, st_);
+                launch_potential_cols(g_, W_, A_, Gq_, rowptr_, s, s2, nZ_, 1, rp_stride_, st_);
+                launch_transmit_rows(g_, W_, tstack + (size_t)s * NN, npair, p_.imPot, 1, st_);
+                launch_bandlimit_cols(g_, tstack + (size_t)s * NN, 1, npair, st_);
+            }
+            tm_.kernel_launches += 4LL * ((p_.m3 + 1) / 2);
+            for (int i0 = 0; i0 < nprobes; i0 += B_) {
+                const int nb = std::min(B_, nprobes - i0);
+                launch_probe_cols(g_, Psi_, scratch_, shifts + 2 * (size_t)i0, nb, st_);
+                for (int s = 0; s < p_.m3; s++) {
+                    launch_multiply_rows(g_, Psi_, tstack + (size_t)s * NN, 0, nb, false, st_);
+                    launch_propagate_cols(g_, Psi_, Pq_, nb, st_);
+                }
+                launch_detector_cols(g_, Psi_, partial, out + (size_t)i0 * ndet, rings, p_.d1, p_.d2, weight, nb, st_);
+                tm_.kernel_launches += 3 + 2LL * p_.m3;
+                tm_.slices_executed += (long long)p_.m3 * nb;
+            }
+        }
+        CK(cudaEventRecord(ev1_, st_));
+        CK(cudaMemcpyAsync(out_host, out, (size_t)nprobes * ndet * sizeof(float), cudaMemcpyDeviceToHost, st_));
+        CK(cudaStreamSynchronize(st_));
+        if (loop_ms) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, ev0_, ev1_)); *loop_ms = ms; }
+    } catch (...) {
+        cudaStreamSynchronize(st_);
+        pool_release(block);
+        throw;
+    }
+    pool_release(block);
+}
+
 // Each of the six sweeps launched `reps` times back to back on the buffers of a prepared batch,
 // bracketed by CUDA events on the engine's stream: ms6[i] = average launch duration of S(i+1).
 void Engine::time_sweeps(int k, int nb, int reps, float* ms6)

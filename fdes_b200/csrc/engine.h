@@ -68,6 +68,12 @@ public:
     // throughput loop used by bench.py: `configs` configurations (coordinates resident in HBM,
     // jitter applied if frPh > 0), returns CUDA-event milliseconds of the whole loop
     double bench_configs(int k, int configs);
+    // STEM scan: detector sums out_host [nprobes][ndet] for probe positions xy_host [nprobes][2]
+    // (metres, relative to the grid centre) and annular detectors det_mrad_host [ndet][2]
+    // (inner, outer half-angle in mrad); averaged over this rank's frozen-phonon configurations
+    // with weight 1/count.  loop_ms (may be null): CUDA-event time of the scan.
+    void stem_scan(int k, int nprobes, const float* xy_host, int ndet, const float* det_mrad_host,
+                   float* out_host, double* loop_ms);
     // average launch duration [ms] of each of the six sweeps on a prepared batch of nb configs
     void time_sweeps(int k, int nb, int reps, float* ms6);
     int batch() const { return B_; }

@@ -49,6 +49,19 @@ void launch_multiply_rows(const SweepGeom& g, cpx* Psi, const cpx* E, size_t e_b
 // S6: column FFT -> x Fresnel propagator (quarter table, mask and 1/N folded in) -> inverse
 void launch_propagate_cols(const SweepGeom& g, cpx* Psi, const cpx* Pq, int batch, cudaStream_t st);
 
+// ---- STEM probe scan ----------------------------------------------------------------------
+constexpr int MAX_DETECTORS = 8;
+struct DetectorRings { int n; float in2[MAX_DETECTORS], out2[MAX_DETECTORS]; };   // |k|^2 bounds [1/m^2]
+// Psi[b] <- centred probe shifted by shifts[b] = (x, y) position / (N * pixel size); PSI0 is the
+// column transform of the centred probe in the (kx, y) domain
+void launch_probe_cols(const SweepGeom& g, cpx* Psi, const cpx* PSI0, const float* shifts, int batch,
+                       cudaStream_t st);
+// out[b][d] += weight * (diffraction intensity of Psi[b] inside ring d); partial: scratch of
+// batch * detector_tiles(g) * MAX_DETECTORS floats
+int detector_tiles(const SweepGeom& g);
+void launch_detector_cols(const SweepGeom& g, const cpx* Psi, float* partial, float* out, const DetectorRings& rings,
+                          float d1, float d2, float weight, int batch, cudaStream_t st);
+
 // ---- generic sweeps used outside the slice loop ------------------------------------------
 enum RowEpilogue {
     ROW_STORE = 0,         // out = scale * v

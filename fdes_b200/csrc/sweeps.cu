@@ -679,6 +679,137 @@ void launch_cols_fft(const SweepGeom& g, const cpx* in, void* out, int dir, ColO
     });
 }
 
+// =============================================================================================
+// STEM: shifted probes from the spectrum of the centred probe, and annular detectors
+// =============================================================================================
+// Psi_b(kx, y) = (1/N) IFFT_col[ PSI0(kx, ky) * exp(-2 pi i (iw(kx) sx_b + iw(ky) sy_b)) ], band
+// columns only; PSI0 = FFT_col of the centred, normalised probe in the (kx, y) domain.  shifts:
+// [batch][2] = probe position / (N * pixel size), i.e. in units of the grid period.
+template <int N>
+__global__ void __launch_bounds__(ColCfg<N, false>::THREADS, ColCfg<N, false>::MIN_CTAS)
+k_probe_cols(cpx* __restrict__ Psi, const cpx* __restrict__ PSI0, const float* __restrict__ shifts,
+             int lo_end, int hi_start, const cpx* __restrict__ tw)
+{
+    using C = ColCfg<N, false>;
+    extern __shared__ cpx smem[];
+    constexpr int E = C::E;
+    const ColCtx<N> ctx(smem);
+    const int theta = ctx.theta;
+    const int kx0 = band_col0(blockIdx.x * C::CW, lo_end, hi_start), kx = kx0 + ctx.line;
+    const float sx = shifts[2 * blockIdx.y], sy = shifts[2 * blockIdx.y + 1];
+    cpx x[E];
+    ctx.load(x, PSI0 + kx0, KeepAll());
+    const int i1 = kx > N / 2 ? kx - N : kx;
+    const float ax = (float)i1 * sx;
+    const float inv = 1.f / (float)N;
+#pragma unroll
+    for (int m = 0; m < E; m++) {
+        const int ky = theta + m * C::T;
+        const int i2 = ky > N / 2 ? ky - N : ky;
+        float t = ax + (float)i2 * sy;      // phase in turns
+        t -= rintf(t);
+        float sn, cs;
+        sincos_compact(-6.283185307179586f * t, sn, cs);
+        x[m] = cmul(x[m], make_float2(cs * inv, sn * inv));
+    }
+    fft_line<N, E, 1>(x, ctx.sm, theta, tw, ctx);
+    ctx.store(x, Psi + (size_t)blockIdx.y * N * N + kx0);
+}
+
+void launch_probe_cols(const SweepGeom& g, cpx* Psi, const cpx* PSI0, const float* shifts, int batch,
+                       cudaStream_t st)
+{
+    FDES_DISPATCH_N(g.N, {
+        using C = ColCfg<NN, false>;
+        static bool once = false;
+        if (!once) { allow_smem(k_probe_cols<NN>, C::SMEM); once = true; }
+        dim3 grid(band_cols(g) / C::CW, batch);
+        k_probe_cols<NN><<<grid, C::THREADS, C::SMEM, st>>>(Psi, PSI0, shifts, g.lo_end, g.hi_start, g.tw);
+    });
+}
+
+// partial[b][tile][d] = sum over the tile's columns and all ky of |FFT_col(Psi_b)|^2 inside the
+// annulus k_in^2 <= |k|^2 < k_out^2 of detector d (|FFT2 psi|^2 / N^2 with Psi = FFT_row(psi)/N,
+// the normalisation of diffractionPattern, src/crystalMaker.cu:714-717).  Fixed reduction order.
+template <int N>
+__global__ void __launch_bounds__(ColCfg<N, false>::THREADS, ColCfg<N, false>::MIN_CTAS)
+k_detector_cols(const cpx* __restrict__ Psi, float* __restrict__ partial, DetectorRings rings, float inv_l1,
+                float inv_l2, int lo_end, int hi_start, const cpx* __restrict__ tw)
+{
+    using C = ColCfg<N, false>;
+    extern __shared__ cpx smem[];
+    constexpr int E = C::E;
+    const ColCtx<N> ctx(smem);
+    const int theta = ctx.theta;
+    const int kx0 = band_col0(blockIdx.x * C::CW, lo_end, hi_start), kx = kx0 + ctx.line;
+    cpx x[E];
+    ctx.load(x, Psi + (size_t)blockIdx.y * N * N + kx0, KeepAll());
+    fft_line<N, E, -1>(x, ctx.sm, theta, tw, ctx);
+    const int i1 = kx > N / 2 ? kx - N : kx;
+    const float k1 = (float)i1 * inv_l1;
+    float acc[MAX_DETECTORS];
+#pragma unroll
+    for (int d = 0; d < MAX_DETECTORS; d++) acc[d] = 0.f;
+#pragma unroll
+    for (int m = 0; m < E; m++) {
+        const int ky = theta + m * C::T;
+        const int i2 = ky > N / 2 ? ky - N : ky;
+        const float k2v = (float)i2 * inv_l2;
+        const float ksq = k1 * k1 + k2v * k2v;
+        const float v = x[m].x * x[m].x + x[m].y * x[m].y;
+#pragma unroll
+        for (int d = 0; d < MAX_DETECTORS; d++)
+            if (d < rings.n && ksq >= rings.in2[d] && ksq < rings.out2[d]) acc[d] += v;
+    }
+    // deterministic CTA reduction: thread order within shared memory, then a serial sum
+    __syncthreads();
+    float* red = reinterpret_cast<float*>(smem);
+    for (int d = 0; d < rings.n; d++) {
+        red[threadIdx.x] = acc[d];
+        __syncthreads();
+        for (int s = C::THREADS / 2; s > 0; s >>= 1) {
+            if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * MAX_DETECTORS + d] = red[0];
+        __syncthreads();
+    }
+}
+
+// out[b][d] += weight * sum_tiles partial[b][tile][d]
+__global__ void k_detector_finish(const float* __restrict__ partial, float* __restrict__ out, int ntiles, int ndet,
+                                  int batch, float weight)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch * ndet) return;
+    const int b = i / ndet, d = i % ndet;
+    float s = 0.f;
+    for (int t = 0; t < ntiles; t++) s += partial[((size_t)b * ntiles + t) * MAX_DETECTORS + d];
+    out[(size_t)b * ndet + d] += weight * s;
+}
+
+int detector_tiles(const SweepGeom& g)
+{
+    FDES_DISPATCH_N(g.N, { return band_cols(g) / ColCfg<NN, false>::CW; });
+    return 0;
+}
+
+void launch_detector_cols(const SweepGeom& g, const cpx* Psi, float* partial, float* out, const DetectorRings& rings,
+                          float d1, float d2, float weight, int batch, cudaStream_t st)
+{
+    FDES_DISPATCH_N(g.N, {
+        using C = ColCfg<NN, false>;
+        static bool once = false;
+        if (!once) { allow_smem(k_detector_cols<NN>, C::SMEM); once = true; }
+        const int tiles = band_cols(g) / C::CW;
+        dim3 grid(tiles, batch);
+        k_detector_cols<NN><<<grid, C::THREADS, C::SMEM, st>>>(Psi, partial, rings, 1.f / ((float)NN * d1),
+                                                              1.f / ((float)NN * d2), g.lo_end, g.hi_start, g.tw);
+        const int n = batch * rings.n;
+        k_detector_finish<<<(n + 127) / 128, 128, 0, st>>>(partial, out, tiles, rings.n, batch, weight);
+    });
+}
+
 // ---------------------------------------------------------------------------------------------
 // twiddle tables (layout: fft_core.cuh) and geometry queries
 // ---------------------------------------------------------------------------------------------

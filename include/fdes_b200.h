@@ -88,6 +88,19 @@ int fdes_b200_simulate(fdes_b200_sim* sim, float* image_host, float* exitwave_ho
 int fdes_b200_potential_slices_count(const fdes_b200_sim* sim);
 int fdes_b200_potential(fdes_b200_sim* sim, float* out_host);
 
+/* ---- STEM probe scan (extension; FDES has mode 2 = one CBED probe at the grid centre only,
+ * src/multisliceSimulation.cu:572-581, and rejects mode: STEM inputs, src/rwQsc.cu:33-44) --------
+ * The .cnf must select mode 2.  A scan position is the reference's probe shifted periodically to
+ * xy_host[i] = (x, y) [m] relative to the grid centre; the specimen stays fixed.  Detector d
+ * integrates the diffraction intensity |FFT2 psi|^2 / N^2 (diffractionPattern,
+ * src/crystalMaker.cu:700-718) over k_in^2 <= |k|^2 < k_out^2 with k = sin(theta * 1e-3) / lambda,
+ * theta = det_mrad_host[d] = (inner, outer) [mrad] (detector convention of src/rwQsc.cu:723-730).
+ * out_host [nprobes][ndet], averaged over the frozen-phonon configurations; an empty specimen
+ * gives n1*n2 on a detector that covers the whole pattern.  Returns the CUDA-event milliseconds
+ * of the scan (negative on failure). */
+double fdes_b200_stem_scan(fdes_b200_sim* sim, int k, int nprobes, const float* xy_host, int ndet,
+                           const float* det_mrad_host, float* out_host);
+
 /* ---- building blocks (parity tests, benchmarks) ------------------------------------------- */
 /* next frozen-phonon coordinates for measurement k -> xyz_host [nAt][3]
  * (atomJitter_d, src/crystalMaker.cu:37-48; advances the XORWOW streams) */

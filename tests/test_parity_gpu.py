@@ -282,3 +282,76 @@ def test_srtio3_512_probe_against_oracle(fb, orc, tmp_path):
     specimens.write_cnf(cnf, image_size=512, border_size=0, slices=16, pixel_size=19.525e-10 / 512,
                         slice_thickness=1.9525e-10, atoms=atoms, voltage=200e3, mode=2, objective_aperture=20e-3)
     _oracle_vs_library(cnf, fb, orc)
+
+
+# ---------------------------------------------------------------------------------------------
+# STEM scan (extension): a scan position is the reference's mode-2 probe shifted periodically.  Oracle
+# (SURVEY.md section 8c): the reference algorithm in mode 2 with every atom translated by -r_p, the
+# detector an annular sum over the diffraction intensity before the detector tail.  Positions are
+# whole pixels so that the bilinear deposition of the translated atoms is the same deposition.
+# ---------------------------------------------------------------------------------------------
+def _oracle_stem(orc, p, Z, xyz_list, occ, pos, det_mrad):
+    ps = p.copy()
+    orc.set_sub_slices(ps, orc.sub_slice_ratio(ps.d3, ps.subSlTh))
+    mask = orc.band_mask(ps)
+    P = orc.fresnel_propagator(ps, mask)
+    Zl = orc.list_of_elements(Z)
+    N = ps.m1
+    kx = (orc.ow(N).astype(np.float32) / np.float32(N * ps.d1))[None, :]
+    ky = (orc.ow(N).astype(np.float32) / np.float32(N * ps.d2))[:, None]
+    ksq = (kx * kx + ky * ky).astype(np.float32)
+    rings = [((np.sin(np.float32(a * 1e-3)) / ps.lam) ** 2, (np.sin(np.float32(b * 1e-3)) / ps.lam) ** 2) for a, b in det_mrad]
+    out = np.zeros((len(pos), len(det_mrad)), np.float64)
+    for xyz in xyz_list:
+        for i, (px, py) in enumerate(pos):
+            shifted = xyz.copy()
+            shifted[:, 0] -= np.float32(px)
+            shifted[:, 1] -= np.float32(py)
+            psi = orc.incoming_wave(ps, 0, mask)
+            bins = orc.bin_atoms(shifted, ps)
+            for s in range(ps.m3):
+                V = orc.phase_grating(s, Z, Zl, shifted, occ, ps.imPot, ps, bins)
+                psi = orc.forward_propagation(psi, V, ps, P, mask)
+            I = orc.diffraction_pattern(psi, ps, 0, mask).astype(np.float64)
+            for d, (lo, hi) in enumerate(rings):
+                out[i, d] += I[(ksq >= lo) & (ksq < hi)].sum() / len(xyz_list)
+    return out
+
+
+@pytest.mark.parametrize("frozen", [0, 2])
+def test_stem_scan_against_oracle(frozen, fb, orc, tmp_path):
+    from fdes_b200 import specimens
+    N, d = 128, 0.25e-10
+    rng = np.random.default_rng(7)
+    atoms = specimens.random_slab(40, N * d * 0.55, 4 * 2e-10, seed=11, species=(79, 14, 8))   # central region only
+    cnf = tmp_path / "stem.cnf"
+    specimens.write_cnf(cnf, image_size=N, border_size=0, slices=4, pixel_size=d, slice_thickness=2e-10, atoms=atoms,
+                        voltage=200e3, mode=2, objective_aperture=12e-3, frozen_phonons=frozen,
+                        aberrations={"C1": (-2e-8, 0.0), "C3": (2e-4, 0.0)})
+    pos_px = np.array([[0, 0], [3, -5], [-7, 2], [12, 9]], np.float32)
+    pos = pos_px * np.float32(d)
+    det = np.array([[0, 10], [10, 25], [25, 45]], np.float32)
+    with fb.Simulation(cnf, batch=3) as sim:
+        got, ms = sim.stem_scan(pos, det)
+    p, Z, xyz, dwf, occ = orc.read_cnf(str(cnf))
+    if frozen:
+        x = orc.Xorwow(1, 3 * len(Z))
+        xyz_list = [orc.atom_jitter(xyz, dwf, x) for _ in range(frozen)]
+    else:
+        xyz_list = [xyz]
+    want = _oracle_stem(orc, p, Z, xyz_list, occ, pos, det)
+    assert got.shape == want.shape and ms > 0
+    assert np.all(want[:, 0] > 1.0)                       # the bright-field disc carries signal
+    np.testing.assert_allclose(got, want, rtol=TOL_INTENSITY, atol=1e-4 * want.max())
+    # empty specimen: the whole pattern integrates to n1*n2 (probe normalisation, src/multisliceSimulation.cu:578-580)
+    a0 = np.ascontiguousarray(atoms, np.float32)
+    a0[:, 3] = 1e-6
+    with fb.Simulation(cnf, atoms6=a0) as sim:
+        tot, _ = sim.stem_scan(pos[:2], np.array([[0, 1000]], np.float32))
+    np.testing.assert_allclose(tot, N * N, rtol=1e-5)
+
+
+def test_stem_scan_needs_probe_mode(fb):
+    with fb.Simulation(DATA / "tem64.cnf") as sim:
+        with pytest.raises(fb.FdesError, match="mode 2"):
+            sim.stem_scan(np.zeros((1, 2), np.float32), np.array([[0, 10]], np.float32))
