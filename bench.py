@@ -190,6 +190,7 @@ def run_ours(a):
     e2e_value = world * px * slices_per_step * a.steps / (e2e_ms * 1e-3) / 1e6
     assert np.isfinite(img).all() and img.mean() > 0.1, "FDES() returned an implausible image"
 
+    stem = None if a.no_stem else run_stem(a, fb, specimens, tmp, local, world, barrier, dist, torch)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -234,11 +235,51 @@ def run_ours(a):
                   "frac_of_peak": round(slice_bytes / (slice_ms * 1e-3) / 1e9 / peak, 4),
                   "frac_of_8TBps": round(slice_bytes / (slice_ms * 1e-3) / 1e9 / 8000.0, 4)},
     }
+    if stem is not None:
+        line["stem"] = stem
     if world == 1 and not a.no_cpu:
         line["cpu_baseline"] = cpu_baseline(cnf, a.cpu_seconds)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_stem(a, fb, specimens, tmp, local, world, barrier, dist, torch):
+    """Second metric of BASELINE.json: STEM probes/s on configs[3] (SrTiO3, 512^2 probe grid, 40 slices,
+    HAADF + ABF detectors).  Every rank scans its own `probes_per_gpu` positions of the raster (weak
+    scaling: 8 x 8192 = the 256 x 256 scan); the transmission stack is built once per call, inside the
+    timed region.  value = device time of the scan (CUDA events), e2e = wall time of the call with host
+    positions in and host detector signals out."""
+    cnf = tmp / "stem_512.cnf"
+    atoms = specimens.config_srtio3_stem_512(cnf)
+    pos = specimens.stem_raster(256)
+    rank = int(os.environ.get("RANK", "0"))
+    n = a.stem_probes
+    mine = pos[(rank * n) % len(pos):][:n]
+    det = np.array([[70.0, 200.0], [11.0, 22.0]], np.float32)      # HAADF, ABF [mrad]
+    with fb.Simulation(cnf, atoms6=np.ascontiguousarray(atoms, np.float32), gpu_index=local, batch=a.stem_batch) as sim:
+        sim.stem_scan(mine[:256], det)        # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        sig, dev_ms = sim.stem_scan(mine, det)
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        m1, m3, batch = sim.m1, sim.m3, sim.batch
+    t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms = float(t[0]), float(t[1])
+    peak, _ = peaks()
+    alg = 40.0 * m1 * m1 * m3 * n * world / (dev_ms * 1e-3) / 1e9      # A_prop = 40 B/px/slice (SURVEY 8d)
+    assert np.isfinite(sig).all() and sig[:, 0].min() > 0
+    return {"metric": "stem_probes_per_s", "value": round(world * n / (dev_ms * 1e-3), 1), "unit": "probes/s",
+            "e2e": {"value": round(world * n / (wall_ms * 1e-3), 1), "unit": "probes/s",
+                    "h2d_bytes_per_step": int(mine.nbytes), "d2h_bytes_per_step": int(sig.nbytes)},
+            "config": {"workload": "srtio3_stem_512", "grid": [m1, m1], "slices": m3, "atoms": int(len(atoms)),
+                       "probes_per_gpu": n, "batch": batch, "detectors_mrad": det.tolist()},
+            "roofline": {"bound": "hbm", "kernel": "S5+S6 per probe slice", "achieved": round(alg, 1), "peak": peak,
+                         "unit": "GB/s", "frac": round(alg / peak, 4), "algorithmic_bytes_per_px_slice": 40},
+            "haadf_mean": float(sig[:, 0].mean()), "abf_mean": float(sig[:, 1].mean())}
 
 
 def cpu_baseline(cnf, budget_s):
@@ -320,6 +361,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-stem", action="store_true")
+    ap.add_argument("--stem-probes", type=int, default=8192)
+    ap.add_argument("--stem-batch", type=int, default=32)
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":

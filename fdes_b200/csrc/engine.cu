@@ -172,7 +172,7 @@ Engine::Engine(const Params& pin, const Atoms& atoms, const EngineOptions& opt) 
     // batch buffers ((4 + nZ) complex grids per configuration) far below the 180 GB of HBM
     B_ = opt_.batch > 0 ? opt_.batch : 8;
     while (B_ > 1 && (size_t)B_ * (4 + nZ_) * (size_t)N_ * N_ * sizeof(cpx) > ((size_t)48 << 30)) B_ /= 2;
-    B_ = std::min(B_, mine);
+    if (opt_.batch <= 0) B_ = std::min(B_, mine);   // an explicit batch is honoured (STEM probes batch independently of the phonon count)
     const long long nk = (long long)p_.m3 * nZ_ * N_;
     if (nk >= (1LL << 31) - 2) throw std::runtime_error("slices * species * rows too large for 32-bit row keys");
     nkeys_ = (int)nk;
@@ -682,6 +682,9 @@ void Engine::stem_scan(int k, int nprobes, const float* xy_host, int ndet, const
                 launch_transmit_rows(g_, W_, tstack + (size_t)s * NN, npair, p_.imPot, 1, st_);
                 launch_bandlimit_cols(g_, tstack + (size_t)s * NN, 1, npair, st_);
             }
+            // (keeping t in real space instead, to save the per-probe inverse row transform of S5,
+            // measured SLOWER on B200: 8.3k vs 9.5k probes/s at 512^2 -- the transform hides the
+            // latency of the wave loads)
             tm_.kernel_launches += 4LL * ((p_.m3 + 1) / 2);
             for (int i0 = 0; i0 < nprobes; i0 += B_) {
                 const int nb = std::min(B_, nprobes - i0);

@@ -58,7 +58,7 @@ struct RowCfg {
     static constexpr int LSTRIDE = L::LS;
     static constexpr size_t SMEM = (size_t)RPB * LSTRIDE * sizeof(cpx);
     static constexpr bool WARP_SYNC = (T <= 32);       // a line lives inside one warp
-    static constexpr int MIN_CTAS = FDES_ROW_MIN_CTAS;
+    static constexpr int MIN_CTAS = N >= 2048 ? 2 : FDES_ROW_MIN_CTAS;   // long lines need the registers
 };
 // threads of one row line: warp-level sync when the line fits a warp, else a named barrier
 template <int N>

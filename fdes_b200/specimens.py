@@ -146,3 +146,20 @@ def config_random_4096(path, n_atoms: int = 100_000, slices: int = 500, frozen_p
               atoms=atoms if with_atoms else None, voltage=200e3, frozen_phonons=frozen_phonons,
               comment="synthetic random slab, 4096^2")
     return atoms
+
+
+def config_srtio3_stem_512(path, frozen_phonons: int = 0, with_atoms: bool = True):
+    """Config 4: SrTiO3 4 x 4 x 20 cells centred in a 5-cell-wide 512^2 box (d = 19.525 A / 512),
+    40 x 1.9525 A slices, 200 kV, 20 mrad probe (mode 2), no aberrations."""
+    atoms = srtio3_slab(4, 4, 20)
+    write_cnf(path, image_size=512, border_size=0, slices=40, pixel_size=19.525e-10 / 512, slice_thickness=1.9525e-10,
+              atoms=atoms if with_atoms else None, voltage=200e3, mode=2, objective_aperture=20e-3,
+              frozen_phonons=frozen_phonons, comment="SrTiO3 4x4x20 cells, 512^2, STEM probe")
+    return atoms
+
+
+def stem_raster(n_side: int, cell: float = 3.905e-10):
+    """n_side x n_side probe positions on a uniform raster over the central unit cell [m]."""
+    g = (np.arange(n_side) + 0.5) / n_side * cell - 0.5 * cell
+    xx, yy = np.meshgrid(g, g, indexing="xy")
+    return np.column_stack([xx.ravel(), yy.ravel()]).astype(np.float32)
