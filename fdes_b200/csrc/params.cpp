@@ -157,7 +157,17 @@ bool read_cnf(const char* file, Params& p, Atoms* atoms, bool atoms_from_externa
     int ts_i = 0, tb_i = 0, df_i = 0;
     char line[100], field[100] = "";
     do {
-        if (fgets(line, sizeof line, fr) != NULL) sscanf(line, "%99s", field);
+        if (fgets(line, sizeof line, fr) != NULL) {
+            // sscanf(line, "%99s", field): first whitespace-delimited token, field untouched when
+            // the line has none (hand-rolled: a specimen file is mostly atom lines)
+            const char* s = line;
+            while (*s == ' ' || *s == '\t' || *s == '\n' || *s == '\v' || *s == '\f' || *s == '\r') s++;
+            if (*s) {
+                int n = 0;
+                while (*s && !(*s == ' ' || *s == '\t' || *s == '\n' || *s == '\v' || *s == '\f' || *s == '\r') && n < 99) field[n++] = *s++;
+                field[n] = 0;
+            }
+        }
         dispatch_line(field, line, p, ts_i, tb_i, df_i);
     } while (!feof(fr));
     if (p.n3 < 1 || p.n3 > 1000) {

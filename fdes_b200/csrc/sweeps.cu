@@ -377,7 +377,7 @@ void launch_transmit_rows(const SweepGeom& g, const cpx* W, cpx* D, int npair, f
 // S4  band-limit columns
 // =============================================================================================
 template <int N>
-__global__ void __launch_bounds__(ColCfg<N, false>::THREADS, ColCfg<N, false>::MIN_CTAS)
+__global__ void __launch_bounds__(ColCfg<N, false>::THREADS, LineCfg<N>::T <= 32 ? 2 : ColCfg<N, false>::MIN_CTAS)
 k_bandlimit_cols(cpx* __restrict__ W, int npair, int lo_end, int hi_start, const cpx* __restrict__ tw)
 {
     using C = ColCfg<N, false>;

@@ -292,14 +292,10 @@ int main(int argc, char** argv)
 {
     const int reps = 20;
     run<1024, 32, 4, 1, 8, false, 1>(16, reps);
-    run_quad<1024, 32, 4, 1>(16, reps);
-    run_rowsT<1024, 32, 8, 1>(16, reps);
-    run_rowsT<1024, 32, 8, 2>(16, reps);
-    run_rowsT<1024, 32, 4, 1>(16, reps);
-    run_rowsT<1024, 32, 4, 4>(16, reps);
-    run_rowsT<1024, 32, 16, 1>(16, reps);
-    run_rowsT<1024, 32, 8, 2>(4, reps);
-    run_rowsT<1024, 32, 4, 4>(4, reps);
-    run_rowsT<512, 32, 16, 2>(16, reps);
+    run<1024, 16, 2, 4, 4, false, 2>(16, reps);
+    run<1024, 16, 2, 5, 4, false, 3>(16, reps);
+    run<1024, 16, 2, 6, 8, false, 1>(16, reps);
+    run<1024, 16, 4, 3, 8, false, 2>(16, reps);
+    run<1024, 8, 1, 8, 2, false, 4>(16, reps);
     return 0;
 }
