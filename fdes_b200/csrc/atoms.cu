@@ -6,6 +6,7 @@
 #include "kernels.cuh"
 #include <curand_kernel.h>   // header-only device XORWOW: same generator and seeding as the
                              // reference (curand_init / curand_normal, src/crystalMaker.cu:34,44)
+#include <cfloat>
 #include <cstdio>
 
 namespace fdes {
@@ -62,6 +63,28 @@ void launch_atom_jitter(float* xyz_out, const float* xyz_in, const float* dwf, i
 {
     k_atom_jitter<<<(3 * nAt + 127) / 128, 128, 0, st>>>(xyz_out, xyz_in, dwf, nAt,
                                                         static_cast<curandState*>(states), burn, nconf);
+}
+
+// ascombeNoise_d, src/crystalMaker.cu:50-70: Poisson noise via the Anscombe transform
+__global__ void k_anscombe_noise(cpx* f, size_t n, float dose, curandState* state)
+{
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    curandState local = state[i];
+    float fi = f[i].x * dose;
+    if (fi > 1e-2f) {
+        float x = curand_normal(&local);
+        x *= sqrtf(1 - expf(-fi / 0.777134f));
+        x += 2.f * sqrtf(fi + 0.375f) - 0.25f / sqrtf(fi);
+        x = roundf(0.25f * x * x - 0.375f);
+        if (x < FLT_MIN) x = 0.f;
+        f[i].x = x / dose;
+    }
+    state[i] = local;
+}
+void launch_anscombe_noise(cpx* f, size_t n, float dose, void* states, cudaStream_t st)
+{
+    k_anscombe_noise<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(f, n, dose, static_cast<curandState*>(states));
 }
 
 // ---------------------------------------------------------------------------------------------

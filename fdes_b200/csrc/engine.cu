@@ -144,8 +144,6 @@ Engine::Engine(const Params& pin, const Atoms& atoms, const EngineOptions& opt) 
     if (!fft_size_supported(p_.m1))
         throw std::runtime_error("grid size " + std::to_string(p_.m1) +
                                  " unsupported: sample size (image + 2*border) must be a power of two in [64, 4096]");
-    if (p_.pD > FLT_EPSILON)
-        throw std::runtime_error("pixel_dose > 0 (Poisson noise) is not implemented yet; set pixel_dose: 0");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         throw std::runtime_error("no CUDA device: fdes_b200 has no CPU fallback");
@@ -206,6 +204,7 @@ Engine::Engine(const Params& pin, const Atoms& atoms, const EngineOptions& opt) 
     plan.add(hist_, (size_t)B_ * 256 * sort_num_blocks(nrec_));
     plan.add(norm_partial_, 256); plan.add(norm_result_, 1);
     if (p_.frPh > 0) plan.add(rng_bytes_, rng_state_bytes() * 3 * (size_t)nAt_);
+    if (p_.pD > FLT_EPSILON) plan.add(noise_rng_, rng_state_bytes() * NN);   // one XORWOW stream per pixel
     pt.mark("ctor: stream+twiddles");
     arena_ = pool_acquire(plan.total(), opt_.gpu_index);
     pt.mark("ctor: arena");
@@ -226,6 +225,11 @@ Engine::Engine(const Params& pin, const Atoms& atoms, const EngineOptions& opt) 
     CK(cudaMemcpyAsync(xyzTO_, xyz0_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
     tilt(xyzTO_, p_.tilt_off[0], p_.tilt_off[1], p_.tilt_off[2]);
 
+    if (p_.pD > FLT_EPSILON) {
+        // Poisson-noise streams: seed 1 + n3, one per pixel (src/crystalMaker.cu:295)
+        launch_rng_init(noise_rng_, (int)NN, 1ULL + (unsigned long long)p_.n3, st_);
+        tm_.kernel_launches += 1;
+    }
     if (p_.frPh > 0) {
         launch_rng_init(rng_, 3 * nAt_, 1ULL, st_);   // seed 1, src/crystalMaker.cu:292
     }
@@ -499,12 +503,25 @@ void Engine::finish_k(int k, float* image_host, float* exitwave_host)
 {
     PhaseTimer pt;
     const size_t NN = (size_t)N_ * N_;
-    // addNoiseAndMtf (src/crystalMaker.cu:579-613) without the noise branch + copyMiddleOut
+    // addNoiseAndMtf (src/crystalMaker.cu:579-613) + copyMiddleOut
     DetectorParams dp{p_.mtfa, p_.mtfb, p_.mtfc, p_.mtfd, p_.illangle, p_.defoci[k], p_.lambda,
                       p_.d1, p_.d2, p_.cst_pi, p_.mode, fabsf(p_.illangle) > FLT_EPSILON ? 1 : 0};
-    launch_detector_table(det_, N_, dp, 1.f / ((float)(N_ * N_)), st_);
+    const float inv_nn = 1.f / ((float)(N_ * N_));
     RowOpts ri; ri.in_is_real = true;
     launch_rows_fft(g_, I_, scratch_, -1, ROW_STORE, ri, 1, st_);
+    if (p_.pD > FLT_EPSILON) {
+        // envelope -> back to real space -> Anscombe/Poisson noise -> forward again (:591-603)
+        DetectorParams de = dp; de.use_mtf = 0;
+        launch_detector_table(det_, N_, de, inv_nn, st_);
+        launch_cols_fft(g_, scratch_, scratch_, -1, COL_MUL_REAL_INV, det_, 1.f, 1, st_);
+        RowOpts rr;
+        launch_rows_fft(g_, scratch_, scratch_, +1, ROW_STORE, rr, 1, st_);
+        launch_anscombe_noise(scratch_, NN, p_.pD, noise_rng_, st_);
+        launch_rows_fft(g_, scratch_, scratch_, -1, ROW_STORE, rr, 1, st_);
+        dp.use_incoherence = 0;   // already applied
+        tm_.kernel_launches += 5;
+    }
+    launch_detector_table(det_, N_, dp, inv_nn, st_);
     launch_cols_fft(g_, scratch_, scratch_, -1, COL_MUL_REAL_INV, det_, 1.f, 1, st_);
     RowOpts rc; rc.dn1 = p_.dn1; rc.dn2 = p_.dn2; rc.n1 = p_.n1; rc.n2 = p_.n2;
     launch_rows_fft(g_, scratch_, J_, +1, ROW_CROP_REAL, rc, 1, st_);

@@ -109,6 +109,7 @@ private:
     int* zidx_ = nullptr;
     void* rng_ = nullptr;
     unsigned char* rng_bytes_ = nullptr;
+    unsigned char* noise_rng_ = nullptr;   // per-pixel XORWOW states of the Poisson noise (pixel_dose > 0)
     void* arena_ = nullptr;           // the one device block all buffers above are carved from
     std::vector<cpx> tw_host_;
     int rng_burn_ = 0;          // normals to discard before this rank's first configuration

@@ -113,6 +113,7 @@ void launch_lens_table(cpx* tab, int N, const LensParams& lp, float extra_scale,
 struct DetectorParams {
     float mtfa, mtfb, mtfc, mtfd, illangle, defocus_k, lambda, d1, d2, pi;
     int mode; int use_incoherence;
+    int use_mtf = 1;   // 0: incoherence envelope only (the stage before the noise, src/crystalMaker.cu:591-599)
 };
 void launch_detector_table(float* tab, int N, const DetectorParams& dp, float scale, cudaStream_t st);
 
@@ -134,6 +135,10 @@ void launch_tilt_beam(cpx* psi, int N, float d1, float d2, float lambda, float t
                       float pi, int flag, cudaStream_t st);
 void launch_tukey_window(cpx* psi, int N, int dn1, int dn2, float pi, cudaStream_t st);
 void launch_area_mask_blend(cpx* psi, int N, int dn1, int dn2, cudaStream_t st);
+
+// Poisson noise through the Anscombe transform on the real part of f (ascombeNoise_d,
+// src/crystalMaker.cu:50-70); states: XORWOW streams curand_init(1 + n3, pixel, 0) (:295)
+void launch_anscombe_noise(cpx* f, size_t n, float dose, void* states, cudaStream_t st);
 
 // ---- atoms: tilt, frozen phonons, binning, sort, row pointers -----------------------------
 struct BinGeom {

@@ -160,7 +160,7 @@ __global__ void k_detector_table(float* __restrict__ tab, int N, DetectorParams 
     nu1 *= dp.pi;
     nu2 *= dp.pi;
     mtf *= ((sinf(nu1) + FLT_EPSILON) / (nu1 + FLT_EPSILON)) * ((sinf(nu2) + FLT_EPSILON) / (nu2 + FLT_EPSILON));
-    tab[i] = f * mtf * scale;
+    tab[i] = dp.use_mtf ? f * mtf * scale : f * scale;
 }
 
 void launch_detector_table(float* tab, int N, const DetectorParams& dp, float scale, cudaStream_t st)

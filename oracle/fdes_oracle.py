@@ -716,6 +716,7 @@ def add_noise_and_mtf(I: np.ndarray, p: Params, k: int, noise_normals: Optional[
         dose = f32(p.pD)
         fi = (fr * dose).astype(f32)
         sel = fi > f32(1e-2)
+        assert sel.all(), "restatement limited to images where every pixel draws (see build_measurements)"
         n = noise_normals.reshape(fi.shape).astype(f32)
         with np.errstate(invalid="ignore", divide="ignore"):
             v = (n * np.sqrt((f32(1) - np.exp((-fi / f32(0.777134)).astype(f32))).astype(f32))).astype(f32)
@@ -897,6 +898,10 @@ def build_measurements(p_in: Params, Z, xyz, dwf, occ, *, jitter_coords: Optiona
     image = np.zeros((p.n3, p.n2, p.n1), f32)
     exitwave = np.zeros((p.n3, p.m2, p.m1), c64)
     I = None
+    # Poisson noise: one XORWOW stream per pixel, curand_init(1 + n3, pixel, 0) (src/crystalMaker.cu:295);
+    # a stream advances only where a pixel draws (fi > 1e-2, :58) -- this restatement draws for every
+    # pixel and therefore requires that condition to hold everywhere (checked in add_noise_and_mtf).
+    noise_rng = Xorwow(1 + p.n3, p.m1 * p.m2) if f32(p.pD) > FLT_EPSILON else None
     for k in range(p.n3):
         I = np.zeros((p.m2, p.m1), f32)
         xyz_k = tilt_coordinates(xyzTO, p.tiltspec[2 * k], p.tiltspec[2 * k + 1], 0.0)
@@ -919,5 +924,5 @@ def build_measurements(p_in: Params, Z, xyz, dwf, occ, *, jitter_coords: Optiona
             else:
                 inten = diffraction_pattern(psi, p, k, mask)
             I = (I + alpha * inten).astype(f32)
-        image[k] = add_noise_and_mtf(I.astype(c64), p, k)
+        image[k] = add_noise_and_mtf(I.astype(c64), p, k, noise_rng.normal() if noise_rng is not None else None)
     return Result(image=image, exitwave=exitwave, params=p, I=I)
