@@ -68,3 +68,39 @@ def simulate_sharded(open_sim: Callable[[int, int], object], *, want_exitwave: b
         return image, exitwave
     finally:
         sim.close()
+
+
+def stem_scan_sharded(open_sim: Callable[[int, int], object], positions, detectors_mrad, *, k: int = 0, group=None,
+                      device=None):
+    """STEM scan with the probe positions sharded over the ranks of `group` (contiguous blocks of the
+    raster, the same ranges as `shard_range`); every rank builds the transmission stack of each
+    frozen-phonon configuration itself (no exchange), and one all-gather of the detector signals
+    ([n_probes, n_detectors] float32, <= 512 KB for a 256 x 256 scan) gives every rank the full result.
+
+    open_sim(rank, world) returns an object with `stem_scan(positions, detectors_mrad, k) -> (signals, ms)`
+    (fdes_b200.Simulation opened WITHOUT rank/world sharding: all configurations on every rank)."""
+    import torch
+    import torch.distributed as dist
+
+    positions = np.ascontiguousarray(positions, np.float32).reshape(-1, 2)
+    det = np.ascontiguousarray(detectors_mrad, np.float32).reshape(-1, 2)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = shard_range(len(positions), rank, world)
+    sim = open_sim(rank, world)
+    try:
+        mine, _ = sim.stem_scan(positions[lo:hi], det, k) if hi > lo else (np.zeros((0, len(det)), np.float32), 0.0)
+    finally:
+        sim.close()
+    if world == 1:
+        return mine
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                             if torch.cuda.is_available() else torch.device("cpu"))
+    longest = max(b - a for a, b in (shard_range(len(positions), r, world) for r in range(world)))
+    send = torch.zeros((longest, len(det)), dtype=torch.float32, device=dev)
+    send[: hi - lo] = torch.from_numpy(np.ascontiguousarray(mine)).to(dev)
+    parts = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(parts, send, group=group)
+    out = [parts[r][: b - a].cpu().numpy() for r, (a, b) in
+           ((r, shard_range(len(positions), r, world)) for r in range(world))]
+    return np.concatenate(out, axis=0)

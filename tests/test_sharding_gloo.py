@@ -105,3 +105,35 @@ def test_two_ranks_equal_single_process(case, tmp_path, oracle_runs):
     ref, _ = oracle_runs(case)                                 # single-process oracle, all configurations
     assert rel_l2(r0["ew"], ref.exitwave) < TOL_WAVE
     assert rel_l2(r0["img"], ref.image) < TOL_INTENSITY
+
+
+class FakeStemSession:
+    """stem_scan stand-in: a deterministic function of the probe position (checks ranges / ordering)."""
+    def stem_scan(self, pos, det, k=0):
+        pos = np.asarray(pos, np.float32)
+        return np.stack([pos[:, 0] * 3 + pos[:, 1], pos[:, 0] - 2 * pos[:, 1]], 1).astype(np.float32), 1.0
+
+    def close(self):
+        pass
+
+
+def _stem_worker(rank, world, port, out):
+    sys.path.insert(0, str(ROOT))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fdes_b200.distributed import stem_scan_sharded
+    pos = np.arange(2 * 37, dtype=np.float32).reshape(37, 2)      # 37 probes: uneven split
+    sig = stem_scan_sharded(lambda r, w: FakeStemSession(), pos, np.array([[0, 10], [10, 20]], np.float32),
+                            device=torch.device("cpu"))
+    np.save(f"{out}/stem{rank}.npy", sig)
+    dist.destroy_process_group()
+
+
+def test_stem_positions_are_sharded_and_gathered(tmp_path):
+    mp.spawn(_stem_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "stem0.npy"), np.load(tmp_path / "stem1.npy")
+    pos = np.arange(2 * 37, dtype=np.float32).reshape(37, 2)
+    want, _ = FakeStemSession().stem_scan(pos, None)
+    np.testing.assert_array_equal(a, want)
+    np.testing.assert_array_equal(b, want)
