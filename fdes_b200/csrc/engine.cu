@@ -434,19 +434,24 @@ void Engine::accumulate_outputs(int k, int nb)
         lens_k_ = k;
         tm_.kernel_launches += 1;
     }
+    // exit wave and imaging-mode intensity: the batch is summed inside one launch, in the fixed
+    // order b = 0 .. nb-1 (deterministic phonon average)
+    if (ew_) {
+        RowOpts ro; ro.scale = alpha; ro.band_only_in = true;
+        launch_rows_fft_sum(g_, Psi_, ew_, +1, ROW_ACCUM, ro, nb, st_);
+        tm_.kernel_launches += 1;
+    }
+    if (p_.mode == 0) {
+        // W_ is free after the slice loop: CTF-filtered waves of the whole batch
+        launch_cols_fft(g_, Psi_, W_, -1, COL_MUL_CPX_INV, lens_, 1.f / ((float)N_), nb, st_);
+        RowOpts ro; ro.scale = alpha;
+        launch_rows_fft_sum(g_, W_, I_, +1, ROW_INTENS_ACCUM, ro, nb, st_);
+        tm_.kernel_launches += 2;
+        return;
+    }
     for (int b = 0; b < nb; b++) {   // fixed order: deterministic phonon average
         cpx* psi = Psi_ + (size_t)b * NN;
-        if (ew_) {
-            RowOpts ro; ro.scale = alpha; ro.band_only_in = true;
-            launch_rows_fft(g_, psi, ew_, +1, ROW_ACCUM, ro, 1, st_);
-            tm_.kernel_launches += 1;
-        }
-        if (p_.mode == 0) {
-            launch_cols_fft(g_, psi, scratch_, -1, COL_MUL_CPX_INV, lens_, 1.f / ((float)N_), 1, st_);
-            RowOpts ro; ro.scale = alpha;
-            launch_rows_fft(g_, scratch_, I_, +1, ROW_INTENS_ACCUM, ro, 1, st_);
-            tm_.kernel_launches += 2;
-        } else {
+        {
             // diffractionPattern, src/crystalMaker.cu:700-718
             // |fftshift(FFT2 psi)|^2 / N^2: FFT_col(Psi) = FFT2(psi) / N already carries the 1/N
             const float scale = alpha;

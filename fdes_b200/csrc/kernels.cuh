@@ -81,6 +81,11 @@ struct RowOpts {
 void launch_rows_fft(const SweepGeom& g, const void* in, void* out, int dir, RowEpilogue epi,
                      const RowOpts& o, int batch, cudaStream_t st);
 
+// batch-summing variant (fixed order b = 0..nb-1): out (+)= sum_b epilogue(FFT_dir(in[b])), for the
+// inverse transform with ROW_ACCUM (complex out) or ROW_INTENS_ACCUM (float out)
+void launch_rows_fft_sum(const SweepGeom& g, const cpx* in, void* out, int dir, RowEpilogue epi,
+                         const RowOpts& o, int nb, cudaStream_t st);
+
 enum ColOp {
     COL_PLAIN = 0,        // out = FFT_dir(in)
     COL_MUL_CPX_INV = 1,  // out = IFFT( FFT(in) * tab_c[ky][kx] )      (lens function / CTF)

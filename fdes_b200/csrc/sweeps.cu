@@ -597,6 +597,78 @@ void launch_rows_fft(const SweepGeom& g, const void* in, void* out, int dir, Row
     });
 }
 
+// Sum over a batch in a fixed order (deterministic phonon average): for b = 0 .. nb-1 in turn,
+// transform row y of in[b] and add scale * v (EPI = ROW_ACCUM, complex out) or scale * |v|^2
+// (EPI = ROW_INTENS_ACCUM, float out) -- one read-modify-write of `out` per batch instead of per
+// configuration.
+template <int N, int DIR, int EPI>
+__global__ void __launch_bounds__(RowCfg<N>::THREADS, RowCfg<N>::MIN_CTAS)
+k_rows_fft_sum(const cpx* __restrict__ in, void* __restrict__ out_, RowOpts o, int nb, int lo_end,
+               int hi_start, const cpx* __restrict__ tw)
+{
+    using C = RowCfg<N>;
+    extern __shared__ cpx smem[];
+    constexpr int E = C::E;
+    const int line = threadIdx.x / C::T, theta = threadIdx.x % C::T;
+    const RowSync<N> sync(line);
+    const int y = blockIdx.x * C::RPB + line;
+    const size_t rowoff = (size_t)y * N;
+    cpx acc[EPI == ROW_ACCUM ? E : 1];
+    float acci[EPI == ROW_ACCUM ? 1 : E];
+    // start from the current content of `out`: the additions then happen in exactly the order and
+    // rounding of nb successive single-configuration accumulations (results do not depend on nb)
+#pragma unroll
+    for (int m = 0; m < E; m++) {
+        const int xx = theta + m * C::T;
+        if (EPI == ROW_ACCUM) acc[m] = static_cast<const cpx*>(out_)[rowoff + xx];
+        else acci[m] = static_cast<const float*>(out_)[rowoff + xx];
+    }
+#pragma unroll 1
+    for (int b = 0; b < nb; b++) {
+        const cpx* src = in + (size_t)b * N * N + rowoff;
+        cpx x[E];
+#pragma unroll
+        for (int m = 0; m < E; m++) {
+            const int kx = theta + m * C::T;
+            x[m] = (!o.band_only_in || in_band(kx, lo_end, hi_start)) ? src[kx] : make_float2(0.f, 0.f);
+        }
+        fft_line<N, E, DIR>(x, smem + line * C::LSTRIDE, theta, tw, sync);
+        // same rounding sequence as nb successive single accumulations: out += scale * v
+#pragma unroll
+        for (int m = 0; m < E; m++) {
+            if (EPI == ROW_ACCUM) { acc[m].x += x[m].x * o.scale; acc[m].y += x[m].y * o.scale; }   // as k_rows_fft: v = x * scale; old + v
+            else acci[m] += o.scale * (x[m].x * x[m].x + x[m].y * x[m].y);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < E; m++) {
+        const int xx = theta + m * C::T;
+        if (EPI == ROW_ACCUM) static_cast<cpx*>(out_)[rowoff + xx] = acc[m];
+        else static_cast<float*>(out_)[rowoff + xx] = acci[m];
+    }
+}
+
+void launch_rows_fft_sum(const SweepGeom& g, const cpx* in, void* out, int dir, RowEpilogue epi,
+                         const RowOpts& o, int nb, cudaStream_t st)
+{
+    FDES_DISPATCH_N(g.N, {
+        using C = RowCfg<NN>;
+        dim3 grid(NN / C::RPB);
+        if (dir > 0 && epi == ROW_ACCUM) {
+            static bool once = false;
+            if (!once) { allow_smem(k_rows_fft_sum<NN, 1, ROW_ACCUM>, C::SMEM); once = true; }
+            k_rows_fft_sum<NN, 1, ROW_ACCUM><<<grid, C::THREADS, C::SMEM, st>>>(in, out, o, nb, g.lo_end, g.hi_start, g.tw);
+        } else if (dir > 0 && epi == ROW_INTENS_ACCUM) {
+            static bool once = false;
+            if (!once) { allow_smem(k_rows_fft_sum<NN, 1, ROW_INTENS_ACCUM>, C::SMEM); once = true; }
+            k_rows_fft_sum<NN, 1, ROW_INTENS_ACCUM><<<grid, C::THREADS, C::SMEM, st>>>(in, out, o, nb, g.lo_end, g.hi_start, g.tw);
+        } else {
+            fprintf(stderr, "fdes_b200: launch_rows_fft_sum supports inverse transforms with ROW_ACCUM / ROW_INTENS_ACCUM\n");
+            abort();
+        }
+    });
+}
+
 // =============================================================================================
 // generic column sweep
 // =============================================================================================
