@@ -314,14 +314,18 @@ def run_reference(a):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_harness not built (needs /root/reference + make -C oracle)"}))
         return
     from fdes_b200 import specimens
-    cps = a.configs_per_step or DEFAULT_CONFIGS_PER_STEP[a.workload]
+    # Bounded sample: the reference needs 0.1 - 1 s per configuration of this workload, so a step
+    # is `ref_configs` configurations (default 2, not the 16 of our arm -- the metric is per
+    # pixel*slice) and the run stops after --ref-seconds even if fewer than --steps steps are done
+    # (the line reports the steps that were timed).
+    cps = a.ref_configs
     tmp = pathlib.Path(tempfile.mkdtemp(prefix="fdes_bench_ref_"))
     cnf = tmp / f"{a.workload}.cnf"
     atoms = getattr(specimens, WORKLOADS[a.workload][0])(cnf, frozen_phonons=cps)
     env = dict(os.environ, TMPDIR=str(tmp), CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
     with ClockSampler(0) as clk:
-        r = subprocess.run([str(harness), "e2e", str(cnf), str(a.steps), str(a.warmup)], env=env, capture_output=True,
-                           text=True, timeout=3000)
+        r = subprocess.run([str(harness), "e2e", str(cnf), str(a.steps), str(a.warmup), str(a.ref_seconds)], env=env,
+                           capture_output=True, text=True, timeout=3000)
     js = [l for l in r.stdout.splitlines() if l.startswith('{"ref_e2e"')]
     if r.returncode != 0 or not js:
         print(json.dumps({"impl": "reference", "unavailable": f"ref_harness failed rc={r.returncode}: {r.stderr[-300:]}"}))
@@ -333,7 +337,7 @@ def run_reference(a):
     value = j["mpx_slices_per_s"]
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world,
-        "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(j["ms_per_call"], 4), "higher_is_better": True,
+        "steps": j["reps"], "steps_requested": a.steps, "warmup": a.warmup, "ms_per_step": round(j["ms_per_call"], 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "complex64 (f32)", "data": "synthetic",
         "config": {"workload": a.workload, "description": WORKLOADS[a.workload][1], "grid": [j["m1"], j["m2"]],
                    "slices": j["slices"], "atoms": int(len(atoms)), "configs_per_step_per_gpu": cps,
@@ -341,7 +345,7 @@ def run_reference(a):
                            "multi-GPU path; whole-call wall time of its exported flow (getParams -> "
                            "readAtomsFromArray -> buildMeasurements -> image copy)"},
         "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": 1, "kind": "reference",
-                         "sample": f"{a.steps} call(s) x {cps} configurations x {j['slices']} slices; 1 host thread "
+                         "sample": f"{j['reps']} call(s) x {cps} configurations x {j['slices']} slices (bounded to {a.ref_seconds:.0f} s); 1 host thread "
                                    "driving 1 B200 (the reference's only implementation is CUDA)"},
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "clocks": clk.summary(),
@@ -360,6 +364,8 @@ def main():
     ap.add_argument("--configs-per-step", type=int, default=0)
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ref-configs", type=int, default=2)
+    ap.add_argument("--ref-seconds", type=float, default=120.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stem", action="store_true")
     ap.add_argument("--stem-probes", type=int, default=8192)

@@ -36,7 +36,7 @@
  *   ref_harness time  <input.{cnf,qsc}> <reps> <configs_per_rep>
  *       CUDA-event time of the slice loop (phaseGrating+forwardPropagation),
  *       prints one JSON line.
- *   ref_harness e2e   <input.cnf> <reps> <warmup>
+ *   ref_harness e2e   <input.cnf> <reps> <warmup> [time budget in seconds]
  *       whole-call wall time of the reference's exported entry point, replayed
  *       step by step as src/FDESExport.cu:59-178 does it (atoms handed over as a
  *       host array, image copied back into a host buffer): getParams ->
@@ -285,7 +285,7 @@ static int modeTime(const std::string& in, int reps, int configs)
     return 0;
 }
 
-static int modeE2E(const std::string& in, int reps, int warm)
+static int modeE2E(const std::string& in, int reps, int warm, double budget_s)
 {
     /* atoms as a host [nAt][6] array, taken once from the file */
     params_t* p0 = NULL; int* Z_d = NULL; float *xyz_d = NULL, *DWF_d = NULL, *occ_d = NULL;
@@ -309,6 +309,7 @@ static int modeE2E(const std::string& in, int reps, int warm)
     freeParams(&p0);
     std::vector<double> ms;
     int slices = 0;
+    double spent_s = 0;
     for (int rep = 0; rep < reps + warm; rep++) {
         cudaDeviceSynchronize();
         timespec t0, t1;
@@ -325,7 +326,11 @@ static int modeE2E(const std::string& in, int reps, int warm)
         cudaFree(xyz_d); cudaFree(DWF_d); cudaFree(occ_d); cudaFree(Z_d);
         cudaDeviceSynchronize();
         clock_gettime(CLOCK_MONOTONIC, &t1);
-        if (rep >= warm) ms.push_back((t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6);
+        const double call_ms = (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
+        if (rep >= warm) ms.push_back(call_ms);
+        spent_s += call_ms * 1e-3;
+        /* bounded run: stop once the time budget is used up (at least one timed call) */
+        if (budget_s > 0 && spent_s > budget_s && !ms.empty()) break;
     }
     double sum = 0; for (double t : ms) sum += t;
     const double mean_ms = sum / ms.size();
@@ -334,7 +339,7 @@ static int modeE2E(const std::string& in, int reps, int warm)
     double chk = 0; for (float v : dst) chk += v;
     printf("{\"ref_e2e\": true, \"m1\": %d, \"m2\": %d, \"slices\": %d, \"configs\": %d, \"nAt\": %d, "
            "\"reps\": %d, \"ms_per_call\": %.6f, \"mpx_slices_per_s\": %.6f, \"image_mean\": %.6f}\n",
-           m1, m2, slices, count, nAt, reps, mean_ms, pxsl / (mean_ms * 1e-3) / 1e6, chk / n123);
+           m1, m2, slices, count, nAt, (int)ms.size(), mean_ms, pxsl / (mean_ms * 1e-3) / 1e6, chk / n123);
     return 0;
 }
 
@@ -351,7 +356,7 @@ int main(int argc, char** argv)
         /* side-effect files of the readers (dataFDES_used.cnf, ...) go to a scratch dir */
         const char* tmp = getenv("TMPDIR") ? getenv("TMPDIR") : "/tmp";
         if (chdir(tmp) != 0) return 3;
-        if (mode == "e2e") return modeE2E(in, atoi(argv[3]), argc > 4 ? atoi(argv[4]) : 1);
+        if (mode == "e2e") return modeE2E(in, atoi(argv[3]), argc > 4 ? atoi(argv[4]) : 1, argc > 5 ? atof(argv[5]) : 0.0);
         return modeTime(in, atoi(argv[3]), argc > 4 ? atoi(argv[4]) : 1);
     }
     g_outdir = absPath(argv[3]);
