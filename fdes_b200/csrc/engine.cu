@@ -164,7 +164,6 @@ Engine::Engine(const Params& pin, const Atoms& atoms, const EngineOptions& opt) 
     const int world = std::max(1, opt_.world), rank = std::min(std::max(0, opt_.rank), world - 1);
     j0_ = (int)(((long long)count_ * rank) / world);
     j1_ = (int)(((long long)count_ * (rank + 1)) / world);
-    rng_burn_ = j0_;
     const int mine = std::max(1, j1_ - j0_);
     // configurations advanced together: 8 fills the GPU at every supported grid size and keeps the
     // batch buffers ((4 + nZ) complex grids per configuration) far below the 180 GB of HBM
@@ -371,8 +370,13 @@ void Engine::bin_and_sort(int b0, int nconf, const float* xyz_dev)
 void Engine::prepare_batch(int nb, const float* xyz_k)
 {
     if (p_.frPh > 0) {
-        launch_atom_jitter(xyzFP_, xyz_k, dwf_, nAt_, rng_, rng_burn_, nb, st_);
-        rng_burn_ = 0;
+        // the XORWOW streams are consumed in the global order (k, j) of the single-GPU reference:
+        // skip the normals that belong to configurations of other ranks (or other calls)
+        const long long burn = rng_target_ - rng_pos_;
+        if (burn < 0) throw std::runtime_error("frozen-phonon configurations must be visited in increasing (k, j) order");
+        launch_atom_jitter(xyzFP_, xyz_k, dwf_, nAt_, rng_, (int)burn, nb, st_);
+        rng_pos_ = rng_target_ + nb;
+        rng_target_ = rng_pos_;
         tm_.kernel_launches += 1;
     } else {
         for (int b = 0; b < nb; b++)
@@ -493,6 +497,7 @@ void Engine::run_k(int k)
     make_incident(k);
     for (int j = j0_; j < j1_; j += B_) {
         const int nb = std::min(B_, j1_ - j);
+        rng_target_ = std::max(rng_pos_, (long long)k * count_ + j);   // position of configuration (k, j)
         prepare_batch(nb, xyzK_);
         for (int b = 0; b < nb; b++)
             CK(cudaMemcpyAsync(Psi_ + (size_t)b * NN, psi_in_, NN * sizeof(cpx), cudaMemcpyDeviceToDevice, st_));
@@ -571,7 +576,7 @@ void Engine::next_jittered_coords(int k, float* xyz_host)
 {
     CK(cudaMemcpyAsync(xyzK_, xyzTO_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
     tilt(xyzK_, p_.tiltspec[2 * k], p_.tiltspec[2 * k + 1], 0.f);
-    if (p_.frPh > 0) { launch_atom_jitter(xyzFP_, xyzK_, dwf_, nAt_, rng_, rng_burn_, 1, st_); rng_burn_ = 0; }
+    if (p_.frPh > 0) { launch_atom_jitter(xyzFP_, xyzK_, dwf_, nAt_, rng_, 0, 1, st_); rng_pos_ += 1; rng_target_ = rng_pos_; }
     else CK(cudaMemcpyAsync(xyzFP_, xyzK_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
     CK(cudaMemcpyAsync(xyz_host, xyzFP_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToHost, st_));
     CK(cudaStreamSynchronize(st_));
@@ -695,6 +700,7 @@ void Engine::stem_scan(int k, int nprobes, const float* xy_host, int ndet, const
         CK(cudaEventRecord(ev0_, st_));
         const float weight = 1.f / (float)count_;
         for (int j = j0_; j < j1_; j++) {
+            rng_target_ = std::max(rng_pos_, (long long)k * count_ + j);
             prepare_batch(1, xyzK_);
             for (int s = 0; s < p_.m3; s += 2) {   // transmission stack of this configuration
                 const int npair = std::min(2, p_.m3 - s);

@@ -112,7 +112,8 @@ private:
     unsigned char* noise_rng_ = nullptr;   // per-pixel XORWOW states of the Poisson noise (pixel_dose > 0)
     void* arena_ = nullptr;           // the one device block all buffers above are carved from
     std::vector<cpx> tw_host_;
-    int rng_burn_ = 0;          // normals to discard before this rank's first configuration
+    long long rng_pos_ = 0;     // normals every XORWOW stream has produced so far
+    long long rng_target_ = 0;  // position of the next configuration in the reference's (k, j) order
     uint32_t *keys_ = nullptr, *keys_tmp_ = nullptr;
     int *cols_ = nullptr, *cols_tmp_ = nullptr, *rowptr_ = nullptr, *bins_ = nullptr;
     float *w_ = nullptr, *w_tmp_ = nullptr;

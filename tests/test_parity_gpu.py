@@ -118,32 +118,45 @@ def test_batching_does_not_change_results(batch, fb):
     np.testing.assert_array_equal(ea, eb)
 
 
-def test_rank_shards_sum_to_the_whole(fb):
-    """rank/world sharding of the phonon configurations incl. the RNG burn-in: the partial sums
-    of (rank 0, rank 1) of 2 add up to the single-rank result."""
+def test_rank_shards_sum_to_the_whole(fb, tmp_path):
+    """rank/world sharding of the phonon configurations incl. the RNG positioning: for every
+    measurement k the partial sums of (rank 0, rank 1) of 2 add up to the single-rank result (the
+    XORWOW streams are consumed in the reference's global (k, j) order on every rank)."""
     import torch
-    with fb.Simulation(DATA / "phonon64.cnf", want_exitwave=True) as whole:
-        whole.run_k(0)
-        img_w, ew_w = whole.finish_k(0)
+    from fdes_b200 import specimens
+    cnf = tmp_path / "ph2.cnf"
+    atoms = specimens.random_slab(30, 64 * 0.25e-10 * 0.8, 4 * 2e-10, seed=3, species=(38, 22, 8))
+    specimens.write_cnf(cnf, image_size=32, border_size=16, slices=4, pixel_size=0.25e-10, slice_thickness=2e-10,
+                        atoms=atoms, frozen_phonons=3, image_size_z=2, defoci=[2e-9, -5e-9],
+                        aberrations={"C3": (1e-3, 0.0)}, objective_aperture=0.02)
+    with fb.Simulation(cnf, want_exitwave=True) as whole:
+        ref = []
+        for k in range(2):
+            whole.run_k(k)
+            ref.append(whole.finish_k(k))
     n = 64 * 64
     accI = torch.zeros(n, dtype=torch.float32, device="cuda")
     accE = torch.zeros(2 * n, dtype=torch.float32, device="cuda")
-    sumI = torch.zeros_like(accI)
-    sumE = torch.zeros_like(accE)
-    for r in range(2):
-        with fb.Simulation(DATA / "phonon64.cnf", want_exitwave=True, rank=r, world=2) as part:
-            part.set_accumulators(accI.data_ptr(), accE.data_ptr())
-            part.run_k(0)
-            torch.cuda.synchronize()
-            sumI += accI
-            sumE += accE
-            if r == 1:
-                accI.copy_(sumI)
-                accE.copy_(sumE)
+    parts = [fb.Simulation(cnf, want_exitwave=True, rank=r, world=2) for r in range(2)]
+    try:
+        for k in range(2):
+            sumI = torch.zeros_like(accI)
+            sumE = torch.zeros_like(accE)
+            for part in parts:
+                part.set_accumulators(accI.data_ptr(), accE.data_ptr())
+                part.run_k(k)
                 torch.cuda.synchronize()
-                img_s, ew_s = part.finish_k(0)
-    assert rel_l2(ew_s, ew_w) < 1e-6
-    assert rel_l2(img_s, img_w) < 1e-6
+                sumI += accI
+                sumE += accE
+            accI.copy_(sumI)
+            accE.copy_(sumE)
+            torch.cuda.synchronize()
+            img_s, ew_s = parts[1].finish_k(k)
+            assert rel_l2(ew_s, ref[k][1]) < 1e-6, k
+            assert rel_l2(img_s, ref[k][0]) < 1e-6, k
+    finally:
+        for part in parts:
+            part.close()
 
 
 # ---------------------------------------------------------------------------------------------
