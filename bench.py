@@ -48,8 +48,10 @@ WORKLOADS = {
     # name: (builder, description, species count)
     "si001_1024": ("config_si001_1024", "Si[001] 11552 atoms, 1024^2 grid, 11 x 2 A slices, 100 kV (BASELINE configs[1])"),
     "au_2048": ("config_au_2048", "Au cuboctahedron 309 atoms, 2048^2 grid, 12 x 2.1 A slices, 50 kV (BASELINE configs[2])"),
+    "slab_4096": ("config_random_4096_short", "random slab 4000 atoms / 3 species, 4096^2 grid, 20 x 2 A slices, 200 kV "
+                                             "(BASELINE configs[4] geometry, 20 of its 500 slices)"),
 }
-DEFAULT_CONFIGS_PER_STEP = {"si001_1024": 16, "au_2048": 8}
+DEFAULT_CONFIGS_PER_STEP = {"si001_1024": 16, "au_2048": 8, "slab_4096": 2}
 
 
 def peaks():

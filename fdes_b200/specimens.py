@@ -148,6 +148,11 @@ def config_random_4096(path, n_atoms: int = 100_000, slices: int = 500, frozen_p
     return atoms
 
 
+def config_random_4096_short(path, frozen_phonons: int = 2, with_atoms: bool = True):
+    """Config 5 geometry with 20 of its 500 slices (4000 of its 100 000 atoms: same areal density per slice)."""
+    return config_random_4096(path, n_atoms=4000, slices=20, frozen_phonons=frozen_phonons, with_atoms=with_atoms)
+
+
 def config_srtio3_stem_512(path, frozen_phonons: int = 0, with_atoms: bool = True):
     """Config 4: SrTiO3 4 x 4 x 20 cells centred in a 5-cell-wide 512^2 box (d = 19.525 A / 512),
     40 x 1.9525 A slices, 200 kV, 20 mrad probe (mode 2), no aberrations."""
