@@ -2,7 +2,8 @@
 //
 // One "line" (a grid row or a grid column) of N points is transformed by T = N/E threads that
 // each keep E points in registers at positions theta + m*T (m = 0..E-1).  A transform is a
-// sequence of radix-R passes (R = E while it divides what is left, then the remainder).  In a
+// sequence of radix-R passes (R = the largest divisor of E that divides what is left; E = 20 with
+// radix-5 butterflies serves the 2^a 5^b grids 320, 800, 1000 of the reference's examples).  In a
 // pass a thread performs E/R radix-R DFTs on registers; between passes the line is exchanged
 // through padded shared memory (Stockham autosort: natural order in, natural order out).  The
 // register layout before the first pass and after the last pass is the same, so
@@ -155,6 +156,34 @@ __device__ __forceinline__ cpx mul_w32(cpx a)
     else return cmul_cs(a, cos32(n), DIR < 0 ? -sin32(n) : sin32(n));
 }
 
+// cos / sin of 2 pi n / 20, for the radix-5 family (5, 10, 20)
+__device__ __forceinline__ constexpr float cos20(int n)
+{
+    constexpr float c[6] = {1.f, 0.95105651629515357212f, 0.80901699437494742410f, 0.58778525229247312917f,
+                            0.30901699437494742410f, 0.f};
+    n = ((n % 20) + 20) % 20;
+    if (n > 10) n = 20 - n;          // cos is even
+    return n <= 5 ? c[n] : -c[10 - n];
+}
+__device__ __forceinline__ constexpr float sin20(int n) { return cos20(n - 5); }
+template <int DIR, int n20>
+__device__ __forceinline__ cpx mul_w20(cpx a)
+{
+    constexpr int n = ((n20 % 20) + 20) % 20;
+    if constexpr (n == 0) return a;
+    else if constexpr (n == 5) return mul_di<DIR>(a);
+    else if constexpr (n == 10) return make_float2(-a.x, -a.y);
+    else if constexpr (n == 15) return mul_di<-DIR>(a);
+    else return cmul_cs(a, cos20(n), DIR < 0 ? -sin20(n) : sin20(n));
+}
+// v *= exp(DIR * 2 pi i * n / R) with compile-time n; R divides 32 or 20
+template <int DIR, int R, int n>
+__device__ __forceinline__ cpx mul_wR(cpx a)
+{
+    if constexpr (32 % R == 0) return mul_w32<DIR, (32 / R) * n>(a);
+    else return mul_w20<DIR, (20 / R) * n>(a);
+}
+
 template <int R, int DIR>
 struct Dft;
 
@@ -179,12 +208,34 @@ struct Dft<4, DIR> {
         v[3] = sub_di<DIR>(t1, d);
     }
 };
+template <int DIR>
+struct Dft<5, DIR> {
+    // X0 = x0 + t1 + t2; X1,4 = a -+ (DIR i) u; X2,3 = b -+ (DIR i) v  (forward: W = exp(-2 pi i / 5))
+    __device__ __forceinline__ static void run(cpx (&v)[5])
+    {
+        constexpr float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;   // cos 72, cos 144
+        constexpr float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;    // sin 72, sin 144
+        const cpx t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]);
+        const cpx t3 = csub(v[1], v[4]), t4 = csub(v[2], v[3]);
+        const cpx x0 = v[0];
+        v[0] = cadd(x0, cadd(t1, t2));
+        const cpx a = pfma(t2, make_float2(c2, c2), pfma(t1, make_float2(c1, c1), x0));
+        const cpx b = pfma(t2, make_float2(c1, c1), pfma(t1, make_float2(c2, c2), x0));
+        const cpx u = pfma(t4, make_float2(s2, s2), pmul(t3, make_float2(s1, s1)));
+        const cpx w = pfma(t4, make_float2(-s1, -s1), pmul(t3, make_float2(s2, s2)));
+        // forward: X1 = a - i u, X4 = a + i u, X2 = b - i w, X3 = b + i w
+        v[1] = add_di<DIR>(a, u);
+        v[4] = sub_di<DIR>(a, u);
+        v[2] = add_di<DIR>(b, w);
+        v[3] = sub_di<DIR>(b, w);
+    }
+};
 // R = R1 * R2, input index t = t1 + R1 t2, output index s = R2 s1 + s2:
 //   X[R2 s1 + s2] = sum_t1 W_R1^{s1 t1} ( W_R^{s2 t1} sum_t2 W_R2^{s2 t2} x[t1 + R1 t2] )
 template <int R, int DIR>
 struct Dft {
-    static constexpr int R1 = 4, R2 = R / 4;
-    static_assert(R == 8 || R == 16 || R == 32, "radix 2..32");
+    static constexpr int R1 = R % 4 == 0 ? 4 : (R % 5 == 0 ? 5 : 2), R2 = R / R1;
+    static_assert(R == 8 || R == 16 || R == 32 || R == 10 || R == 20, "radix 2, 4, 5, 8, 10, 16, 20, 32");
     __device__ __forceinline__ static void run(cpx (&v)[R])
     {
         cpx y[R1][R2];
@@ -198,8 +249,9 @@ struct Dft {
             for (int s2 = 0; s2 < R2; s2++) y[t1][s2] = u[s2];
         }
         twiddle_rows<1>(y);
-        twiddle_rows<2>(y);
-        twiddle_rows<3>(y);
+        if constexpr (R1 > 2) twiddle_rows<2>(y);
+        if constexpr (R1 > 3) twiddle_rows<3>(y);
+        if constexpr (R1 > 4) twiddle_rows<4>(y);
 #pragma unroll
         for (int s2 = 0; s2 < R2; s2++) {
             cpx z[R1];
@@ -214,7 +266,7 @@ struct Dft {
     __device__ __forceinline__ static void twiddle_rows(cpx (&y)[R1][R2])
     {
         if constexpr (s2 < R2) {
-            y[t1][s2] = mul_w32<DIR, (32 / R) * s2 * t1>(y[t1][s2]);
+            y[t1][s2] = mul_wR<DIR, R, s2 * t1>(y[t1][s2]);
             twiddle_rows<t1, s2 + 1>(y);
         }
     }
@@ -241,11 +293,19 @@ __host__ __device__ constexpr int line_smem_elems(int N) { return N + N / E; }
 // points with E points per thread and passes of radix R_1 = E, R_2, ...:
 //   pass p >= 2 with NS = R_1 ... R_{p-1}:  tab_p[t * NS + k] = exp(-2 pi i t k / (NS R_p)), t < R_p, k < NS
 // stored back to back: offsets twiddle_offset<N, E>(p).
+__host__ __device__ constexpr int pass_radix(int rem, int E)
+{
+    int r = 1;
+    for (int d = 2; d <= E; d++)
+        if (E % d == 0 && rem % d == 0) r = d;     // largest divisor of E that divides the rest
+    return r;
+}
 template <int N, int E, int NS>
 struct PassInfo {
     static constexpr int rem = N / NS;
-    static constexpr int R = rem >= E ? E : rem;
+    static constexpr int R = pass_radix(rem, E);
     static constexpr bool last = (rem == R);
+    static_assert(R > 1, "line length must factor into divisors of E");
 };
 template <int N, int E, int NS = 1>
 __host__ __device__ constexpr int twiddle_table_elems()
@@ -282,7 +342,7 @@ __device__ __forceinline__ void fft_pass(cpx (&x)[E], cpx* __restrict__ sm, int 
 #pragma unroll
     for (int u = 0; u < U; u++) {
         const int j = theta + u * T;
-        const int k = j & (NS - 1);
+        const int k = j % NS;
         cpx v[R];
 #pragma unroll
         for (int t = 0; t < R; t++) v[t] = x[u + t * U];
@@ -320,7 +380,7 @@ struct LinePasses {
 template <int N, int E, int DIR, class Sync>
 __device__ __forceinline__ void fft_line(cpx (&x)[E], cpx* sm, int theta, const cpx* tw, Sync sync)
 {
-    static_assert(N >= E && (N & (N - 1)) == 0, "power-of-two line length >= E");
+    static_assert(N >= E && N % E == 0, "line length must be a multiple of E");
     LinePasses<N, E, 1, DIR, Sync>::run(x, sm, theta, tw, sync);
 }
 

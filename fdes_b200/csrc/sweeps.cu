@@ -45,7 +45,8 @@ namespace fdes {
 // twiddle table per grid size serves both).
 template <int N>
 struct LineCfg {
-    static constexpr int E = N >= 512 ? 32 : (N >= 128 ? 16 : 8);
+    static constexpr int E = (N & (N - 1)) != 0 ? 20                        // 2^a 5^b grids: 320, 800, 1000
+                                                : (N >= 512 ? 32 : (N >= 128 ? 16 : 8));
     static constexpr int T = N / E;                     // threads per line
     static constexpr int LS = line_smem_elems<E>(N);    // padded line buffer [elements]
 };
@@ -53,14 +54,16 @@ template <int N>
 struct RowCfg {
     using L = LineCfg<N>;
     static constexpr int E = L::E, T = L::T;
-    static constexpr int RPB = (128 / T) > 0 ? (128 / T) : 1;      // lines (rows) per CTA
+    static constexpr int RPB = (T & (T - 1)) != 0 ? 4 : ((128 / T) > 0 ? (128 / T) : 1);   // lines (rows) per CTA
     static constexpr int THREADS = RPB * T;
     static constexpr int LSTRIDE = L::LS;
     static constexpr size_t SMEM = (size_t)RPB * LSTRIDE * sizeof(cpx);
-    static constexpr bool WARP_SYNC = (T <= 32);       // a line lives inside one warp
-    static constexpr int MIN_CTAS = N >= 2048 ? 2 : FDES_ROW_MIN_CTAS;   // long lines need the registers
+    static constexpr bool WARP_SYNC = (32 % T == 0);   // a line lives inside one warp
+    static constexpr bool NAMED_SYNC = (T % 32 == 0);  // a line is a whole number of warps
+    static constexpr int MIN_CTAS = (N >= 2048 || !WARP_SYNC) ? 2 : FDES_ROW_MIN_CTAS;   // long lines need the registers
 };
-// threads of one row line: warp-level sync when the line fits a warp, else a named barrier
+// threads of one row line: warp-level sync when the line fits a warp, a named barrier when it is a
+// whole number of warps, else (T = 40, 50: lines straddle warps) the whole CTA
 template <int N>
 struct RowSync {
     int id;
@@ -68,21 +71,23 @@ struct RowSync {
     __device__ __forceinline__ void operator()() const
     {
         if constexpr (RowCfg<N>::WARP_SYNC) __syncwarp();
-        else asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(RowCfg<N>::T) : "memory");
+        else if constexpr (RowCfg<N>::NAMED_SYNC) asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(RowCfg<N>::T) : "memory");
+        else __syncthreads();
     }
 };
 template <int N, bool HEAVY>
 struct ColCfg {
     using L = LineCfg<N>;
     static constexpr int E = L::E, T = L::T;
-    static constexpr int CW = (256 / T) >= 16 ? 16 : ((256 / T) >= 2 ? (256 / T) : 2);   // columns per CTA
+    static constexpr int CW = (T & (T - 1)) != 0 ? (T <= 40 ? 8 : 4)                       // T = 40, 50
+                                                 : ((256 / T) >= 16 ? 16 : ((256 / T) >= 2 ? (256 / T) : 2));   // columns per CTA
     static constexpr int THREADS = CW * T;
     static constexpr int LSTRIDE = L::LS + 16 / CW;   // bank-conflict-free line stride
     static constexpr size_t SMEM = (size_t)CW * LSTRIDE * sizeof(cpx);
     // Staged tiles: the CTA moves its [N rows][CW columns] tile between global and shared memory
     // with a column-fastest thread mapping (coalesced CW*8-byte row segments), while each column
     // is transformed by the threads of ONE warp (warp-level synchronisation inside the FFT).
-    static constexpr bool STAGED = (T <= 32);
+    static constexpr bool STAGED = (32 % T == 0);
     static constexpr int RPI = THREADS / CW;          // tile rows moved per iteration (= T)
     static constexpr int MIN_CTAS = FDES_COL_MIN_CTAS;
 };
@@ -106,7 +111,8 @@ struct KeepAll { __device__ __forceinline__ bool operator()(int) const { return 
 
 bool fft_size_supported(int N)
 {
-    return N == 64 || N == 128 || N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096;
+    return N == 64 || N == 128 || N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096 ||
+           N == 320 || N == 800 || N == 1000;
 }
 
 #define FDES_DISPATCH_N(N_, ...)                                                               \
@@ -118,9 +124,12 @@ bool fft_size_supported(int N)
         case 1024: { constexpr int NN = 1024; __VA_ARGS__; } break;                                     \
         case 2048: { constexpr int NN = 2048; __VA_ARGS__; } break;                                     \
         case 4096: { constexpr int NN = 4096; __VA_ARGS__; } break;                                     \
+        case 320: { constexpr int NN = 320; __VA_ARGS__; } break;                                       \
+        case 800: { constexpr int NN = 800; __VA_ARGS__; } break;                                       \
+        case 1000: { constexpr int NN = 1000; __VA_ARGS__; } break;                                     \
         default:                                                                                 \
             fprintf(stderr, "fdes_b200: unsupported grid size %d (need a power of two in "       \
-                            "[64, 4096])\n", N_);                                                \
+                            "[64, 4096] or 320, 800, 1000)\n", N_);                              \
             abort();                                                                             \
     }
 
@@ -555,7 +564,7 @@ k_rows_fft(const void* __restrict__ in_, void* __restrict__ out_, RowOpts o, int
             float* q = static_cast<float*>(out_) + rowoff + xx;
             *q += o.scale * (x[m].x * x[m].x + x[m].y * x[m].y);
         } else if (EPI == ROW_STORE_SHIFT) {
-            const int ys = (y + N / 2) & (N - 1), xs = (xx + N / 2) & (N - 1);
+            const int ys = (y + N / 2) % N, xs = (xx + N / 2) % N;
             static_cast<cpx*>(out_)[((size_t)blockIdx.y * N + ys) * N + xs] = v;
         } else {  // ROW_CROP_REAL
             const int cx = xx - o.dn1, cy = y - o.dn2;
@@ -698,10 +707,10 @@ k_cols_fft(const cpx* __restrict__ in, void* __restrict__ out_, const void* __re
         // |fftshift(FFT psi)|^2 / N accumulated with weight (diffractionPattern,
         // src/crystalMaker.cu:714-717; cufftShift2D_h, src/complexMath.cu:510-557)
         float* out = static_cast<float*>(out_);
-        const int xs = (kx + N / 2) & (N - 1);
+        const int xs = (kx + N / 2) % N;
 #pragma unroll
         for (int m = 0; m < E; m++) {
-            const int ys = (theta + m * C::T + N / 2) & (N - 1);
+            const int ys = (theta + m * C::T + N / 2) % N;
             out[boff + (size_t)ys * N + xs] += scale * (x[m].x * x[m].x + x[m].y * x[m].y);
         }
         return;
@@ -892,7 +901,7 @@ static std::vector<cpx> make_twiddles_n()
     std::vector<cpx> tw;
     int NS = 1;
     while (NS < N) {
-        const int rem = N / NS, R = rem >= E ? E : rem;
+        const int rem = N / NS, R = pass_radix(rem, E);
         if (NS > 1)
             for (int t = 0; t < R; t++)
                 for (int k = 0; k < NS; k++) {

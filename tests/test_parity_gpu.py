@@ -22,7 +22,7 @@ HARNESS = ROOT / "oracle" / "_ref" / "ref_harness"
 # ---------------------------------------------------------------------------------------------
 # building blocks
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048, 4096])
+@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048, 4096, 320, 800, 1000])
 def test_fft2d_against_numpy(n, fb):
     rng = np.random.default_rng(n)
     a = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(np.complex64)
@@ -284,6 +284,21 @@ def test_random_4096_against_oracle(fb, orc, tmp_path):
     atoms = specimens.random_slab(3000, 4096 * 0.1e-10, 5 * 2e-10)
     specimens.write_cnf(cnf, image_size=2048, border_size=1024, slices=5, pixel_size=0.1e-10, slice_thickness=2e-10,
                         atoms=atoms, voltage=200e3, absorptive=0.05)
+    _oracle_vs_library(cnf, fb, orc)
+
+
+@pytest.mark.parametrize("n,border,mode", [(320, 80, 0), (800, 200, 0), (1000, 170, 0), (320, 0, 2), (800, 100, 1)])
+def test_mixed_radix_grids_against_oracle(n, border, mode, fb, orc, tmp_path):
+    """The 2^a 5^b grids of the reference's shipped examples (Au 320^2, SrTiO3 800^2, Si 1000^2):
+    radix-5 passes, lines of 16 / 40 / 50 threads."""
+    from fdes_b200 import specimens
+    cnf = tmp_path / f"g{n}.cnf"
+    d = 0.2e-10
+    atoms = specimens.random_slab(150, n * d, 5 * 2e-10, seed=n, species=(79, 14, 8))
+    specimens.write_cnf(cnf, image_size=n - 2 * border, border_size=border, slices=5, pixel_size=d, slice_thickness=2e-10,
+                        atoms=atoms, voltage=120e3, mode=mode, absorptive=0.03, objective_aperture=0.015,
+                        frozen_phonons=2 if mode == 0 else 0, mtf=(0.58, 0.42, 2.7, 15.5),
+                        aberrations={"C1": (-3e-8, 0.0), "C3": (5e-4, 0.0), "A1": (1e-9, 0.4)})
     _oracle_vs_library(cnf, fb, orc)
 
 
