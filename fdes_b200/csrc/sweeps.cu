@@ -75,7 +75,7 @@ struct RowSync {
         else __syncthreads();
     }
 };
-template <int N, bool HEAVY>
+template <int N>
 struct ColCfg {
     using L = LineCfg<N>;
     static constexpr int E = L::E, T = L::T;
@@ -93,7 +93,7 @@ struct ColCfg {
 };
 
 template <int N>
-using ColCtx = ColTile<N, LineCfg<N>::E, ColCfg<N, false>::CW, ColCfg<N, false>::STAGED>;
+using ColCtx = ColTile<N, LineCfg<N>::E, ColCfg<N>::CW, ColCfg<N>::STAGED>;
 // Multiply x[m] (ky = theta + m*T) by the quarter table tab[min(ky, N - ky) * Q + ax]: the first
 // half of the points sits at base_lo + m*T*Q, the second at base_hi + (N - m*T)*Q with
 // base_lo = tab + ax + theta*Q and base_hi = tab + ax - theta*Q -- compile-time offsets.
@@ -231,12 +231,12 @@ void launch_density_rows(const SweepGeom& g, cpx* A, const int* rowptr, const in
 // S2  potential columns
 // =============================================================================================
 template <int N>
-__global__ void __launch_bounds__(ColCfg<N, true>::THREADS, ColCfg<N, true>::MIN_CTAS)
+__global__ void __launch_bounds__(ColCfg<N>::THREADS, ColCfg<N>::MIN_CTAS)
 k_potential_cols(cpx* __restrict__ B, const cpx* __restrict__ A, const float* __restrict__ Gq,
                  const int* __restrict__ rowptr, int slice, int slice2, int nZ, size_t rp_stride,
                  const cpx* __restrict__ tw)
 {
-    using C = ColCfg<N, true>;
+    using C = ColCfg<N>;
     extern __shared__ cpx smem[];
     constexpr int Q = N / 2 + 1;
     constexpr int E = C::E;
@@ -276,7 +276,7 @@ void launch_potential_cols(const SweepGeom& g, cpx* B, const cpx* A, const float
                            cudaStream_t st)
 {
     FDES_DISPATCH_N(g.N, {
-        using C = ColCfg<NN, true>;
+        using C = ColCfg<NN>;
         static bool once = false;
         if (!once) { allow_smem(k_potential_cols<NN>, C::SMEM); once = true; }
         dim3 grid(NN / C::CW, batch);
@@ -386,10 +386,10 @@ void launch_transmit_rows(const SweepGeom& g, const cpx* W, cpx* D, int npair, f
 // S4  band-limit columns
 // =============================================================================================
 template <int N>
-__global__ void __launch_bounds__(ColCfg<N, false>::THREADS, LineCfg<N>::T <= 32 ? 2 : ColCfg<N, false>::MIN_CTAS)
+__global__ void __launch_bounds__(ColCfg<N>::THREADS, LineCfg<N>::T <= 32 ? 2 : ColCfg<N>::MIN_CTAS)
 k_bandlimit_cols(cpx* __restrict__ W, int npair, int lo_end, int hi_start, const cpx* __restrict__ tw)
 {
-    using C = ColCfg<N, false>;
+    using C = ColCfg<N>;
     extern __shared__ cpx smem[];
     constexpr int E = C::E;
     const ColCtx<N> ctx(smem);
@@ -419,7 +419,7 @@ k_bandlimit_cols(cpx* __restrict__ W, int npair, int lo_end, int hi_start, const
 void launch_bandlimit_cols(const SweepGeom& g, cpx* W, int batch, int npair, cudaStream_t st)
 {
     FDES_DISPATCH_N(g.N, {
-        using C = ColCfg<NN, false>;
+        using C = ColCfg<NN>;
         static bool once = false;
         if (!once) { allow_smem(k_bandlimit_cols<NN>, C::SMEM); once = true; }
         dim3 grid(band_cols(g) / C::CW, npair == 0 ? batch : batch * npair);
@@ -490,11 +490,11 @@ void launch_multiply_rows(const SweepGeom& g, cpx* Psi, const cpx* E, size_t e_b
 // S6  propagate columns
 // =============================================================================================
 template <int N>
-__global__ void __launch_bounds__(ColCfg<N, false>::THREADS, ColCfg<N, false>::MIN_CTAS)
+__global__ void __launch_bounds__(ColCfg<N>::THREADS, ColCfg<N>::MIN_CTAS)
 k_propagate_cols(cpx* __restrict__ Psi, const cpx* __restrict__ Pq, int lo_end, int hi_start,
                  const cpx* __restrict__ tw)
 {
-    using C = ColCfg<N, false>;
+    using C = ColCfg<N>;
     extern __shared__ cpx smem[];
     constexpr int Q = N / 2 + 1;
     constexpr int E = C::E;
@@ -514,7 +514,7 @@ k_propagate_cols(cpx* __restrict__ Psi, const cpx* __restrict__ Pq, int lo_end, 
 void launch_propagate_cols(const SweepGeom& g, cpx* Psi, const cpx* Pq, int batch, cudaStream_t st)
 {
     FDES_DISPATCH_N(g.N, {
-        using C = ColCfg<NN, false>;
+        using C = ColCfg<NN>;
         static bool once = false;
         if (!once) { allow_smem(k_propagate_cols<NN>, C::SMEM); once = true; }
         dim3 grid(band_cols(g) / C::CW, batch);
@@ -682,11 +682,11 @@ void launch_rows_fft_sum(const SweepGeom& g, const cpx* in, void* out, int dir, 
 // generic column sweep
 // =============================================================================================
 template <int N, int DIR, int OP>
-__global__ void __launch_bounds__(ColCfg<N, false>::THREADS, ColCfg<N, false>::MIN_CTAS)
+__global__ void __launch_bounds__(ColCfg<N>::THREADS, ColCfg<N>::MIN_CTAS)
 k_cols_fft(const cpx* __restrict__ in, void* __restrict__ out_, const void* __restrict__ table,
            float scale, const cpx* __restrict__ tw)
 {
-    using C = ColCfg<N, false>;
+    using C = ColCfg<N>;
     extern __shared__ cpx smem[];
     constexpr int E = C::E;
     const ColCtx<N> ctx(smem);
@@ -737,7 +737,7 @@ template <int N, int DIR, int OP>
 static void cols_fft_one(const SweepGeom& g, const cpx* in, void* out, const void* table,
                          float scale, int batch, cudaStream_t st)
 {
-    using C = ColCfg<N, false>;
+    using C = ColCfg<N>;
     static bool once = false;
     if (!once) { allow_smem(k_cols_fft<N, DIR, OP>, C::SMEM); once = true; }
     dim3 grid(N / C::CW, batch);
@@ -767,11 +767,11 @@ void launch_cols_fft(const SweepGeom& g, const cpx* in, void* out, int dir, ColO
 // columns only; PSI0 = FFT_col of the centred, normalised probe in the (kx, y) domain.  shifts:
 // [batch][2] = probe position / (N * pixel size), i.e. in units of the grid period.
 template <int N>
-__global__ void __launch_bounds__(ColCfg<N, false>::THREADS, ColCfg<N, false>::MIN_CTAS)
+__global__ void __launch_bounds__(ColCfg<N>::THREADS, ColCfg<N>::MIN_CTAS)
 k_probe_cols(cpx* __restrict__ Psi, const cpx* __restrict__ PSI0, const float* __restrict__ shifts,
              int lo_end, int hi_start, const cpx* __restrict__ tw)
 {
-    using C = ColCfg<N, false>;
+    using C = ColCfg<N>;
     extern __shared__ cpx smem[];
     constexpr int E = C::E;
     const ColCtx<N> ctx(smem);
@@ -801,7 +801,7 @@ void launch_probe_cols(const SweepGeom& g, cpx* Psi, const cpx* PSI0, const floa
                        cudaStream_t st)
 {
     FDES_DISPATCH_N(g.N, {
-        using C = ColCfg<NN, false>;
+        using C = ColCfg<NN>;
         static bool once = false;
         if (!once) { allow_smem(k_probe_cols<NN>, C::SMEM); once = true; }
         dim3 grid(band_cols(g) / C::CW, batch);
@@ -813,11 +813,11 @@ void launch_probe_cols(const SweepGeom& g, cpx* Psi, const cpx* PSI0, const floa
 // annulus k_in^2 <= |k|^2 < k_out^2 of detector d (|FFT2 psi|^2 / N^2 with Psi = FFT_row(psi)/N,
 // the normalisation of diffractionPattern, src/crystalMaker.cu:714-717).  Fixed reduction order.
 template <int N>
-__global__ void __launch_bounds__(ColCfg<N, false>::THREADS, ColCfg<N, false>::MIN_CTAS)
+__global__ void __launch_bounds__(ColCfg<N>::THREADS, ColCfg<N>::MIN_CTAS)
 k_detector_cols(const cpx* __restrict__ Psi, float* __restrict__ partial, DetectorRings rings, float inv_l1,
                 float inv_l2, int lo_end, int hi_start, const cpx* __restrict__ tw)
 {
-    using C = ColCfg<N, false>;
+    using C = ColCfg<N>;
     extern __shared__ cpx smem[];
     constexpr int E = C::E;
     const ColCtx<N> ctx(smem);
@@ -871,7 +871,7 @@ __global__ void k_detector_finish(const float* __restrict__ partial, float* __re
 
 int detector_tiles(const SweepGeom& g)
 {
-    FDES_DISPATCH_N(g.N, { return band_cols(g) / ColCfg<NN, false>::CW; });
+    FDES_DISPATCH_N(g.N, { return band_cols(g) / ColCfg<NN>::CW; });
     return 0;
 }
 
@@ -879,7 +879,7 @@ void launch_detector_cols(const SweepGeom& g, const cpx* Psi, float* partial, fl
                           float d1, float d2, float weight, int batch, cudaStream_t st)
 {
     FDES_DISPATCH_N(g.N, {
-        using C = ColCfg<NN, false>;
+        using C = ColCfg<NN>;
         static bool once = false;
         if (!once) { allow_smem(k_detector_cols<NN>, C::SMEM); once = true; }
         const int tiles = band_cols(g) / C::CW;
@@ -937,7 +937,7 @@ int rows_per_block(int N)
 }
 int cols_per_block(int N)
 {
-    FDES_DISPATCH_N(N, { return ColCfg<NN, false>::CW; });
+    FDES_DISPATCH_N(N, { return ColCfg<NN>::CW; });
     return 0;
 }
 
