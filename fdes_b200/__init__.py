@@ -43,6 +43,8 @@ def load_library() -> ctypes.CDLL:
     lib.fdes_b200_open_cnf.argtypes = [ctypes.c_char_p, c_f, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_int, ctypes.c_int, ctypes.c_int]
     lib.fdes_b200_parse_cnf.argtypes = [ctypes.c_char_p, c_i, c_f, c_f, c_f, ctypes.c_int]
+    lib.fdes_b200_write_used_cnf.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+    lib.fdes_b200_write_emd.argtypes = [ctypes.c_char_p, ctypes.c_char_p, c_f, c_f, ctypes.c_int, c_f]
     lib.fdes_b200_close.argtypes = [vp]
     lib.fdes_b200_close.restype = None
     lib.fdes_b200_get_dims.argtypes = [vp, c_i]
@@ -123,6 +125,25 @@ def parse_cnf(cnf_path):
     out["tiltspec"], out["tiltbeam"], out["defoci"] = per_k[:, 0:2].copy(), per_k[:, 2:4].copy(), per_k[:, 4].copy()
     out["atoms"] = atoms
     return out
+
+
+def write_emd(input_path, emd_path, image=None, potential=None, exitwave=None):
+    """Host-only: EMD (HDF5) file with the reference's layout from a parameter file and arrays
+    (image [n3,n2,n1] float32, potential [m3,m2,m1] complex64, exitwave [n3,m2,m1] complex64)."""
+    lib = load_library()
+    keep = []
+
+    def ptr(a, dt):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dt)
+        keep.append(a)
+        return a.view(np.float32).ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    nslices = 0 if potential is None else int(np.asarray(potential).shape[0])
+    rc = lib.fdes_b200_write_emd(str(input_path).encode(), str(emd_path).encode(), ptr(image, np.float32),
+                                 ptr(potential, np.complex64), nslices, ptr(exitwave, np.complex64))
+    if rc != 0:
+        raise FdesError(lib.fdes_b200_last_error().decode())
 
 
 class Simulation:

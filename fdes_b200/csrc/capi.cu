@@ -2,6 +2,7 @@
 // (src/FDESExport.cu:59-178) and the session API over the engine.
 #include "../../include/fdes_b200.h"
 #include "engine.h"
+#include "emd.h"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -43,7 +44,7 @@ int fdes_b200_parse_cnf(const char* cnf_path, int* dims, float* scalars, float* 
     if (!cnf_path) throw std::runtime_error("cnf_path is NULL");
     Params p;
     Atoms at;
-    if (!read_cnf(cnf_path, p, &at, false)) throw std::runtime_error(std::string("cannot read ") + cnf_path);
+    if (!read_input(cnf_path, p, &at, false)) throw std::runtime_error(std::string("cannot read ") + cnf_path);
     set_sub_slices(p, sub_slice_ratio(p.d3, p.subSlTh));
     if (dims) {
         dims[0] = p.n1; dims[1] = p.n2; dims[2] = p.n3; dims[3] = p.m1; dims[4] = p.m2; dims[5] = p.m3;
@@ -69,13 +70,39 @@ int fdes_b200_parse_cnf(const char* cnf_path, int* dims, float* scalars, float* 
     API_CATCH(-1)
 }
 
+int fdes_b200_write_used_cnf(const char* input_path, const char* out_path)
+{
+    API_TRY
+    if (!input_path || !out_path) throw std::runtime_error("path is NULL");
+    Params p;
+    Atoms at;
+    if (!read_input(input_path, p, &at, false)) throw std::runtime_error(std::string("cannot read ") + input_path);
+    if (!write_cnf(out_path, p, at, 0)) throw std::runtime_error(std::string("cannot write ") + out_path);
+    return 0;
+    API_CATCH(-1)
+}
+
+int fdes_b200_write_emd(const char* input_path, const char* emd_path, const float* image_host,
+                        const float* potential_host, int pot_slices, const float* exitwave_host)
+{
+    API_TRY
+    if (!input_path || !emd_path) throw std::runtime_error("path is NULL");
+    Params p;
+    Atoms at;
+    if (!read_input(input_path, p, &at, false)) throw std::runtime_error(std::string("cannot read ") + input_path);
+    if (!write_emd(emd_path, p, at, image_host, potential_host, pot_slices, exitwave_host))
+        throw std::runtime_error(std::string("cannot write ") + emd_path);
+    return 0;
+    API_CATCH(-1)
+}
+
 fdes_b200_sim* fdes_b200_open_cnf(const char* cnf_path, const float* atoms6, int numAtoms,
                                   int gpu_index, int batch, int rank, int world, int want_exitwave)
 {
     API_TRY
     auto sim = std::make_unique<fdes_b200_sim>();
     if (!cnf_path) throw std::runtime_error("cnf_path is NULL");
-    if (!read_cnf(cnf_path, sim->params, &sim->atoms, atoms6 != nullptr))
+    if (!read_input(cnf_path, sim->params, &sim->atoms, atoms6 != nullptr))
         throw std::runtime_error(std::string("cannot read ") + cnf_path);
     if (atoms6) {
         if (numAtoms <= 0) throw std::runtime_error("numAtoms must be positive");
@@ -306,11 +333,6 @@ void FDES(int gpu_Index, int print_Level, char* input_name, char* image_name, ch
         fprintf(stderr, " \n input file %s error   \n", input_name ? input_name : "(null)");
         exit(0);   // reference: src/FDESExport.cu:100-101
     }
-    if (!strstr(input_name, ".cnf")) {
-        fprintf(stderr, " \n fdes_b200: only .cnf parameter files are supported by this build "
-                        "(.emd needs libhdf5, .qsc the QSTEM reader) \n");
-        exit(EXIT_FAILURE);
-    }
     if (numAtoms <= 0) exit(0);   // readAtomsFromArray, src/paramStructure.cu:306-307
     if (print_Level < 0 || print_Level > 2) {
         fprintf(stderr, " \n printLevel error %s  \n", input_name);
@@ -328,7 +350,16 @@ void FDES(int gpu_Index, int print_Level, char* input_name, char* image_name, ch
     const auto t1 = clk::now();
     // side-effect file of getParams (src/paramStructure.cu:629-631), written by a helper thread
     // while the GPU works (formatting tens of thousands of atom lines takes milliseconds)
-    std::thread cnf_writer([sim, gpu_Index] { write_cnf("dataFDES_used.cnf", sim->eng->params(), sim->atoms, gpu_Index); });
+    // (readQsc writes ParamsUsedQsc.txt instead, src/rwQsc.cu:1084)
+    // (readQsc writes ParamsUsedQsc.txt, readHdf5 ParamsUsedEmd.txt instead: src/rwQsc.cu:1084,
+    // src/rwHdf5.cu:2565); .cnf and .qsc inputs also leave "config.emd" behind (src/FDESExport.cu:123, 141)
+    const bool from_emd = strstr(input_name, ".emd") != nullptr;
+    const char* used_name = from_emd ? "ParamsUsedEmd.txt"
+                          : (is_qsc_name(input_name) && !strstr(input_name, ".cnf")) ? "ParamsUsedQsc.txt" : "dataFDES_used.cnf";
+    std::thread cnf_writer([sim, gpu_Index, used_name, from_emd] {
+        write_cnf(used_name, sim->params, sim->atoms, gpu_Index);
+        if (!from_emd) write_emd("config.emd", sim->params, sim->atoms, nullptr, nullptr, 0, nullptr);
+    });
     fprintf(stderr, "  Number of atoms %d \n", sim->atoms.size());
     const Params& p = sim->eng->params();
     const size_t n123 = (size_t)p.n1 * p.n2 * p.n3, m12 = (size_t)p.m1 * p.m2;
@@ -350,12 +381,10 @@ void FDES(int gpu_Index, int print_Level, char* input_name, char* image_name, ch
     }
     if (image_name && image_name[0]) write_binary(image_name, image, n123);
     if (emd_save_name && emd_save_name[0]) {
-        // libhdf5 is not available in this build: the EMD payload is written as raw float32
-        // side files next to the requested name (layout: INTEGRATION.md).
-        std::string base(emd_save_name);
-        write_binary((base + ".images.f32").c_str(), image, n123);
-        if (!ew.empty()) write_binary((base + ".exit_wave.f32").c_str(), ew.data(), ew.size());
-        if (!pot.empty()) write_binary((base + ".potential_slices.f32").c_str(), pot.data(), pot.size());
+        // results file of buildMeasurements (src/crystalMaker.cu:402 -> writeHdf5, src/rwHdf5.cu:27-1084):
+        // HDF5 bytes written by our own serialiser (emd.cpp; no libhdf5 in this build)
+        write_emd(emd_save_name, sim->params, sim->atoms, image, pot.empty() ? nullptr : pot.data(), sim->m3_orig,
+                  ew.empty() ? nullptr : ew.data());
     }
     const auto t3 = clk::now();
     cnf_writer.join();

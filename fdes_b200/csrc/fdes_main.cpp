@@ -5,10 +5,12 @@
 // Defaults as in src/FDES.cu:40-44: dataFDES.cnf -> Measurements.bin, results.emd.
 #include "../../include/fdes_b200.h"
 #include "params.h"
+#include "emd.h"
 #include <getopt.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <vector>
 
@@ -57,7 +59,10 @@ int main(int argc, char** argv)
     // The CLI takes the atoms from the file; FDES() wants them as an array (atomsFromExternal).
     fdes::Params p;
     fdes::Atoms atoms;
-    if (!fdes::read_cnf(input.c_str(), p, &atoms, false)) {
+    bool ok = false;
+    try { ok = fdes::read_input(input.c_str(), p, &atoms, false); }
+    catch (const std::exception& e) { fprintf(stderr, " \n fdes_b200: %s \n", e.what()); }
+    if (!ok) {
         fprintf(stderr, " \n Errors occur when reading \"%s\" \n", input.c_str());
         return EXIT_FAILURE;
     }
@@ -91,11 +96,11 @@ int main(int argc, char** argv)
             return EXIT_FAILURE;
         }
     }
-    fdes::write_cnf("dataFDES_used.cnf", p, atoms, gpu_index);
+    fdes::write_cnf(strstr(input.c_str(), ".emd") ? "ParamsUsedEmd.txt" : fdes::is_qsc_name(input.c_str()) && !strstr(input.c_str(), ".cnf") ? "ParamsUsedQsc.txt" : "dataFDES_used.cnf", p, atoms, gpu_index);
     fdes::write_binary(image.c_str(), img.data(), n123);
-    fdes::write_binary((emd + ".images.f32").c_str(), img.data(), n123);
-    if (!ew.empty()) fdes::write_binary((emd + ".exit_wave.f32").c_str(), ew.data(), ew.size());
-    if (!pot.empty()) fdes::write_binary((emd + ".potential_slices.f32").c_str(), pot.data(), pot.size());
+    if (!strstr(input.c_str(), ".emd")) fdes::write_emd("config.emd", p, atoms, nullptr, nullptr, 0, nullptr);   // src/FDES.cu:229-232
+    fdes::write_emd(emd.c_str(), p, atoms, img.data(), pot.empty() ? nullptr : pot.data(),
+                    pot.empty() ? 0 : fdes_b200_potential_slices_count(sim), ew.empty() ? nullptr : ew.data());
     fdes_b200_close(sim);
     fprintf(stderr, "  Done.\n");
     return 0;

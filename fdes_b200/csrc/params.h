@@ -52,6 +52,13 @@ struct Atoms {
 // atoms_from_external is set the `atom:` lines are ignored (src/paramStructure.cu:268).
 // Returns false if the file cannot be opened.
 bool read_cnf(const char* file, Params& p, Atoms* atoms, bool atoms_from_external);
+// readQsc (src/rwQsc.cu:8-1088) with the QSTEM .cfg unit-cell reader behind it
+// (qstem-libs/fileio_fftw3.cpp:721-776, 908-975, 1188-1657); see qsc.cpp for what is kept and what
+// is refused.  Throws std::runtime_error on unusable input, returns false if the file cannot be opened.
+bool read_qsc(const char* file, Params& p, Atoms* atoms, bool atoms_from_external);
+// Reader selected by the file name like src/FDESExport.cu:85-102 (.cnf, else .qsc)
+bool read_input(const char* file, Params& p, Atoms* atoms, bool atoms_from_external);
+bool is_qsc_name(const char* file);
 // consitentParams (src/paramStructure.cu:637-673)
 void consistent_params(Params& p);
 // readAtomsFromArray (src/paramStructure.cu:304-345): [numAtoms][6] = Z x y z DWF occ; occupancy is

@@ -163,6 +163,79 @@ def config_srtio3_stem_512(path, frozen_phonons: int = 0, with_atoms: bool = Tru
     return atoms
 
 
+SRTIO3_CFG = """Number of particles = 5
+A = 1.0 Angstrom (basic length-scale)
+H0(1,1) = 3.905 A
+H0(1,2) = 0 A
+H0(1,3) = 0 A
+H0(2,1) = 0 A
+H0(2,2) = 3.905 A
+H0(2,3) = 0 A
+H0(3,1) = 0 A
+H0(3,2) = 0 A
+H0(3,3) = 3.905 A
+.NO_VELOCITY.
+entry_count = 5
+87.62
+Sr
+0 0 0 0.6214 1.0
+47.867
+Ti
+0.5 0.5 0.5 0.4390 1.0
+15.999
+O
+0 0.5 0.5 0.7323 1.0
+0.5 0 0.5 0.7323 1.0
+0.5 0.5 0 0.7323 1.0
+"""
+
+
+def config_srtio3_qsc_800(directory, cal_mode: int = 0, pixel_dose: float = 0.0, frozen_phonons: int = 0,
+                          ncell_z: int = 20):
+    """Config 1 (BASELINE configs[0]): the SrTiO3 plane-wave case of the reference's bin/test.qsc +
+    bin/SrTiO3.cfg as a QSTEM parameter file: 9 x 9 x 20 cells (8100 atoms, 3 species), 200 kV,
+    nx = 400 -> 800^2 grid at 0.087862 A, 40 slices of 1.9525 A -> 400 sub-slices of 0.19525 A.
+    Writes <directory>/SrTiO3.cfg and <directory>/srtio3_800.qsc (SURVEY 8d overrides: cal_mode 0,
+    pixel_dose 0) and returns the .qsc path.  ncell_z < 20 gives a thinner crystal (2 slices per cell)."""
+    import pathlib
+    d = pathlib.Path(directory)
+    d.mkdir(parents=True, exist_ok=True)
+    (d / "SrTiO3.cfg").write_text(SRTIO3_CFG)
+    qsc = d / "srtio3_800.qsc"
+    qsc.write_text(f"""% SrTiO3 [001] plane-wave exit wave, QSTEM syntax (generated by fdes_b200.specimens)
+mode: TEM
+filename: SrTiO3.cfg
+resolutionX:  0.087862
+resolutionY:  0.087862
+NCELLX: 9
+NCELLY: 9
+NCELLZ: {ncell_z}
+v0: 200.0
+tds: no
+slice-thickness: 1.9525
+slices: {2 * ncell_z}
+center slices: no
+nx: 400
+ny: 400
+Cs: 0.05
+C5: 0.0
+alpha: 15.0
+defocus: 13.7
+astigmatism: 0.0
+astigmatism angle: 0.0
+cal_mode:  {cal_mode}
+focus_spread:  1e-9
+mtf_a:  1
+mtf_b:  0
+mtf_c:  0
+pixel_dose:  {pixel_dose}
+objective_aperture:  20e-3
+absorptive_potential_factor:  0.1
+frozen_phonons: {frozen_phonons}
+""")
+    return qsc
+
+
 def stem_raster(n_side: int, cell: float = 3.905e-10):
     """n_side x n_side probe positions on a uniform raster over the central unit cell [m]."""
     g = (np.arange(n_side) + 0.5) / n_side * cell - 0.5 * cell

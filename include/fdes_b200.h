@@ -28,10 +28,9 @@ extern "C" {
  * Replaces: extern "C" void FDES(...)                     reference src/FDESExport.cu:59-178
  *   gpu_Index      CUDA device ordinal                    (:68, :106)
  *   print_Level    0 images | 1 + potential | 2 + exit waves (:69)
- *   input_name     parameter file; ".cnf" (".qsc"/".emd" are rejected with a message, see
- *                  INTEGRATION.md)                         (:73-102)
+ *   input_name     parameter file: ".emd", ".cnf" or ".qsc", tested in that order     (:73-102)
  *   image_name     raw float32 output file [n3][n2][n1]    (src/crystalMaker.cu:399)
- *   emd_save_name  results file (see INTEGRATION.md for the layout written)
+ *   emd_save_name  results file, EMD/HDF5 with the reference's groups (src/rwHdf5.cu:27-1084)
  *   atomsArray     host float32 [numAtoms][6] = Z, x, y, z [m], DWF [m^2], occupancy
  *                                                          (src/paramStructure.cu:316-324)
  *   dstImage       host float32 [n3][n2][n1], caller-allocated (:162, src/paramStructure.cu:347-359)
@@ -48,7 +47,7 @@ const char* fdes_b200_last_error(void);
 void fdes_b200_release_cache(void);
 int fdes_b200_version(void);
 
-/* Host-only (no CUDA call): parse a .cnf exactly as fdes_b200_open_cnf does and report what the
+/* Host-only (no CUDA call): parse a .cnf (or .qsc / .emd) exactly as fdes_b200_open_cnf does and report what the
  * engine would run (readConfig + consitentParams, src/paramStructure.cu:42-302, 637-673; sub-slice
  * logic src/crystalMaker.cu:720-743).  dims[10] = n1 n2 n3 m1 m2 m3(after sub-slicing) nAt nZ
  * frozen_phonons mode; scalars[8] as fdes_b200_get_scalars; per_k [n3][5] = specimen_tilt x y,
@@ -57,7 +56,26 @@ int fdes_b200_version(void);
 int fdes_b200_parse_cnf(const char* cnf_path, int* dims, float* scalars, float* per_k,
                         float* atoms6_out, int max_atoms);
 
-/* Open a simulation from a .cnf file (reader: getParams, reference src/paramStructure.cu:588-635).
+/* Host-only (no CUDA call): read a .cnf / .qsc / .emd parameter file exactly as fdes_b200_open_cnf does and
+ * write parameters + atoms back in .cnf syntax -- the side-effect file the reference leaves behind
+ * (writeConfig, src/paramStructure.cu:360-487: "dataFDES_used.cnf" from getParams :629-631,
+ * "ParamsUsedQsc.txt" from readQsc, src/rwQsc.cu:1084). */
+int fdes_b200_write_used_cnf(const char* input_path, const char* out_path);
+
+/* Host-only (no CUDA call): write an EMD (HDF5) file with the reference's layout (writeHdf5,
+ * src/rwHdf5.cu:27-1084; the bytes are produced by the library's own serialiser, there is no libhdf5
+ * here) from the parameters + atoms of input_path (.cnf / .qsc / .emd) and the caller's arrays:
+ * image_host [n3][n2][n1] -> /data/images/data [n1][n2][n3]; potential_host [pot_slices][m2][m1][2]
+ * -> /data/potential_slices/data [m1][m2][pot_slices][2]; exitwave_host [n3][m2][m1][2] ->
+ * /data/exit_wave/data [m1][m2][n3][2].  Any array may be NULL (all NULL = the "config.emd" of the
+ * 6-argument writeHdf5, :1085-1945).  FDES() writes emd_save_name through the same code. */
+int fdes_b200_write_emd(const char* input_path, const char* emd_path, const float* image_host,
+                        const float* potential_host, int pot_slices, const float* exitwave_host);
+
+/* Open a simulation from a parameter file, selected by name like src/FDESExport.cu:85-102:
+ * .emd (readHdf5, src/rwHdf5.cu:1946-2571, parsed by the library's own HDF5 reader),
+ * .cnf (reader: getParams, reference src/paramStructure.cu:588-635) or QSTEM .qsc + the .cfg unit
+ * cell it names (readQsc, src/rwQsc.cu:8-1088; fdes_b200/csrc/qsc.cpp lists what is refused).
  * atoms6 == NULL: atoms come from the file's `atom:` lines; otherwise [numAtoms][6] like FDES().
  * batch: phonon configurations advanced together (0 = automatic).
  * rank/world: this process handles configurations [count*rank/world, count*(rank+1)/world).

@@ -176,7 +176,8 @@ def test_FDES_drop_in_call(fb, orc, tmp_path, monkeypatch):
     assert rel_l2(dst, res.image) < TOL_INTENSITY
     on_disk = np.fromfile(tmp_path / "M.bin", np.float32).reshape(dst.shape)
     np.testing.assert_array_equal(on_disk, dst)
-    ew = np.fromfile(str(tmp_path / "r.emd") + ".exit_wave.f32", np.float32).view(np.complex64).reshape(p.n3, p.m2, p.m1)
+    import h5min          # results file = EMD/HDF5 with the exit wave stored [m1][m2][n3][2] (src/rwHdf5.cu:248-267)
+    ew = np.ascontiguousarray(h5min.File(tmp_path / "r.emd").root["data/exit_wave/data"].data.transpose(2, 1, 0, 3)).view(np.complex64)[..., 0]
     assert rel_l2(ew, res.exitwave) < TOL_WAVE
     assert (tmp_path / "dataFDES_used.cnf").exists()     # side-effect file of getParams (:629-631)
 
@@ -189,7 +190,11 @@ def test_cli_binary(orc, tmp_path, oracle_runs):
     res, _ = oracle_runs("sub128")
     img = np.fromfile(tmp_path / "out.bin", np.float32).reshape(res.image.shape)
     assert rel_l2(img, res.image) < TOL_INTENSITY
-    ew = np.fromfile(tmp_path / "results.emd.exit_wave.f32", np.float32).view(np.complex64).reshape(res.exitwave.shape)
+    import h5min
+    f = h5min.File(tmp_path / "results.emd")
+    ew = np.ascontiguousarray(f.root["data/exit_wave/data"].data.transpose(2, 1, 0, 3)).view(np.complex64)[..., 0]
+    np.testing.assert_array_equal(f.root["data/images/data"].data.transpose(2, 1, 0), img)
+    assert (tmp_path / "config.emd").exists()      # side-effect file of the CLI for .cnf / .qsc inputs (src/FDES.cu:229-232)
     assert rel_l2(ew, res.exitwave) < TOL_WAVE
 
 

@@ -45,6 +45,9 @@ def run_case(cnf: pathlib.Path, out_dir: pathlib.Path, max_dump: int = 2):
         td = pathlib.Path(td)
         local = td / cnf.name
         shutil.copy(cnf, local)
+        if cnf.suffix == ".qsc":       # the QSTEM reader opens the .cfg unit cell relative to the cwd
+            for cfg in cnf.parent.glob("*.cfg"):
+                shutil.copy(cfg, td / cfg.name)
         d_run, d_tr = td / "run", td / "trace"
         subprocess.run([str(HARNESS), "run", str(local), str(d_run), "2"], check=True,
                        stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
@@ -69,6 +72,8 @@ def run_case(cnf: pathlib.Path, out_dir: pathlib.Path, max_dump: int = 2):
         g["I_k0"] = np.ascontiguousarray(c(d_tr / "I_d.c64").real)
         g["J_k0"] = np.fromfile(d_tr / "J.f32", np.float32)[: n1 * n2].reshape(n2, n1)
         out_dir.mkdir(parents=True, exist_ok=True)
+        if cnf.suffix == ".qsc":       # side-effect file of readQsc (src/rwQsc.cu:1084): what the reader understood
+            shutil.copy(td / "ParamsUsedQsc.txt", out_dir / f"{cnf.stem}.ParamsUsedQsc.txt")
         np.savez_compressed(out_dir / f"{cnf.stem}.npz", **g)
         return meta
 
@@ -80,7 +85,8 @@ def main():
     a = ap.parse_args()
     if not HARNESS.exists():
         sys.exit(f"{HARNESS} missing: run `make -C oracle` where /root/reference is mounted")
-    cases = [ROOT / "tests" / "data" / f"{c}.cnf" for c in a.cases] or sorted((ROOT / "tests" / "data").glob("*.cnf"))
+    data = ROOT / "tests" / "data"
+    cases = [data / (c if "." in c else f"{c}.cnf") for c in a.cases] or sorted(data.glob("*.cnf")) + sorted(data.glob("*.qsc"))
     for cnf in cases:
         meta = run_case(cnf, pathlib.Path(a.out))
         print(f"golden {cnf.stem}: m={int(meta['m1'])} m3={int(meta['m3'])} nAt={int(meta['nAt'])} mode={int(meta['mode'])}")
