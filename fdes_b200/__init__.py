@@ -45,6 +45,7 @@ def load_library() -> ctypes.CDLL:
     lib.fdes_b200_parse_cnf.argtypes = [ctypes.c_char_p, c_i, c_f, c_f, c_f, ctypes.c_int]
     lib.fdes_b200_write_used_cnf.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
     lib.fdes_b200_write_emd.argtypes = [ctypes.c_char_p, ctypes.c_char_p, c_f, c_f, ctypes.c_int, c_f]
+    lib.fdes_b200_qsc_scan.argtypes = [ctypes.c_char_p, c_i, c_f, ctypes.c_int, c_f, ctypes.c_int]
     lib.fdes_b200_close.argtypes = [vp]
     lib.fdes_b200_close.restype = None
     lib.fdes_b200_get_dims.argtypes = [vp, c_i]
@@ -125,6 +126,20 @@ def parse_cnf(cnf_path):
     out["tiltspec"], out["tiltbeam"], out["defoci"] = per_k[:, 0:2].copy(), per_k[:, 2:4].copy(), per_k[:, 4].copy()
     out["atoms"] = atoms
     return out
+
+
+def qsc_scan(qsc_path):
+    """Host-only: (positions [nx, ny, 2] in metres, detectors [ndet, 2] in mrad) of a `mode: STEM` .qsc,
+    ready for Simulation.stem_scan(positions.reshape(-1, 2), detectors)."""
+    lib = load_library()
+    nxy = np.zeros(2, np.int32)
+    nd = lib.fdes_b200_qsc_scan(str(qsc_path).encode(), _ip(nxy), None, 0, None, 0)
+    if nd < 0:
+        raise FdesError(lib.fdes_b200_last_error().decode())
+    xy = np.zeros((int(nxy[0]), int(nxy[1]), 2), np.float32)
+    det = np.zeros((nd, 2), np.float32)
+    lib.fdes_b200_qsc_scan(str(qsc_path).encode(), _ip(nxy), _fp(xy), xy.shape[0] * xy.shape[1], _fp(det), nd)
+    return xy, det
 
 
 def write_emd(input_path, emd_path, image=None, potential=None, exitwave=None):

@@ -3,6 +3,7 @@
 #include "../../include/fdes_b200.h"
 #include "engine.h"
 #include "emd.h"
+#include "qsc.h"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -79,6 +80,21 @@ int fdes_b200_write_used_cnf(const char* input_path, const char* out_path)
     if (!read_input(input_path, p, &at, false)) throw std::runtime_error(std::string("cannot read ") + input_path);
     if (!write_cnf(out_path, p, at, 0)) throw std::runtime_error(std::string("cannot write ") + out_path);
     return 0;
+    API_CATCH(-1)
+}
+
+int fdes_b200_qsc_scan(const char* qsc_path, int* nxy, float* xy_host, int max_probes, float* det_mrad_host,
+                       int max_det)
+{
+    API_TRY
+    if (!qsc_path) throw std::runtime_error("qsc_path is NULL");
+    QscScan sc;
+    if (!read_qsc_scan(qsc_path, sc)) throw std::runtime_error(std::string("cannot read ") + qsc_path);
+    const int np = sc.nx * sc.ny, nd = (int)sc.det_mrad.size() / 2;
+    if (nxy) { nxy[0] = sc.nx; nxy[1] = sc.ny; }
+    if (xy_host) memcpy(xy_host, sc.xy.data(), sizeof(float) * 2 * (size_t)std::min(np, max_probes));
+    if (det_mrad_host) memcpy(det_mrad_host, sc.det_mrad.data(), sizeof(float) * 2 * (size_t)std::min(nd, max_det));
+    return nd;
     API_CATCH(-1)
 }
 
@@ -379,12 +395,18 @@ void FDES(int gpu_Index, int print_Level, char* input_name, char* image_name, ch
         pot.resize(2 * m12 * (size_t)sim->m3_orig);
         if (fdes_b200_potential(sim, pot.data()) != 0) fail();
     }
-    if (image_name && image_name[0]) write_binary(image_name, image, n123);
-    if (emd_save_name && emd_save_name[0]) {
+    {
         // results file of buildMeasurements (src/crystalMaker.cu:402 -> writeHdf5, src/rwHdf5.cu:27-1084):
-        // HDF5 bytes written by our own serialiser (emd.cpp; no libhdf5 in this build)
-        write_emd(emd_save_name, sim->params, sim->atoms, image, pot.empty() ? nullptr : pot.data(), sim->m3_orig,
-                  ew.empty() ? nullptr : ew.data());
+        // HDF5 bytes written by our own serialiser (emd.cpp; no libhdf5 in this build), on a helper
+        // thread while this one writes the raw image file
+        std::thread emd_writer;
+        if (emd_save_name && emd_save_name[0])
+            emd_writer = std::thread([&] {
+                write_emd(emd_save_name, sim->params, sim->atoms, image, pot.empty() ? nullptr : pot.data(),
+                          sim->m3_orig, ew.empty() ? nullptr : ew.data());
+            });
+        if (image_name && image_name[0]) write_binary(image_name, image, n123);
+        if (emd_writer.joinable()) emd_writer.join();
     }
     const auto t3 = clk::now();
     cnf_writer.join();

@@ -264,13 +264,18 @@ Bytes transposed(const float* src, int n1, int n2, int n3, int comps)
 {
     Bytes out((size_t)n1 * n2 * n3 * comps * 4);
     float* dst = reinterpret_cast<float*>(out.data());
+    constexpr int TILE = 32;   // (i, j) tiles: both the reads along i and the writes along j stay in cache
     for (int k = 0; k < n3; k++)
-        for (int j = 0; j < n2; j++) {
-            const float* s = src + ((size_t)k * n2 + j) * n1 * comps;
-            for (int i = 0; i < n1; i++)
-                for (int c = 0; c < comps; c++)
-                    dst[(((size_t)i * n2 + j) * n3 + k) * comps + c] = s[(size_t)i * comps + c];
-        }
+        for (int j0 = 0; j0 < n2; j0 += TILE)
+            for (int i0 = 0; i0 < n1; i0 += TILE) {
+                const int j1 = std::min(n2, j0 + TILE), i1 = std::min(n1, i0 + TILE);
+                for (int i = i0; i < i1; i++)
+                    for (int j = j0; j < j1; j++) {
+                        const float* s = src + (((size_t)k * n2 + j) * n1 + i) * comps;
+                        float* d = dst + (((size_t)i * n2 + j) * n3 + k) * comps;
+                        for (int c = 0; c < comps; c++) d[c] = s[c];
+                    }
+            }
     return out;
 }
 void complex_axis(Obj* grp)

@@ -25,6 +25,7 @@
 // contain "TEM" (the reference tests with strstr, so "STEM" passes as TEM there and here, src/rwQsc.cu:35).
 #include "params.h"
 #include "emd.h"
+#include "qsc.h"
 
 #include <algorithm>
 #include <cctype>
@@ -280,8 +281,64 @@ std::vector<CellAtom> read_unit_cell(const std::string& cfg, int ncx, int ncy, i
 
 bool is_qsc_name(const char* file) { return file && strstr(file, ".qsc") != nullptr; }
 
+namespace {
+bool read_qsc_impl(const char* file, Params& p, Atoms* atoms_out, bool atoms_from_external, float shift[3]);
+}
+
 bool read_qsc(const char* file, Params& p, Atoms* atoms_out, bool atoms_from_external)
 {
+    float shift[3];
+    return read_qsc_impl(file, p, atoms_out, atoms_from_external, shift);
+}
+
+// Scan raster and detectors of a `mode: STEM` parameter file: the keys readQsc parses into MULS
+// (scan_x_start / stop / pixels, scan_y_*: src/rwQsc.cu:444-466; `detector: inner outer name shiftx
+// shifty` in mrad: :698-735) and FDES then never uses.  Positions follow QSTEM's raster
+// x_i = start + i (stop - start) / pixels in the super-cell frame [A]; they are returned in the frame
+// of the atoms after readQsc's centring (src/rwQsc.cu:1071-1076), in metres, x index slowest.
+bool read_qsc_scan(const char* file, QscScan& out)
+{
+    Params p;
+    Atoms atoms;
+    float shift[3];
+    if (!read_qsc_impl(file, p, &atoms, false, shift)) return false;
+    ParFile q;
+    if (!q.open(file)) return false;
+    std::string buf;
+    float xs = 0, xe = 0, ys = 0, ye = 0;
+    int nx = 0, ny = 0;
+    auto needf = [&](const char* key, float& v) {
+        if (!q.readparam(key, buf) || !scan_f(buf, v)) throw std::runtime_error(std::string(".qsc: STEM scan needs `") + key + "`");
+    };
+    auto needi = [&](const char* key, int& v) {
+        if (!q.readparam(key, buf) || !scan_i(buf, v)) throw std::runtime_error(std::string(".qsc: STEM scan needs `") + key + "`");
+    };
+    needf("scan_x_start:", xs); needf("scan_x_stop:", xe); needi("scan_x_pixels:", nx);
+    needf("scan_y_start:", ys); needf("scan_y_stop:", ye); needi("scan_y_pixels:", ny);
+    if (nx < 1) nx = 1;
+    if (ny < 1) ny = 1;
+    out.nx = nx; out.ny = ny;
+    out.xy.resize(2 * (size_t)nx * ny);
+    const float dx = (xe - xs) / (float)nx, dy = (ye - ys) / (float)ny;
+    for (int ix = 0; ix < nx; ix++)
+        for (int iy = 0; iy < ny; iy++) {
+            const float x = xs + (float)ix * dx, y = ys + (float)iy * dy;
+            out.xy[2 * ((size_t)ix * ny + iy) + 0] = (float)(x * 1e-10) - shift[0];
+            out.xy[2 * ((size_t)ix * ny + iy) + 1] = (float)(y * 1e-10) - shift[1];
+        }
+    out.det_mrad.clear();
+    q.pos = 0;
+    while (q.readparam("detector:", buf, false)) {
+        float in = 0, outer = 0;
+        if (sscanf(buf.c_str(), "%g %g", &in, &outer) == 2) { out.det_mrad.push_back(in); out.det_mrad.push_back(outer); }
+    }
+    return true;
+}
+
+namespace {
+bool read_qsc_impl(const char* file, Params& p, Atoms* atoms_out, bool atoms_from_external, float shift[3])
+{
+    shift[0] = shift[1] = shift[2] = 0.f;
     ParFile q;
     if (!q.open(file)) {
         fprintf(stderr, "could not open input file %s!\n", file);
@@ -468,11 +525,13 @@ bool read_qsc(const char* file, Params& p, Atoms* atoms_out, bool atoms_from_ext
         }
         for (size_t i = 0; i < n; i++)
             for (int k = 0; k < 3; k++) at.xyz[3 * i + k] = at.xyz[3 * i + k] - (mx[k] - mn[k]) / 2;
+        for (int k = 0; k < 3; k++) shift[k] = (mx[k] - mn[k]) / 2;
         p.nAt = (int)n;
     }
     consistent_params(p);
     return true;
 }
+}  // namespace
 
 bool read_input(const char* file, Params& p, Atoms* atoms, bool atoms_from_external)
 {

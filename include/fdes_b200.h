@@ -119,6 +119,15 @@ int fdes_b200_potential(fdes_b200_sim* sim, float* out_host);
 double fdes_b200_stem_scan(fdes_b200_sim* sim, int k, int nprobes, const float* xy_host, int ndet,
                            const float* det_mrad_host, float* out_host);
 
+/* Host-only: the scan raster and detectors a QSTEM `mode: STEM` .qsc describes -- the keys readQsc
+ * parses (scan_x_start/stop/pixels, scan_y_*, src/rwQsc.cu:444-466; `detector: inner outer name ..`
+ * [mrad], :698-735) but FDES never uses -- in the form fdes_b200_stem_scan takes: nxy[2] = pixels in
+ * x, y; xy_host [nx][ny][2] probe positions [m] (QSTEM raster start + i (stop - start) / pixels, moved
+ * into the frame of the atoms as readQsc centres them); det_mrad_host [ndet][2].  Returns the number
+ * of detectors, -1 on failure.  Call once with NULL arrays to size them. */
+int fdes_b200_qsc_scan(const char* qsc_path, int* nxy, float* xy_host, int max_probes, float* det_mrad_host,
+                       int max_det);
+
 /* ---- building blocks (parity tests, benchmarks) ------------------------------------------- */
 /* next frozen-phonon coordinates for measurement k -> xyz_host [nAt][3]
  * (atomJitter_d, src/crystalMaker.cu:37-48; advances the XORWOW streams) */

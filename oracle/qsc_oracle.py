@@ -236,7 +236,7 @@ def read_unit_cell(cfg, ncx, ncy, ncz, ctilt, xoff, yoff):
     return Z, xyz, dwv, occv, box
 
 
-def read_qsc(path, atoms_from_external=False):
+def read_qsc(path, atoms_from_external=False, return_shift=False):
     """-> (Params after consitentParams, Z, xyz [m], DWF [m^2], occ), like fdes_oracle.read_cnf."""
     q = ParFile(path)
     pi = 3.1415926535897
@@ -396,13 +396,52 @@ def read_qsc(path, atoms_from_external=False):
         if r is not None:
             setattr(p, attr, (_scan_d if kind == "d" else _scan_g)(r, getattr(p, attr)))
     xyz = np.zeros((0, 3), f32)
+    shift = np.zeros(3, f32)
     if not atoms_from_external:
         xyz = (xyzA.astype(f64) * 1e-10).astype(f32)
         dw = (dw.astype(f64) * 1e-20).astype(f32)
         mx = np.maximum(xyz.max(0), f32(0))
         mn = np.minimum(xyz.min(0), f32(1))
-        xyz = (xyz - (mx - mn) / f32(2)).astype(f32)
+        shift = ((mx - mn) / f32(2)).astype(f32)
+        xyz = (xyz - shift).astype(f32)
     else:
         Z, dw, occ = Z[:0], dw[:0], occ[:0]
     consistent_params(p)
+    if return_shift:
+        return p, Z, xyz, dw, occ, shift
     return p, Z, xyz, dw, occ
+
+
+def read_qsc_scan(path):
+    """STEM raster and detectors of a .qsc: the keys of src/rwQsc.cu:444-466 and :698-735.
+    -> (positions float32 [nx, ny, 2] in metres in the frame of the centred atoms, detectors [ndet, 2] mrad)."""
+    shift = read_qsc(path, return_shift=True)[5]
+    q = ParFile(path)
+
+    def need(key, scan):
+        r = q.readparam(key)
+        v = scan(r, None) if r is not None else None
+        if v is None:
+            raise ValueError("STEM scan needs " + key)
+        return v
+
+    xs, xe, nx = need("scan_x_start:", _scan_g), need("scan_x_stop:", _scan_g), max(1, need("scan_x_pixels:", _scan_d))
+    ys, ye, ny = need("scan_y_start:", _scan_g), need("scan_y_stop:", _scan_g), max(1, need("scan_y_pixels:", _scan_d))
+    dx, dy = f32(f32(xe - xs) / f32(nx)), f32(f32(ye - ys) / f32(ny))
+    xy = np.zeros((nx, ny, 2), f32)
+    for ix in range(nx):
+        for iy in range(ny):
+            x, y = f32(xs + f32(f32(ix) * dx)), f32(ys + f32(f32(iy) * dy))
+            xy[ix, iy, 0] = f32(f32(f64(x) * 1e-10) - shift[0])
+            xy[ix, iy, 1] = f32(f32(f64(y) * 1e-10) - shift[1])
+    det = []
+    q.pos = 0
+    while True:
+        r = q.readparam("detector:", wrap=False)
+        if r is None:
+            break
+        m1 = _NUM.match(r)
+        m2 = _NUM.match(r[m1.end():]) if m1 else None
+        if m1 and m2:
+            det.append((f32(float(m1.group(1))), f32(float(m2.group(1)))))
+    return xy, np.array(det, f32).reshape(-1, 2)

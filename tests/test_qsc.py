@@ -13,7 +13,7 @@ import pytest
 
 from conftest import DATA, GOLDEN, TOL_INTENSITY, TOL_WAVE, golden, rel_l2
 
-QSC_CASES = sorted(p.stem for p in DATA.glob("*.qsc"))
+QSC_CASES = sorted(p.stem for p in DATA.glob("qsc*.qsc"))
 AB = ["C1", "A1", "A2", "B2", "C3", "A3", "S3", "A4", "B4", "D4", "C5", "A5", "R5", "S5"]
 
 
@@ -236,3 +236,44 @@ def test_fdes_export_accepts_qsc(fb, tmp_path):
         os.chdir(cwd)
     assert (tmp_path / "ParamsUsedQsc.txt").exists()
     np.testing.assert_array_equal(dst, img)
+
+
+# ---------------------------------------------------------------------------------------------
+# `mode: STEM` parameter files: scan raster + detectors (keys readQsc parses, src/rwQsc.cu:444-466,
+# 698-735, and FDES never uses) feeding the batched STEM scan
+# ---------------------------------------------------------------------------------------------
+def test_stem_qsc_scan_keys_cpp_matches_oracle(fb, qorc, monkeypatch):
+    monkeypatch.chdir(DATA)
+    xy, det = fb.qsc_scan(DATA / "stem128.qsc")
+    oxy, odet = qorc.read_qsc_scan(str(DATA / "stem128.qsc"))
+    assert xy.shape == (4, 3, 2) and det.shape == (3, 2)
+    np.testing.assert_array_equal(xy, oxy)            # bit-exact float32
+    np.testing.assert_array_equal(det, odet)
+    np.testing.assert_array_equal(det, np.array([[70, 200], [11, 22], [0, 10]], np.float32))
+    # QSTEM raster: start + i (stop - start) / pixels in the super-cell frame, minus the centring shift
+    p, Z, xyz, dwf, occ, shift = qorc.read_qsc(str(DATA / "stem128.qsc"), return_shift=True)
+    step = (5.8575 - 1.9525) / 4 * 1e-10
+    np.testing.assert_allclose(xy[:, 0, 0], 1.9525e-10 + step * np.arange(4) - shift[0], rtol=0, atol=5e-17)
+    np.testing.assert_allclose(xy[0, :, 1], 1.9525e-10 + (4.88125 - 1.9525) / 3 * 1e-10 * np.arange(3) - shift[1], rtol=0, atol=5e-17)
+    r = fb.parse_cnf(DATA / "stem128.qsc")
+    assert (r["mode"], r["m1"], r["nAt"]) == (2, 128, 40)     # "STEM" contains "TEM" (src/rwQsc.cu:35); cal_mode 2
+    lib = fb.load_library()
+    assert lib.fdes_b200_qsc_scan(str(DATA / "qsc64.qsc").encode(), None, None, 0, None, 0) == -1   # no scan keys
+    assert b"scan_x_start" in lib.fdes_b200_last_error()
+
+
+@pytest.mark.gpu
+def test_stem_scan_from_qsc_against_oracle(fb, orc, qorc, monkeypatch):
+    """The whole path from a QSTEM STEM file: reader -> raster/detectors -> batched probe scan, against
+    the oracle's per-probe restatement (reference mode-2 run with the atoms translated by -r_p)."""
+    from test_parity_gpu import _oracle_stem
+    monkeypatch.chdir(DATA)
+    qsc = DATA / "stem128.qsc"
+    xy, det = fb.qsc_scan(qsc)
+    with fb.Simulation(qsc, batch=5) as sim:
+        got, ms = sim.stem_scan(xy.reshape(-1, 2), det)
+    p, Z, xyz, dwf, occ = qorc.read_qsc(str(qsc))
+    want = _oracle_stem(orc, p, Z, [xyz], occ, xy.reshape(-1, 2), det)
+    assert got.shape == want.shape == (12, 3) and ms > 0
+    np.testing.assert_allclose(got, want, rtol=TOL_INTENSITY, atol=1e-4 * want.max())
+    assert np.ptp(want[:, 0]) > 1e-3 * want[:, 0].mean()        # the HAADF signal really varies over the raster
