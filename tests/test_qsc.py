@@ -131,6 +131,74 @@ def test_cpp_qsc_reader_matches_oracle_bitwise(case, fb, orc, qorc, tmp_path):
     assert len(atoms) == len(Z)
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_cpp_qsc_reader_matches_oracle_on_random_cells(seed, fb, qorc, tmp_path, monkeypatch):
+    """Random triclinic cells, atom lists, replications, tilts, offsets and key orders: the C++ reader and the
+    (reference-pinned) oracle agree bit for bit on every parameter and atom."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(1, 7))
+    H = np.diag(rng.uniform(2.5, 6.0, 3)) + np.tril(rng.uniform(-1.0, 1.0, (3, 3)), -1) * (seed % 2)
+    vel = seed % 3 == 0
+    lines = [f"Number of particles = {n}", f"A = {rng.choice([1.0, 0.9, 1.25])} Angstrom"]
+    lines += [f"H0({a + 1},{b + 1}) = {H[a, b]:.5f} A" for a in range(3) for b in range(3)]
+    ncols = int(rng.integers(0, 3))                                  # extra columns: DWF, occupancy
+    lines += ([] if vel else [".NO_VELOCITY."]) + [f"entry_count = {3 + ncols}"]
+    species = [("12.011", "C"), ("28.086", "Si"), ("196.97", "Au"), ("15.999", "O"), ("55.845", "Fe")]
+    for i in range(n):
+        if i == 0 or rng.random() < 0.5:
+            m, el = species[int(rng.integers(len(species)))]
+            lines += [m + (" # mass" if rng.random() < 0.3 else ""), el]
+        xyz = rng.uniform(0, 1, 3).round(4) + i * 1e-3                # distinct sites
+        cols = [f"{v:.4f}" for v in xyz] + (["0", "0", "0"] if vel else [])
+        cols += [f"{rng.uniform(0.2, 0.9):.4f}", "1.0"][:ncols]
+        lines.append((" " if rng.random() < 0.3 else "") + "  ".join(cols))
+    (tmp_path / "cell.cfg").write_text("\n".join(lines) + "\n")
+    ncell = rng.integers(1, 4, 3)
+    keys = {
+        "mode": "mode: TEM", "file": "filename: " + rng.choice(["cell.cfg", '"cell"', "cell"]),
+        "nc": f"NCELLX: {ncell[0]}\nNCELLY: {ncell[1]}\nNCELLZ: {ncell[2]}",
+        "v0": f"v0: {rng.choice([80.0, 120.0, 300.0])}", "nx": "nx: 32" + ("\nny: 32" if seed % 2 else ""),
+        "res": "" if seed % 4 == 0 else "resolutionX: 0.31\nresolutionY: 0.29",
+        "sl": rng.choice(["slice-thickness: 2.1\nslices: 5", "slices: 6", "slice-thickness: 1.7"]),
+        "tilt": f"Crystal tilt X: {rng.uniform(-0.05, 0.05):.4f}\nCrystal tilt Y: {rng.uniform(-2, 2):.3f} deg\n"
+                f"Crystal tilt Z: {rng.uniform(-0.2, 0.2):.4f}" if seed % 2 else "",
+        "beam": f"Beam tilt X: {rng.uniform(-0.1, 0.1):.4f} deg\nBeam tilt Y: {rng.uniform(-2e-3, 2e-3):.5f}",
+        "off": f"xOffset: {rng.uniform(-1, 1):.3f}\nyOffset: {rng.uniform(-1, 1):.3f}" if seed % 3 else "",
+        "lens": f"Cs: {rng.uniform(0.01, 1.5):.3f}\nalpha: {rng.uniform(5, 20):.2f}\n"
+                f"defocus: {rng.choice(['Scherzer', 'opt', f'{rng.uniform(-60, 60):.2f}'])}\n"
+                f"astigmatism: {rng.uniform(0, 3):.2f}\nastigmatism angle: {rng.uniform(0, 90):.1f}",
+        "fdes": f"cal_mode: {int(rng.integers(0, 3))}\nobjective_aperture: {rng.uniform(5e-3, 3e-2):.4g}\n"
+                f"frozen_phonons: {int(rng.integers(0, 3))}\nabsorptive_potential_factor: {rng.uniform(0, 0.2):.3f}\n"
+                f"focus_spread: {rng.uniform(0, 5e-9):.3g}\nmtf_a: 0.6\nmtf_b: 0.4\nmtf_c: 2.5\npixel_dose: 0",
+    }
+    order = [k for k in keys if k != "mode"]
+    rng.shuffle(order)                                               # readparam wraps: any order of UNIQUE keys works,
+    order = ["mode"] + order                                         # but "mode:" must precede "cal_mode:" (strstr)
+    (tmp_path / "r.qsc").write_text("\n".join(keys[k] for k in order if keys[k]) + "\n")
+    monkeypatch.chdir(tmp_path)
+    r = fb.parse_cnf(tmp_path / "r.qsc")
+    p, Z, xyz, dwf, occ = qorc.read_qsc(str(tmp_path / "r.qsc"))
+    used = tmp_path / "used.txt"
+    assert fb.load_library().fdes_b200_write_used_cnf(str(tmp_path / "r.qsc").encode(), str(used).encode()) == 0
+    keysu, atoms = parse_used(used.read_text())
+    assert (r["n1"], r["n2"], r["m1"], r["nAt"], r["frPh"], r["mode"]) == (p.n1, p.n2, p.m1, len(Z), p.frPh, p.mode)
+    sub = p.copy()
+    import fdes_oracle as orc
+    orc.set_sub_slices(sub, orc.sub_slice_ratio(sub.d3, sub.subSlTh))
+    assert (r["m3"], np.float32(r["d3"])) == (sub.m3, np.float32(sub.d3))
+    for k, v in dict(lam=p.lam, sigma=p.sigma, d1=p.d1, d2=p.d2, E0=p.E0, imPot=p.imPot).items():
+        assert np.float32(r[k]) == np.float32(v), k
+    np.testing.assert_array_equal(r["atoms"][:, 0].astype(np.int32), Z)
+    np.testing.assert_array_equal(r["atoms"][:, 1:4], xyz)
+    np.testing.assert_array_equal(r["atoms"][:, 4], dwf)
+    np.testing.assert_array_equal(r["tiltbeam"].ravel(), p.tiltbeam[:2])
+    for name in AB:
+        assert close(p.ab0[name], keysu[name][0][0]) and close(p.ab1[name], keysu[name][0][1]), name
+    for k in ("illumination_angle", "objective_aperture", "specimen_tilt_offset_x", "specimen_tilt_offset_y",
+              "specimen_tilt_offset_z", "subpixel_size_z", "focus_spread", "mtf_c"):
+        assert close(used_from_params(p, Z, xyz, dwf, occ)[k], keysu[k][0][0]), k
+
+
 def test_qsc_reader_refuses_what_it_cannot_reproduce(fb, tmp_path):
     lib = fb.load_library()
     base = (DATA / "qsc64.qsc").read_text()
