@@ -1,0 +1,64 @@
+#!/usr/bin/env python3
+"""Turn the ncu outputs a GPU trip brings back (tools/gpu_bench.sh -> gpurun_out/) into the tracked
+summaries under profiles/:  python tools/summarize_profiles.py r1_v4
+  gpurun_out/launches.csv        -> profiles/<tag>_launches.csv, <tag>_launch_shares.txt
+  gpurun_out/prof_sweeps.ncu-rep -> profiles/<tag>_ncu_full_raw.csv (ncu --page raw --csv),
+                                    <tag>_ncu_sweeps_summary.json, dram_traffic.json (read by bench.py)"""
+import collections
+import csv
+import json
+import pathlib
+import shutil
+import subprocess
+import sys
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+NAMES = {"k_multiply_rows": "S5_multiply_rows", "k_propagate_cols": "S6_propagate_cols", "k_density_rows": "S1_density_rows",
+         "k_potential_cols": "S2_potential_cols", "k_transmit_rows": "S3_transmit_rows", "k_bandlimit_cols": "S4_bandlimit_cols"}
+SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1, "ms": 1e3, "nsecond": 1e-3, "usecond": 1, "msecond": 1e3}
+
+
+def main(tag):
+    out, prof = ROOT / "gpurun_out", ROOT / "profiles"
+    shutil.copy(out / "launches.csv", prof / f"{tag}_launches.csv")
+    rows = list(csv.reader(l for l in open(prof / f"{tag}_launches.csv") if l.startswith('"')))
+    hdr = rows[0]
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        a = agg.setdefault(r[ki], [0, 0.0])
+        a[0] += 1
+        a[1] += float(r[vi].replace(",", "")) * SCALE.get(r[ui], 1)
+    tot = sum(a[1] for a in agg.values())
+    with open(prof / f"{tag}_launch_shares.txt", "w") as f:
+        f.write("kernel launches of `python bench.py --steps 2 --warmup 3 --no-cpu` (ncu --metrics gpu__time_duration.sum "
+                "--clock-control none, launches 300..800; cold-cache serialised times: compare shares)\n\n")
+        for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
+            f.write(f"{k[:52]:52s} n={a[0]:4d} avg={a[1] / a[0]:8.2f}us share={100 * a[1] / tot:5.1f}%\n")
+    raw = prof / f"{tag}_ncu_full_raw.csv"
+    raw.write_text(subprocess.run(["ncu", "-i", str(out / "prof_sweeps.ncu-rep"), "--page", "raw", "--csv"],
+                                  capture_output=True, text=True, check=True).stdout)
+    rows = list(csv.reader(open(raw)))
+    hdr, units = rows[0], rows[1]
+    val = lambda r, n: float(r[hdr.index(n)].replace(",", "")) * SCALE.get(units[hdr.index(n)], 1)
+    summary, traffic = [], {}
+    for r in rows[2:]:
+        key = [v for k, v in NAMES.items() if k in r[hdr.index("Kernel Name")]][0]
+        rd, wr = val(r, "dram__bytes_read.sum"), val(r, "dram__bytes_write.sum")
+        summary.append(dict(kernel=key, grid=r[hdr.index("Grid Size")], block=r[hdr.index("Block Size")],
+                            dur_us=val(r, "gpu__time_duration.sum"), dram_read_MB=round(rd / 1e6, 2), dram_write_MB=round(wr / 1e6, 2),
+                            regs=int(val(r, "launch__registers_per_thread")),
+                            warps_active_pct=val(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
+                            issue_active_pct=val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                            eligible_warps_per_cycle=val(r, "smsp__warps_eligible.avg.per_cycle_active"),
+                            inst_executed=val(r, "smsp__inst_executed.sum"),
+                            fma_pipe_pct=val(r, "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                            dram_throughput_pct=val(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")))
+        traffic.setdefault(key, int(rd + wr))
+    json.dump(summary, open(prof / f"{tag}_ncu_sweeps_summary.json", "w"), indent=1)
+    json.dump(traffic, open(prof / "dram_traffic.json", "w"), indent=1)
+    print("wrote", tag, traffic)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1] if len(sys.argv) > 1 else "r1_v4")
