@@ -18,6 +18,7 @@ int main(int argc, char** argv)
 {
     std::string input = "dataFDES.cnf", image = "Measurements.bin", emd = "results.emd";
     int gpu_index = 0, print_level = 0;
+    bool stem_scan = false;
     static struct option opts[] = {{"gpu_index", required_argument, 0, 0},
                                    {"input_name", required_argument, 0, 0},
                                    {"image_name", required_argument, 0, 0},
@@ -25,6 +26,7 @@ int main(int argc, char** argv)
                                    {"print_level", required_argument, 0, 0},
                                    {"help", no_argument, 0, 0},
                                    {"version", no_argument, 0, 0},
+                                   {"stem_scan", no_argument, 0, 0},   // extension, see below
                                    {NULL, 0, 0, 0}};
     while (true) {
         int idx = 0;
@@ -51,8 +53,11 @@ int main(int argc, char** argv)
                         "  [ --emd_name    <results name, default results.emd> ]\n"
                         "  [ --print_level <0 images | 1 + potential slices | 2 + exit waves> ]\n"
                         "  [ --gpu_index   <CUDA device ordinal, default 0> ]\n"
-                        "  [ --help ] [ --version ]\n");
+                        "  [ --help ] [ --version ]\n"
+                        "  [ --stem_scan   extension: run the probe scan a `mode: STEM` .qsc describes (scan_* and\n"
+                        "                  detector: keys); image_name receives float32 [detector][x][y] ]\n");
                 return EXIT_FAILURE;
+            case 7: stem_scan = true; break;
             case 6: fprintf(stderr, " \n FDES (fdes_b200) Version : %1.1f  \n", fdes_b200_version() / 100.0); return EXIT_FAILURE;
         }
     }
@@ -75,6 +80,31 @@ int main(int argc, char** argv)
         a6[6 * i + 3] = atoms.xyz[3 * i + 2];
         a6[6 * i + 4] = atoms.dwf[i];
         a6[6 * i + 5] = atoms.occ[i];
+    }
+    if (stem_scan) {
+        // Extension (FDES has no STEM mode): the raster and detectors of a QSTEM `mode: STEM` file, keys the
+        // reference parses and drops (src/rwQsc.cu:444-466, 698-735), drive the batched probe scan.
+        int nxy[2] = {0, 0};
+        const int ndet = fdes_b200_qsc_scan(input.c_str(), nxy, nullptr, 0, nullptr, 0);
+        if (ndet <= 0) {
+            fprintf(stderr, " \n fdes_b200: %s \n", ndet < 0 ? fdes_b200_last_error() : "--stem_scan: the file has no `detector:` line");
+            return EXIT_FAILURE;
+        }
+        const int np = nxy[0] * nxy[1];
+        std::vector<float> xy(2 * (size_t)np), det(2 * (size_t)ndet), sig((size_t)np * ndet), out((size_t)np * ndet);
+        fdes_b200_qsc_scan(input.c_str(), nxy, xy.data(), np, det.data(), ndet);
+        fdes_b200_sim* sim = fdes_b200_open_cnf(input.c_str(), nullptr, 0, gpu_index, 32, 0, 1, 0);
+        if (!sim) { fprintf(stderr, " \n fdes_b200: %s \n", fdes_b200_last_error()); return EXIT_FAILURE; }
+        const double ms = fdes_b200_stem_scan(sim, 0, np, xy.data(), ndet, det.data(), sig.data());
+        if (ms < 0) { fprintf(stderr, " \n fdes_b200: %s \n", fdes_b200_last_error()); return EXIT_FAILURE; }
+        for (int i = 0; i < np; i++)
+            for (int d = 0; d < ndet; d++) out[(size_t)d * np + i] = sig[(size_t)i * ndet + d];   // [probe][det] -> [det][x][y]
+        fdes::write_binary(image.c_str(), out.data(), out.size());
+        fdes::write_cnf("ParamsUsedQsc.txt", p, atoms, gpu_index);
+        fdes_b200_close(sim);
+        fprintf(stderr, "  STEM scan: %d x %d probes, %d detectors, %.2f ms on the device (%.0f probes/s)\n  Done.\n", nxy[0],
+                nxy[1], ndet, ms, np / (ms * 1e-3));
+        return 0;
     }
     // NOTE: FDES() truncates the occupancy to an integer like the reference's readAtomsFromArray;
     // the file path keeps fractional occupancies, so the CLI goes through the session API.

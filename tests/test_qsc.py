@@ -345,3 +345,29 @@ def test_stem_scan_from_qsc_against_oracle(fb, orc, qorc, monkeypatch):
     assert got.shape == want.shape == (12, 3) and ms > 0
     np.testing.assert_allclose(got, want, rtol=TOL_INTENSITY, atol=1e-4 * want.max())
     assert np.ptp(want[:, 0]) > 1e-3 * want[:, 0].mean()        # the HAADF signal really varies over the raster
+
+
+@pytest.mark.gpu
+def test_cli_stem_scan_from_qsc(fb, tmp_path):
+    """FDES --stem_scan (extension): the STEM .qsc drives the batched probe scan from the command line;
+    image_name holds float32 [detector][x][y]."""
+    import subprocess
+    from conftest import ROOT
+    for f in ("stem128.qsc", "sto.cfg"):
+        (tmp_path / f).write_text((DATA / f).read_text())
+    exe = ROOT / "fdes_b200" / "bin" / "FDES"
+    r = subprocess.run([str(exe), "--input_name", "stem128.qsc", "--stem_scan", "--image_name", "stem.bin"], cwd=tmp_path,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-500:]
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        xy, det = fb.qsc_scan(tmp_path / "stem128.qsc")
+        with fb.Simulation(tmp_path / "stem128.qsc", batch=32) as sim:
+            want, _ = sim.stem_scan(xy.reshape(-1, 2), det)
+    finally:
+        os.chdir(cwd)
+    got = np.fromfile(tmp_path / "stem.bin", np.float32).reshape(len(det), xy.shape[0], xy.shape[1])
+    np.testing.assert_array_equal(got, want.reshape(xy.shape[0], xy.shape[1], len(det)).transpose(2, 0, 1))
+    r = subprocess.run([str(exe), "--input_name", str(DATA / "qsc64.qsc"), "--stem_scan"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode != 0 and "scan_x_start" in r.stderr
