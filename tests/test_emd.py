@@ -188,3 +188,24 @@ def test_fdes_writes_the_results_emd_and_reads_it_back_as_input(fb, orc, tmp_pat
     fb.cuda_FDES(0, 0, str(tmp_path / "r.emd"), str(tmp_path / "M2.bin"), str(tmp_path / "r2.emd"), atoms6, len(atoms6), dst2)
     np.testing.assert_array_equal(dst2, dst)
     assert (tmp_path / "ParamsUsedEmd.txt").exists()
+
+
+def test_array_layouts_with_several_measurements(fb, tmp_path):
+    """n3 = 2 (tilt64): the k index is the FASTEST spatial index of the stored arrays
+    (f_xyz[i * n3 * n2 + j * n3 + k], src/rwHdf5.cu:413-419) -- a layout a single image cannot tell apart."""
+    r = fb.parse_cnf(DATA / "tilt64.cnf")
+    assert r["n3"] == 2
+    rng = np.random.default_rng(3)
+    img = rng.random((2, r["n2"], r["n1"]), np.float32)
+    ew = (rng.random((2, r["m2"], r["m1"])) + 1j * rng.random((2, r["m2"], r["m1"]))).astype(np.complex64)
+    fb.write_emd(DATA / "tilt64.cnf", tmp_path / "r.emd", img, None, ew)
+    f = h5min.File(tmp_path / "r.emd")
+    d = f.root["data/images/data"].data
+    assert d.shape == (r["n1"], r["n2"], 2)
+    for k in range(2):
+        np.testing.assert_array_equal(d[:, :, k], img[k].T)
+        np.testing.assert_array_equal(f.root["data/exit_wave/data"].data[:, :, k, 0], ew[k].real.T)
+        np.testing.assert_array_equal(f.root["data/exit_wave/data"].data[:, :, k, 1], ew[k].imag.T)
+    assert "potential_slices" not in f.root["data"].children
+    np.testing.assert_array_equal(f.root["imaging/specimen_tilt_x"].data, r["tiltspec"][:, 0])
+    np.testing.assert_array_equal(f.root["imaging/defoci"].data, r["defoci"])
