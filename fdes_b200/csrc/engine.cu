@@ -234,31 +234,6 @@ Engine::Engine(const Params& pin, const Atoms& atoms, const EngineOptions& opt) 
     }
     setup_tables();
     CK(cudaStreamSynchronize(st_));
-    // Experiment (FDES_B200_L2_PERSIST=1): keep the wave functions -- read and written by S5 and S6 of every
-    // slice -- resident in L2 through an access-policy window on the engine's stream; the potential /
-    // transmission grids stream past them.
-    if (const char* e = getenv("FDES_B200_L2_PERSIST")) {
-        if (atoi(e) > 0) {
-            cudaDeviceProp prop;
-            CK(cudaGetDeviceProperties(&prop, opt_.gpu_index));
-            const size_t want = (size_t)B_ * NN * sizeof(cpx);
-            const size_t persist = std::min((size_t)prop.persistingL2CacheMaxSize, want);
-            if (persist > 0) {
-                CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist));
-                cudaStreamAttrValue attr = {};
-                attr.accessPolicyWindow.base_ptr = Psi_;
-                attr.accessPolicyWindow.num_bytes = std::min(want, (size_t)prop.accessPolicyMaxWindowSize);
-                attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)persist / (double)attr.accessPolicyWindow.num_bytes);
-                attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-                attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-                CK(cudaStreamSetAttribute(st_, cudaStreamAttributeAccessPolicyWindow, &attr));
-                if (getenv("FDES_B200_TIMING"))
-                    fprintf(stderr, "  fdes_b200: L2 persistence window %zu MB (max persisting %zu MB, hit ratio %.2f)\n",
-                            attr.accessPolicyWindow.num_bytes >> 20, (size_t)prop.persistingL2CacheMaxSize >> 20,
-                            attr.accessPolicyWindow.hitRatio);
-            }
-        }
-    }
     pt.mark("ctor: rng+tables");
 }
 
