@@ -32,7 +32,6 @@ using Bytes = std::vector<uint8_t>;
 void put(Bytes& b, uint64_t v, int n) { for (int i = 0; i < n; i++) b.push_back((uint8_t)(v >> (8 * i))); }
 void pad8(Bytes& b) { while (b.size() % 8) b.push_back(0); }
 void append(Bytes& b, const Bytes& s) { b.insert(b.end(), s.begin(), s.end()); }
-size_t dt_size(DT dt, uint32_t strsize) { return dt == DT_STR ? strsize : dt == DT_U8 ? 1 : 4; }
 
 Bytes datatype_msg(DT dt, uint32_t strsize)
 {
@@ -517,6 +516,7 @@ struct H5In {
         if (t.cls == 1 && t.size == 8) { double v; memcpy(&v, &b.at(pos), 8); return v; }
         if (t.cls == 0) {
             const uint64_t raw = u(pos, (int)t.size);
+            if (t.sign && t.size == 8) return (double)(int64_t)raw;
             if (t.sign && t.size < 8 && (raw >> (8 * t.size - 1))) return (double)((int64_t)raw - ((int64_t)1 << (8 * t.size)));
             return (double)raw;
         }
@@ -552,7 +552,11 @@ struct H5In {
     bool attr_str(uint64_t ohdr, const std::string& name, std::string& out) const
     {
         Type t; uint64_t n, d;
-        if (ohdr == UNDEF || !attribute(ohdr, name, t, n, d) || t.cls != 3) return false;
+        if (ohdr == UNDEF) return false;
+        // names / comments are optional: a string this reader cannot decode (e.g. h5py's variable-length
+        // strings) leaves the default in place instead of failing the whole file
+        try { if (!attribute(ohdr, name, t, n, d) || t.cls != 3) return false; }
+        catch (const std::runtime_error&) { return false; }
         out.assign((const char*)&b.at(d), strnlen((const char*)&b.at(d), t.size));
         return true;
     }
