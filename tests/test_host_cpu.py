@@ -113,3 +113,27 @@ def test_shard_ranges():
             assert r[0][0] == 0 and r[-1][1] == count
             assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
             assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+
+
+def test_used_cnf_atom_table_is_formatted_like_printf(fb, tmp_path):
+    """writeConfig prints the atom table with "%i %14.8g %14.8g %14.8g %14.8g %14.8g \\n"
+    (src/paramStructure.cu:480-484); the product formats it with std::to_chars on a few threads --
+    every line must be what printf would have written, over 35 decades and the awkward values."""
+    from fdes_b200 import specimens
+    rng = np.random.default_rng(0)
+    vals = np.concatenate([
+        np.array([0.0, -0.0, 1.0, -1.5, 1e-10, 5.3837e-21, 123456789.0, 1.23456785e-5, 9.9999999e9, 3.4e38, 1e-38, 0.1,
+                  2 / 3, 99999999.5, 0.00001, 1e-5, 123456.78, 0.000123456785, 1e-4, 9.9999995e-5], np.float32),
+        (rng.standard_normal(12000) * 10.0 ** rng.integers(-25, 10, 12000)).astype(np.float32)])
+    v = vals[: len(vals) // 5 * 5].reshape(-1, 5)
+    atoms = np.column_stack([np.full(len(v), 14, np.float32), v]).astype(np.float32)
+    specimens.write_cnf(tmp_path / "adv.cnf", image_size=32, border_size=16, slices=2, pixel_size=0.25e-10,
+                        slice_thickness=2e-10, atoms=atoms)
+    lib = fb.load_library()
+    assert lib.fdes_b200_write_used_cnf(str(tmp_path / "adv.cnf").encode(), str(tmp_path / "used.txt").encode()) == 0
+    a = fb.parse_cnf(tmp_path / "adv.cnf")["atoms"]
+    lines = (tmp_path / "used.txt").read_text().splitlines()
+    i0 = next(i for i, l in enumerate(lines) if l.startswith("# Atomic no.")) + 1
+    assert len(a) >= 2400 and len(lines) - i0 == len(a)
+    for k, line in enumerate(lines[i0:]):
+        assert line == "%i %14.8g %14.8g %14.8g %14.8g %14.8g " % (int(a[k, 0]), *[float(x) for x in a[k, 1:6]]), k
