@@ -1,0 +1,36 @@
+// fdes_b200 -- run-time dispatch over the grid sizes the fast sweeps are instantiated for.
+// Every size lives in its own translation unit (sweeps_size.cu compiled with -DFDES_SWEEP_N=<N>),
+// so the sizes build in parallel; sweeps.cu selects the table of launchers by N.
+#pragma once
+#include "kernels.cuh"
+#include <vector>
+
+// grid sizes with register-resident Stockham line transforms (E points per thread, see
+// fft_core.cuh): powers of two and the 2^a 5^b sizes of the reference's shipped examples
+#define FDES_SWEEP_SIZES(X) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(320) X(800) X(1000)
+
+namespace fdes {
+
+struct SweepVTable {
+    int N, rows_per_block, cols_per_block;
+    void (*density_rows)(const SweepGeom&, cpx*, const int*, const int*, const float*, int, int, int, int, size_t, size_t, cudaStream_t);
+    void (*potential_cols)(const SweepGeom&, cpx*, const cpx*, const float*, const int*, int, int, int, int, size_t, cudaStream_t);
+    void (*transmit_rows)(const SweepGeom&, const cpx*, cpx*, int, float, int, cudaStream_t);
+    void (*bandlimit_cols)(const SweepGeom&, cpx*, int, int, cudaStream_t);
+    void (*multiply_rows)(const SweepGeom&, cpx*, const cpx*, size_t, int, bool, cudaStream_t);
+    void (*propagate_cols)(const SweepGeom&, cpx*, const cpx*, int, cudaStream_t);
+    void (*rows_fft)(const SweepGeom&, const void*, void*, int, RowEpilogue, const RowOpts&, int, cudaStream_t);
+    void (*rows_fft_sum)(const SweepGeom&, const cpx*, void*, int, RowEpilogue, const RowOpts&, int, cudaStream_t);
+    void (*cols_fft)(const SweepGeom&, const cpx*, void*, int, ColOp, const void*, float, int, cudaStream_t);
+    void (*probe_cols)(const SweepGeom&, cpx*, const cpx*, const float*, int, cudaStream_t);
+    int (*detector_tiles)(const SweepGeom&);
+    void (*detector_cols)(const SweepGeom&, const cpx*, float*, float*, const DetectorRings&, float, float, float, int, cudaStream_t);
+    std::vector<cpx> (*make_twiddles)();
+};
+
+// one per size, defined in that size's translation unit
+#define FDES_DECLARE_VT(N_) const SweepVTable* sweep_vtable_##N_();
+FDES_SWEEP_SIZES(FDES_DECLARE_VT)
+#undef FDES_DECLARE_VT
+
+}  // namespace fdes

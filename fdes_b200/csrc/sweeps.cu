@@ -1,944 +1,85 @@
-// fdes_b200 -- the multislice sweeps: hand-written sm_100a kernels that replace the
-// cuFFT + cuBLAS + one-thread-per-pixel chain of the reference's per-slice loop
-// (phaseGrating, src/crystalMaker.cu:507-536; forwardPropagation,
-// src/multisliceSimulation.cu:538-611).
-//
-// The wave function lives in the mixed (kx, y) domain between slices ("row space": rows are
-// Fourier transformed, columns are not).  One slice is six sweeps over the grid:
-//   S1 rows : density rows of each species (from sorted deposit records) -> FFT_row          -> A_z
-//   S2 cols : FFT_col(A_z) * G_z, sum over species, IFFT_col                                -> B
-//   S3 rows : IFFT_row(B) = V ; t0 = exp(iV) ; FFT_row(t0)                                   -> D
-//   S4 cols : FFT_col(D) * (2/3 mask / N) ; IFFT_col                                         -> E
-//   S5 rows : t = IFFT_row(E), psi = IFFT_row(Psi) ; FFT_row(t * psi)                        -> F
-//   S6 cols : FFT_col(F) * P ; IFFT_col                                                      -> Psi'
-// Every sweep reads and writes each pixel once; all multipliers come from small L2-resident
-// quarter tables.  Columns that the 2/3 band limit zeroes entirely (|kx| > N/3) are neither
-// stored, loaded nor transformed by S3..S6.
-#include "fft_core.cuh"
-#include "kernels.cuh"
-#include <cmath>
-#include <cstdio>
-#include <cstdlib>
-#include <vector>
+// fdes_b200 -- run-time dispatch of the multislice sweeps (kernels: sweep_kernels.cuh, one
+// translation unit per grid size: sweeps_size.cu).  Replaces the cuFFT + cuBLAS +
+// one-thread-per-pixel chain of the reference's per-slice loop (phaseGrating,
+// src/crystalMaker.cu:507-536; forwardPropagation, src/multisliceSimulation.cu:538-611).
+#include "sweep_vtable.h"
+#include <stdexcept>
+#include <string>
 
 namespace fdes {
 
-#define FDES_CUDA_CHECK(x)                                                                       \
-    do {                                                                                         \
-        cudaError_t e_ = (x);                                                                    \
-        if (e_ != cudaSuccess) {                                                                 \
-            fprintf(stderr, "fdes_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_),       \
-                    __FILE__, __LINE__);                                                         \
-            abort();                                                                             \
-        }                                                                                        \
-    } while (0)
-
-// register budget per thread that __launch_bounds__ asks the compiler to respect
-#ifndef FDES_ROW_MIN_CTAS
-#define FDES_ROW_MIN_CTAS 3
-#endif
-#ifndef FDES_COL_MIN_CTAS
-#define FDES_COL_MIN_CTAS 1
-#endif
-
-// Points per thread for a line of N points (rows and columns use the same split, so one
-// twiddle table per grid size serves both).
-template <int N>
-struct LineCfg {
-    static constexpr int E = (N & (N - 1)) != 0 ? 20                        // 2^a 5^b grids: 320, 800, 1000
-                                                : (N >= 512 ? 32 : (N >= 128 ? 16 : 8));
-    static constexpr int T = N / E;                     // threads per line
-    static constexpr int LS = line_smem_elems<E>(N);    // padded line buffer [elements]
-};
-template <int N>
-struct RowCfg {
-    using L = LineCfg<N>;
-    static constexpr int E = L::E, T = L::T;
-    static constexpr int RPB = (T & (T - 1)) != 0 ? 4 : ((128 / T) > 0 ? (128 / T) : 1);   // lines (rows) per CTA
-    static constexpr int THREADS = RPB * T;
-    static constexpr int LSTRIDE = L::LS;
-    static constexpr size_t SMEM = (size_t)RPB * LSTRIDE * sizeof(cpx);
-    static constexpr bool WARP_SYNC = (32 % T == 0);   // a line lives inside one warp
-    static constexpr bool NAMED_SYNC = (T % 32 == 0);  // a line is a whole number of warps
-    static constexpr int MIN_CTAS = (N >= 2048 || !WARP_SYNC) ? 2 : FDES_ROW_MIN_CTAS;   // long lines need the registers
-};
-// threads of one row line: warp-level sync when the line fits a warp, a named barrier when it is a
-// whole number of warps, else (T = 40, 50: lines straddle warps) the whole CTA
-template <int N>
-struct RowSync {
-    int id;
-    __device__ __forceinline__ explicit RowSync(int line) : id(line + 1) {}
-    __device__ __forceinline__ void operator()() const
-    {
-        if constexpr (RowCfg<N>::WARP_SYNC) __syncwarp();
-        else if constexpr (RowCfg<N>::NAMED_SYNC) asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(RowCfg<N>::T) : "memory");
-        else __syncthreads();
-    }
-};
-template <int N>
-struct ColCfg {
-    using L = LineCfg<N>;
-    static constexpr int E = L::E, T = L::T;
-    static constexpr int CW = (T & (T - 1)) != 0 ? (T <= 40 ? 8 : 4)                       // T = 40, 50
-                                                 : ((256 / T) >= 16 ? 16 : ((256 / T) >= 2 ? (256 / T) : 2));   // columns per CTA
-    static constexpr int THREADS = CW * T;
-    static constexpr int LSTRIDE = L::LS + 16 / CW;   // bank-conflict-free line stride
-    static constexpr size_t SMEM = (size_t)CW * LSTRIDE * sizeof(cpx);
-    // Staged tiles: the CTA moves its [N rows][CW columns] tile between global and shared memory
-    // with a column-fastest thread mapping (coalesced CW*8-byte row segments), while each column
-    // is transformed by the threads of ONE warp (warp-level synchronisation inside the FFT).
-    static constexpr bool STAGED = (32 % T == 0);
-    static constexpr int RPI = THREADS / CW;          // tile rows moved per iteration (= T)
-    static constexpr int MIN_CTAS = FDES_COL_MIN_CTAS;
-};
-
-template <int N>
-using ColCtx = ColTile<N, LineCfg<N>::E, ColCfg<N>::CW, ColCfg<N>::STAGED>;
-// Multiply x[m] (ky = theta + m*T) by the quarter table tab[min(ky, N - ky) * Q + ax]: the first
-// half of the points sits at base_lo + m*T*Q, the second at base_hi + (N - m*T)*Q with
-// base_lo = tab + ax + theta*Q and base_hi = tab + ax - theta*Q -- compile-time offsets.
-template <int N, int E, int M, class TabT, class F>
-__device__ __forceinline__ void quarter_table_apply(cpx (&x)[E], const TabT* lo, const TabT* hi, F f)
+static const SweepVTable* find_vtable(int N)
 {
-    constexpr int T = N / E, Q = N / 2 + 1;
-    if constexpr (M < E) {
-        if constexpr (M < E / 2) x[M] = f(x[M], ld_nc_at<M * T * Q>(lo));
-        else x[M] = f(x[M], ld_nc_at<(N - M * T) * Q>(hi));
-        quarter_table_apply<N, E, M + 1>(x, lo, hi, f);
+    switch (N) {
+#define FDES_VT_CASE(N_) case N_: return sweep_vtable_##N_();
+        FDES_SWEEP_SIZES(FDES_VT_CASE)
+#undef FDES_VT_CASE
+        default: return nullptr;
     }
 }
-struct KeepAll { __device__ __forceinline__ bool operator()(int) const { return true; } };
-
-bool fft_size_supported(int N)
+static const SweepVTable& vt(int N)
 {
-    return N == 64 || N == 128 || N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096 ||
-           N == 320 || N == 800 || N == 1000;
+    const SweepVTable* t = find_vtable(N);
+    if (!t) throw std::runtime_error("grid size " + std::to_string(N) + " has no fast sweep instantiation");
+    return *t;
 }
 
-#define FDES_DISPATCH_N(N_, ...)                                                               \
-    switch (N_) {                                                                                \
-        case 64: { constexpr int NN = 64; __VA_ARGS__; } break;                                         \
-        case 128: { constexpr int NN = 128; __VA_ARGS__; } break;                                       \
-        case 256: { constexpr int NN = 256; __VA_ARGS__; } break;                                       \
-        case 512: { constexpr int NN = 512; __VA_ARGS__; } break;                                       \
-        case 1024: { constexpr int NN = 1024; __VA_ARGS__; } break;                                     \
-        case 2048: { constexpr int NN = 2048; __VA_ARGS__; } break;                                     \
-        case 4096: { constexpr int NN = 4096; __VA_ARGS__; } break;                                     \
-        case 320: { constexpr int NN = 320; __VA_ARGS__; } break;                                       \
-        case 800: { constexpr int NN = 800; __VA_ARGS__; } break;                                       \
-        case 1000: { constexpr int NN = 1000; __VA_ARGS__; } break;                                     \
-        default:                                                                                 \
-            fprintf(stderr, "fdes_b200: unsupported grid size %d (need a power of two in "       \
-                            "[64, 4096] or 320, 800, 1000)\n", N_);                              \
-            abort();                                                                             \
-    }
+bool fft_size_supported(int N) { return find_vtable(N) != nullptr; }
+std::vector<cpx> make_twiddles(int N) { return vt(N).make_twiddles(); }
+int rows_per_block(int N) { return vt(N).rows_per_block; }
+int cols_per_block(int N) { return vt(N).cols_per_block; }
 
-template <typename K>
-static void allow_smem(K kernel, size_t bytes)
+void launch_density_rows(const SweepGeom& g, cpx* A, const int* rowptr, const int* rec_col, const float* rec_w,
+                         int slice, int slice2, int nZ, int batch, size_t rec_stride, size_t rowptr_stride, cudaStream_t st)
 {
-    if (bytes > 48 * 1024)
-        FDES_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)bytes));
+    vt(g.N).density_rows(g, A, rowptr, rec_col, rec_w, slice, slice2, nZ, batch, rec_stride, rowptr_stride, st);
 }
-
-__device__ __forceinline__ bool in_band(int kx, int lo_end, int hi_start)
+void launch_potential_cols(const SweepGeom& g, cpx* B, const cpx* A, const float* Gq, const int* rowptr, int slice,
+                           int slice2, int nZ, int batch, size_t rowptr_stride, cudaStream_t st)
 {
-    return kx < lo_end || kx >= hi_start;
+    vt(g.N).potential_cols(g, B, A, Gq, rowptr, slice, slice2, nZ, batch, rowptr_stride, st);
 }
-// band column tiles are numbered contiguously: [0, lo_end) then [hi_start, N)
-__device__ __forceinline__ int band_col0(int tile_col, int lo_end, int hi_start)
+void launch_transmit_rows(const SweepGeom& g, const cpx* W, cpx* D, int npair, float imPot, int batch, cudaStream_t st)
 {
-    return tile_col < lo_end ? tile_col : hi_start + (tile_col - lo_end);
+    vt(g.N).transmit_rows(g, W, D, npair, imPot, batch, st);
 }
-static int band_cols(const SweepGeom& g)
-{
-    return g.lo_end >= g.hi_start ? g.N : g.lo_end + (g.N - g.hi_start);
-}
-
-// The reference multiplies complex fields with a 3-multiplication form (multiplyElementwise,
-// src/complexMath.cu:44-62); here the plain product is used (FMUL2 + FFMA2).  Both are correctly
-// rounded to within 1-2 ulp of the exact product; the parity bound is 1e-5.
-
-// =============================================================================================
-// S1  density rows
-// =============================================================================================
-// Two slices share one complex transform: the density of `slice` goes to the real part and the
-// density of `slice2` (or nothing, slice2 < 0) to the imaginary part.  The scattering-factor
-// multiplier of S2 is real and even, so the two potentials come out of S3's inverse transform as
-// the real and the imaginary part -- half the potential work per slice.  (The absorptive factor
-// (1 + i*imPot) of squareAtoms_d, src/crystalMaker.cu:100-119, is a constant complex scale of a
-// real field and is applied in S3.)
-template <int N>
-__global__ void __launch_bounds__(RowCfg<N>::THREADS, RowCfg<N>::MIN_CTAS)
-k_density_rows(cpx* __restrict__ A, const int* __restrict__ rowptr, const int* __restrict__ rec_col,
-               const float* __restrict__ rec_w, int slice, int slice2, int nZ, size_t rec_stride,
-               size_t rp_stride, const cpx* __restrict__ tw)
-{
-    using C = RowCfg<N>;
-    extern __shared__ cpx smem[];
-    constexpr int E = C::E;
-    const int line = threadIdx.x / C::T, theta = threadIdx.x % C::T;
-    const RowSync<N> sync(line);
-    const int z = blockIdx.y, b = blockIdx.z;
-    const int row = blockIdx.x * C::RPB + line;
-    const int* rp = rowptr + (size_t)b * rp_stride + (size_t)(slice * nZ + z) * N;
-    const int lo = rp[row], hi = rp[row + 1];
-    int lo2 = 0, hi2 = 0;
-    if (slice2 >= 0) {
-        const int* rp2 = rowptr + (size_t)b * rp_stride + (size_t)(slice2 * nZ + z) * N;
-        lo2 = rp2[row]; hi2 = rp2[row + 1];
-    }
-    // rows without deposits are never read by S2 (it consults the same row pointers)
-    if (!__syncthreads_or(hi > lo || hi2 > lo2)) return;
-    cpx* dens = smem + C::RPB * C::LSTRIDE + line * N;
-#pragma unroll
-    for (int m = 0; m < E; m++) dens[theta + m * C::T] = make_float2(0.f, 0.f);
-    __syncthreads();
-    if (theta == 0) {
-        // sorted, stable order -> the summation order is fixed (deterministic, unlike the
-        // float atomicAdd of squareAtoms_d, src/crystalMaker.cu:100-119)
-        const int* cc = rec_col + (size_t)b * rec_stride;
-        const float* ww = rec_w + (size_t)b * rec_stride;
-        for (int i = lo; i < hi; i++) dens[cc[i]].x += ww[i];
-        for (int i = lo2; i < hi2; i++) dens[cc[i]].y += ww[i];
-    }
-    __syncthreads();
-    cpx x[E];
-#pragma unroll
-    for (int m = 0; m < E; m++) x[m] = dens[theta + m * C::T];
-    fft_line<N, E, -1>(x, smem + line * C::LSTRIDE, theta, tw, sync);
-    cpx* out = A + ((size_t)(b * nZ + z) * N + row) * N;
-#pragma unroll
-    for (int m = 0; m < E; m++) out[theta + m * C::T] = x[m];
-}
-
-void launch_density_rows(const SweepGeom& g, cpx* A, const int* rowptr, const int* rec_col,
-                         const float* rec_w, int slice, int slice2, int nZ, int batch, size_t rec_stride,
-                         size_t rowptr_stride, cudaStream_t st)
-{
-    FDES_DISPATCH_N(g.N, {
-        using C = RowCfg<NN>;
-        const size_t smem = C::SMEM + (size_t)C::RPB * NN * sizeof(cpx);
-        static bool once = false;
-        if (!once) { allow_smem(k_density_rows<NN>, smem); once = true; }
-        dim3 grid(NN / C::RPB, nZ, batch);
-        k_density_rows<NN><<<grid, C::THREADS, smem, st>>>(A, rowptr, rec_col, rec_w, slice, slice2, nZ,
-                                                          rec_stride, rowptr_stride, g.tw);
-    });
-}
-
-// =============================================================================================
-// S2  potential columns
-// =============================================================================================
-template <int N>
-__global__ void __launch_bounds__(ColCfg<N>::THREADS, ColCfg<N>::MIN_CTAS)
-k_potential_cols(cpx* __restrict__ B, const cpx* __restrict__ A, const float* __restrict__ Gq,
-                 const int* __restrict__ rowptr, int slice, int slice2, int nZ, size_t rp_stride,
-                 const cpx* __restrict__ tw)
-{
-    using C = ColCfg<N>;
-    extern __shared__ cpx smem[];
-    constexpr int Q = N / 2 + 1;
-    constexpr int E = C::E;
-    const ColCtx<N> ctx(smem);
-    const int theta = ctx.theta;
-    const int kx0 = blockIdx.x * C::CW, kx = kx0 + ctx.line, b = blockIdx.y;
-    const int ax = min(kx, N - kx);
-    cpx acc[E];
-#pragma unroll
-    for (int m = 0; m < E; m++) acc[m] = make_float2(0.f, 0.f);
-    bool any = false;
-    for (int z = 0; z < nZ; z++) {
-        const int* rp = rowptr + (size_t)b * rp_stride + (size_t)(slice * nZ + z) * N;
-        // second slice of the pair (imaginary part); the same slice again when there is none
-        const int* rp2 = slice2 >= 0 ? rowptr + (size_t)b * rp_stride + (size_t)(slice2 * nZ + z) * N : rp;
-        if (rp[N] == rp[0] && rp2[N] == rp2[0]) continue;  // species absent from both slices (CTA-uniform)
-        const cpx* Az = A + (size_t)(b * nZ + z) * N * N + kx0;
-        cpx x[E];
-        // rows without deposits were not written by S1: read them as zero (branch-free test so the
-        // tile loads stay batched)
-        ctx.load(x, Az, [rp, rp2](int y) { return (rp[y + 1] > rp[y]) | (rp2[y + 1] > rp2[y]); }, any);
-        any = true;
-        fft_line<N, E, -1>(x, ctx.sm, theta, tw, ctx);
-        const float* G = Gq + (size_t)z * Q * Q + ax;
-        // acc += x * G  (tmp holds x * G; the accumulate stays a separate packed add)
-        quarter_table_apply<N, E, 0>(x, G + theta * Q, G - theta * Q,
-                                     [](cpx v, float gz) { return pmul(v, make_float2(gz, gz)); });
-#pragma unroll
-        for (int m = 0; m < E; m++) acc[m] = padd(acc[m], x[m]);
-    }
-    if (any) fft_line<N, E, 1>(acc, ctx.sm, theta, tw, ctx);
-    ctx.store(acc, B + (size_t)b * N * N + kx0);
-}
-
-void launch_potential_cols(const SweepGeom& g, cpx* B, const cpx* A, const float* Gq,
-                           const int* rowptr, int slice, int slice2, int nZ, int batch, size_t rowptr_stride,
-                           cudaStream_t st)
-{
-    FDES_DISPATCH_N(g.N, {
-        using C = ColCfg<NN>;
-        static bool once = false;
-        if (!once) { allow_smem(k_potential_cols<NN>, C::SMEM); once = true; }
-        dim3 grid(NN / C::CW, batch);
-        k_potential_cols<NN><<<grid, C::THREADS, C::SMEM, st>>>(B, A, Gq, rowptr, slice, slice2, nZ,
-                                                               rowptr_stride, g.tw);
-    });
-}
-
-// =============================================================================================
-// S3  transmission rows
-// =============================================================================================
-// W holds the packed potential spectrum of a slice pair in the (kx, y) domain (S2); its inverse
-// row transform is V_a + i V_b.  For each slice of the pair: t0 = exp(i V (1 + i imPot)) and its
-// row transform goes to D[(2 b + p)], band columns only.
-// sin and cos of one argument with a compact code footprint: Cody-Waite reduction to
-// [-pi/4, pi/4] (three-term pi/2, exact products through FMA) and the Cephes single-precision
-// minimax polynomials, ~1 ulp for |x| < 1e5.  The library sincosf() inlines its Payne-Hanek slow
-// path at every call site; 64 call sites made this kernel 180 KB of code and instruction-cache
-// bound.  Arguments beyond 1e5 rad (no physical potential gets there) take one shared out-of-line
-// copy of the library routine.
-__device__ __noinline__ void sincos_large(float x, float* s, float* c) { sincosf(x, s, c); }
-__device__ __forceinline__ void sincos_compact(float x, float& sn, float& cs)
-{
-    if (fabsf(x) > 1.0e5f) { sincos_large(x, &sn, &cs); return; }
-    const float kf = rintf(x * 0.636619772f);
-    const int k = (int)kf;
-    float r = fmaf(kf, -1.57079601e+00f, x);
-    r = fmaf(kf, -3.13916473e-07f, r);
-    r = fmaf(kf, -5.39030253e-15f, r);
-    const float r2 = r * r;
-    float ps = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
-    ps = fmaf(ps, r2, -1.6666654611e-1f);
-    ps = fmaf(ps * r2, r, r);                                   // sin(r)
-    float pc = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
-    pc = fmaf(pc, r2, 4.166664568298827e-2f);
-    pc = fmaf(pc * r2, r2, fmaf(r2, -0.5f, 1.0f));              // cos(r)
-    const float a = (k & 1) ? pc : ps;                          // quadrant rotation
-    const float b = (k & 1) ? ps : pc;
-    sn = (k & 2) ? -a : a;
-    cs = ((k + 1) & 2) ? -b : b;
-}
-template <int N>
-__device__ __forceinline__ cpx transmission(float V, float imPot)
-{
-    // potential2Transmission, src/multisliceSimulation.cu:41-52, with V.x = V and V.y = imPot * V
-    float sn, cs;
-    sincos_compact(V, sn, cs);
-    if (imPot != 0.f) {
-        const float e = __expf(-(V * imPot));
-        return make_float2(e * cs, e * sn);
-    }
-    return make_float2(cs, sn);
-}
-template <int N>
-__global__ void __launch_bounds__(RowCfg<N>::THREADS, RowCfg<N>::MIN_CTAS)
-k_transmit_rows(const cpx* __restrict__ W, cpx* __restrict__ D, int npair, float imPot, int lo_end,
-                int hi_start, const cpx* __restrict__ tw)
-{
-    using C = RowCfg<N>;
-    extern __shared__ cpx smem[];
-    constexpr int E = C::E;
-    const int line = threadIdx.x / C::T, theta = threadIdx.x % C::T;
-    const RowSync<N> sync(line);
-    const size_t row = (size_t)blockIdx.x * C::RPB + line;
-    const size_t in_off = ((size_t)blockIdx.y * N + row) * N;
-    cpx* sm = smem + line * C::LSTRIDE;
-    float* park = reinterpret_cast<float*>(smem + C::RPB * C::LSTRIDE) + line * (2 * N);   // V_a | V_b
-    cpx x[E];
-#pragma unroll
-    for (int m = 0; m < E; m++) x[m] = W[in_off + theta + m * C::T];
-    fft_line<N, E, 1>(x, sm, theta, tw, sync);
-#pragma unroll
-    for (int m = 0; m < E; m++) {
-        park[theta + m * C::T] = x[m].x;
-        park[N + theta + m * C::T] = x[m].y;
-    }
-    // one copy of the exp / forward-transform code for both slices of the pair
-#pragma unroll 1
-    for (int p = 0; p < npair; p++) {
-        const float* V = park + p * N;
-#pragma unroll
-        for (int m = 0; m < E; m++) x[m] = transmission<N>(V[theta + m * C::T], imPot);
-        fft_line<N, E, -1>(x, sm, theta, tw, sync);
-        cpx* out = D + ((size_t)(blockIdx.y * 2 + p) * N + row) * N;
-#pragma unroll
-        for (int m = 0; m < E; m++) {
-            const int kx = theta + m * C::T;
-            if (in_band(kx, lo_end, hi_start)) out[kx] = x[m];
-        }
-    }
-}
-
-void launch_transmit_rows(const SweepGeom& g, const cpx* W, cpx* D, int npair, float imPot, int batch,
-                          cudaStream_t st)
-{
-    FDES_DISPATCH_N(g.N, {
-        using C = RowCfg<NN>;
-        const size_t smem = C::SMEM + (size_t)C::RPB * NN * 2 * sizeof(float);
-        static bool once = false;
-        if (!once) { allow_smem(k_transmit_rows<NN>, smem); once = true; }
-        dim3 grid(NN / C::RPB, batch);
-        k_transmit_rows<NN><<<grid, C::THREADS, smem, st>>>(W, D, npair, imPot, g.lo_end, g.hi_start, g.tw);
-    });
-}
-
-// =============================================================================================
-// S4  band-limit columns
-// =============================================================================================
-template <int N>
-__global__ void __launch_bounds__(ColCfg<N>::THREADS, LineCfg<N>::T <= 32 ? 2 : ColCfg<N>::MIN_CTAS)
-k_bandlimit_cols(cpx* __restrict__ W, int npair, int lo_end, int hi_start, const cpx* __restrict__ tw)
-{
-    using C = ColCfg<N>;
-    extern __shared__ cpx smem[];
-    constexpr int E = C::E;
-    const ColCtx<N> ctx(smem);
-    const int theta = ctx.theta;
-    const int kx0 = band_col0(blockIdx.x * C::CW, lo_end, hi_start), kx = kx0 + ctx.line;
-    // entry (b, p) of a [batch][2] stack; npair = 1 uses p = 0 only, npair = 0: plain [batch]
-    const size_t entry = npair == 0 ? blockIdx.y : (size_t)(blockIdx.y / npair) * 2 + blockIdx.y % npair;
-    cpx* tile = W + entry * N * N + kx0;
-    cpx x[E];
-    ctx.load(x, tile, KeepAll());
-    fft_line<N, E, -1>(x, ctx.sm, theta, tw, ctx);
-    // zeroHighFreq (src/multisliceSimulation.cu:225-250) and the 1/N of bandwidthLimit (:558-559)
-    const int i1 = kx > N / 2 ? kx - N : kx;
-    const float mind = (float)N;
-    const float alpha = 1.f / ((float)(N * N));
-#pragma unroll
-    for (int m = 0; m < E; m++) {
-        const int ky = theta + m * C::T;
-        const int i2 = ky > N / 2 ? ky - N : ky;
-        const bool cut = ((float)(i1 * i1 + i2 * i2) * 9.f / (mind * mind)) > 1.f;
-        x[m] = cut ? make_float2(0.f, 0.f) : make_float2(x[m].x * alpha, x[m].y * alpha);
-    }
-    fft_line<N, E, 1>(x, ctx.sm, theta, tw, ctx);
-    ctx.store(x, tile);
-}
-
 void launch_bandlimit_cols(const SweepGeom& g, cpx* W, int batch, int npair, cudaStream_t st)
 {
-    FDES_DISPATCH_N(g.N, {
-        using C = ColCfg<NN>;
-        static bool once = false;
-        if (!once) { allow_smem(k_bandlimit_cols<NN>, C::SMEM); once = true; }
-        dim3 grid(band_cols(g) / C::CW, npair == 0 ? batch : batch * npair);
-        k_bandlimit_cols<NN><<<grid, C::THREADS, C::SMEM, st>>>(W, npair, g.lo_end, g.hi_start, g.tw);
-    });
+    vt(g.N).bandlimit_cols(g, W, batch, npair, st);
 }
-
-// =============================================================================================
-// S5  multiply rows
-// =============================================================================================
-template <int N>
-__global__ void __launch_bounds__(RowCfg<N>::THREADS, RowCfg<N>::MIN_CTAS)
-k_multiply_rows(cpx* __restrict__ Psi, const cpx* __restrict__ Tk, size_t e_batch_stride,
-                int lo_end, int hi_start, int psi_full, const cpx* __restrict__ tw)
+void launch_multiply_rows(const SweepGeom& g, cpx* Psi, const cpx* E, size_t e_batch_stride, int batch, bool psi_full,
+                          cudaStream_t st)
 {
-    using C = RowCfg<N>;
-    extern __shared__ cpx smem[];
-    constexpr int E = C::E;
-    const int line = threadIdx.x / C::T, theta = threadIdx.x % C::T;
-    const RowSync<N> sync(line);
-    const size_t row = (size_t)blockIdx.x * C::RPB + line;
-    const cpx* e = Tk + (size_t)blockIdx.y * e_batch_stride + row * N;
-    cpx* p = Psi + ((size_t)blockIdx.y * N + row) * N;
-    cpx* sm = smem + line * C::LSTRIDE;
-    // t = IFFT_row(Tk) is parked in shared memory while psi is transformed (two register sets of
-    // E points each would not fit)
-    cpx* park = smem + C::RPB * C::LSTRIDE + line * N;
-    cpx x[E];
-#pragma unroll
-    for (int m = 0; m < E; m++) {
-        const int kx = theta + m * C::T;
-        x[m] = in_band(kx, lo_end, hi_start) ? e[kx] : make_float2(0.f, 0.f);
-    }
-    fft_line<N, E, 1>(x, sm, theta, tw, sync);
-#pragma unroll
-    for (int m = 0; m < E; m++) park[theta + m * C::T] = x[m];
-#pragma unroll
-    for (int m = 0; m < E; m++) {
-        const int kx = theta + m * C::T;
-        x[m] = (in_band(kx, lo_end, hi_start) || psi_full) ? ld_g(p + kx) : make_float2(0.f, 0.f);
-    }
-    fft_line<N, E, 1>(x, sm, theta, tw, sync);
-#pragma unroll
-    for (int m = 0; m < E; m++) x[m] = cmul(park[theta + m * C::T], x[m]);
-    fft_line<N, E, -1>(x, sm, theta, tw, sync);
-#pragma unroll
-    for (int m = 0; m < E; m++) {
-        const int kx = theta + m * C::T;
-        if (in_band(kx, lo_end, hi_start)) p[kx] = x[m];
-    }
+    vt(g.N).multiply_rows(g, Psi, E, e_batch_stride, batch, psi_full, st);
 }
-
-void launch_multiply_rows(const SweepGeom& g, cpx* Psi, const cpx* E, size_t e_batch_stride,
-                          int batch, bool psi_full, cudaStream_t st)
-{
-    FDES_DISPATCH_N(g.N, {
-        using C = RowCfg<NN>;
-        const size_t smem = C::SMEM + (size_t)C::RPB * NN * sizeof(cpx);
-        static bool once = false;
-        if (!once) { allow_smem(k_multiply_rows<NN>, smem); once = true; }
-        dim3 grid(NN / C::RPB, batch);
-        k_multiply_rows<NN><<<grid, C::THREADS, smem, st>>>(Psi, E, e_batch_stride, g.lo_end,
-                                                              g.hi_start, psi_full ? 1 : 0, g.tw);
-    });
-}
-
-// =============================================================================================
-// S6  propagate columns
-// =============================================================================================
-template <int N>
-__global__ void __launch_bounds__(ColCfg<N>::THREADS, ColCfg<N>::MIN_CTAS)
-k_propagate_cols(cpx* __restrict__ Psi, const cpx* __restrict__ Pq, int lo_end, int hi_start,
-                 const cpx* __restrict__ tw)
-{
-    using C = ColCfg<N>;
-    extern __shared__ cpx smem[];
-    constexpr int Q = N / 2 + 1;
-    constexpr int E = C::E;
-    const ColCtx<N> ctx(smem);
-    const int theta = ctx.theta;
-    const int kx0 = band_col0(blockIdx.x * C::CW, lo_end, hi_start), kx = kx0 + ctx.line;
-    cpx* tile = Psi + (size_t)blockIdx.y * N * N + kx0;
-    cpx x[E];
-    ctx.load(x, tile, KeepAll());
-    fft_line<N, E, -1>(x, ctx.sm, theta, tw, ctx);
-    const cpx* P = Pq + min(kx, N - kx);
-    quarter_table_apply<N, E, 0>(x, P + theta * Q, P - theta * Q, [](cpx v, cpx p) { return cmul(v, p); });
-    fft_line<N, E, 1>(x, ctx.sm, theta, tw, ctx);
-    ctx.store(x, tile);
-}
-
 void launch_propagate_cols(const SweepGeom& g, cpx* Psi, const cpx* Pq, int batch, cudaStream_t st)
 {
-    FDES_DISPATCH_N(g.N, {
-        using C = ColCfg<NN>;
-        static bool once = false;
-        if (!once) { allow_smem(k_propagate_cols<NN>, C::SMEM); once = true; }
-        dim3 grid(band_cols(g) / C::CW, batch);
-        k_propagate_cols<NN><<<grid, C::THREADS, C::SMEM, st>>>(Psi, Pq, g.lo_end, g.hi_start, g.tw);
-    });
+    vt(g.N).propagate_cols(g, Psi, Pq, batch, st);
 }
-
-// =============================================================================================
-// generic row sweep
-// =============================================================================================
-template <int N, int DIR, int EPI>
-__global__ void __launch_bounds__(RowCfg<N>::THREADS, RowCfg<N>::MIN_CTAS)
-k_rows_fft(const void* __restrict__ in_, void* __restrict__ out_, RowOpts o, int lo_end,
-           int hi_start, const cpx* __restrict__ tw)
+void launch_rows_fft(const SweepGeom& g, const void* in, void* out, int dir, RowEpilogue epi, const RowOpts& o, int batch,
+                     cudaStream_t st)
 {
-    using C = RowCfg<N>;
-    extern __shared__ cpx smem[];
-    constexpr int E = C::E;
-    const int line = threadIdx.x / C::T, theta = threadIdx.x % C::T;
-    const RowSync<N> sync(line);
-    const int y = blockIdx.x * C::RPB + line;
-    const size_t rowoff = ((size_t)blockIdx.y * N + y) * N;
-    cpx x[E];
-#pragma unroll
-    for (int m = 0; m < E; m++) {
-        const int kx = theta + m * C::T;
-        if (o.in_is_real)
-            x[m] = make_float2(static_cast<const float*>(in_)[rowoff + kx], 0.f);
-        else if (!o.band_only_in || in_band(kx, lo_end, hi_start))
-            x[m] = static_cast<const cpx*>(in_)[rowoff + kx];
-        else
-            x[m] = make_float2(0.f, 0.f);
-    }
-    fft_line<N, E, DIR>(x, smem + line * C::LSTRIDE, theta, tw, sync);
-#pragma unroll
-    for (int m = 0; m < E; m++) {
-        const int xx = theta + m * C::T;
-        const cpx v = make_float2(x[m].x * o.scale, x[m].y * o.scale);
-        if (EPI == ROW_STORE) {
-            static_cast<cpx*>(out_)[rowoff + xx] =
-                (o.band_only_out && !in_band(xx, lo_end, hi_start)) ? make_float2(0.f, 0.f) : v;
-        } else if (EPI == ROW_ACCUM) {
-            cpx* q = static_cast<cpx*>(out_) + rowoff + xx;
-            const cpx old = *q;
-            *q = make_float2(old.x + v.x, old.y + v.y);
-        } else if (EPI == ROW_INTENS_ACCUM) {
-            float* q = static_cast<float*>(out_) + rowoff + xx;
-            *q += o.scale * (x[m].x * x[m].x + x[m].y * x[m].y);
-        } else if (EPI == ROW_STORE_SHIFT) {
-            const int ys = (y + N / 2) % N, xs = (xx + N / 2) % N;
-            static_cast<cpx*>(out_)[((size_t)blockIdx.y * N + ys) * N + xs] = v;
-        } else {  // ROW_CROP_REAL
-            const int cx = xx - o.dn1, cy = y - o.dn2;
-            if (cx >= 0 && cx < o.n1 && cy >= 0 && cy < o.n2)
-                static_cast<float*>(out_)[((size_t)blockIdx.y * o.n2 + cy) * o.n1 + cx] = v.x;
-        }
-    }
+    vt(g.N).rows_fft(g, in, out, dir, epi, o, batch, st);
 }
-
-template <int N, int DIR>
-static void rows_fft_epi(const SweepGeom& g, const void* in, void* out, RowEpilogue epi,
-                         const RowOpts& o, int batch, cudaStream_t st)
+void launch_rows_fft_sum(const SweepGeom& g, const cpx* in, void* out, int dir, RowEpilogue epi, const RowOpts& o, int nb,
+                         cudaStream_t st)
 {
-    using C = RowCfg<N>;
-    dim3 grid(N / C::RPB, batch);
-#define FDES_ROWS_CASE(EPI_)                                                                     \
-    case EPI_: {                                                                                 \
-        static bool once = false;                                                                \
-        if (!once) { allow_smem(k_rows_fft<N, DIR, EPI_>, C::SMEM); once = true; }               \
-        k_rows_fft<N, DIR, EPI_><<<grid, C::THREADS, C::SMEM, st>>>(in, out, o, g.lo_end,        \
-                                                                   g.hi_start, g.tw);            \
-    } break;
-    switch (epi) {
-        FDES_ROWS_CASE(ROW_STORE)
-        FDES_ROWS_CASE(ROW_ACCUM)
-        FDES_ROWS_CASE(ROW_INTENS_ACCUM)
-        FDES_ROWS_CASE(ROW_STORE_SHIFT)
-        FDES_ROWS_CASE(ROW_CROP_REAL)
-    }
-#undef FDES_ROWS_CASE
+    vt(g.N).rows_fft_sum(g, in, out, dir, epi, o, nb, st);
 }
-
-void launch_rows_fft(const SweepGeom& g, const void* in, void* out, int dir, RowEpilogue epi,
-                     const RowOpts& o, int batch, cudaStream_t st)
+void launch_cols_fft(const SweepGeom& g, const cpx* in, void* out, int dir, ColOp op, const void* table, float scale,
+                     int batch, cudaStream_t st)
 {
-    FDES_DISPATCH_N(g.N, {
-        if (dir < 0) rows_fft_epi<NN, -1>(g, in, out, epi, o, batch, st);
-        else rows_fft_epi<NN, 1>(g, in, out, epi, o, batch, st);
-    });
+    vt(g.N).cols_fft(g, in, out, dir, op, table, scale, batch, st);
 }
-
-// Sum over a batch in a fixed order (deterministic phonon average): for b = 0 .. nb-1 in turn,
-// transform row y of in[b] and add scale * v (EPI = ROW_ACCUM, complex out) or scale * |v|^2
-// (EPI = ROW_INTENS_ACCUM, float out) -- one read-modify-write of `out` per batch instead of per
-// configuration.
-template <int N, int DIR, int EPI>
-__global__ void __launch_bounds__(RowCfg<N>::THREADS, RowCfg<N>::MIN_CTAS)
-k_rows_fft_sum(const cpx* __restrict__ in, void* __restrict__ out_, RowOpts o, int nb, int lo_end,
-               int hi_start, const cpx* __restrict__ tw)
+void launch_probe_cols(const SweepGeom& g, cpx* Psi, const cpx* PSI0, const float* shifts, int batch, cudaStream_t st)
 {
-    using C = RowCfg<N>;
-    extern __shared__ cpx smem[];
-    constexpr int E = C::E;
-    const int line = threadIdx.x / C::T, theta = threadIdx.x % C::T;
-    const RowSync<N> sync(line);
-    const int y = blockIdx.x * C::RPB + line;
-    const size_t rowoff = (size_t)y * N;
-    cpx acc[EPI == ROW_ACCUM ? E : 1];
-    float acci[EPI == ROW_ACCUM ? 1 : E];
-    // start from the current content of `out`: the additions then happen in exactly the order and
-    // rounding of nb successive single-configuration accumulations (results do not depend on nb)
-#pragma unroll
-    for (int m = 0; m < E; m++) {
-        const int xx = theta + m * C::T;
-        if (EPI == ROW_ACCUM) acc[m] = static_cast<const cpx*>(out_)[rowoff + xx];
-        else acci[m] = static_cast<const float*>(out_)[rowoff + xx];
-    }
-#pragma unroll 1
-    for (int b = 0; b < nb; b++) {
-        const cpx* src = in + (size_t)b * N * N + rowoff;
-        cpx x[E];
-#pragma unroll
-        for (int m = 0; m < E; m++) {
-            const int kx = theta + m * C::T;
-            x[m] = (!o.band_only_in || in_band(kx, lo_end, hi_start)) ? src[kx] : make_float2(0.f, 0.f);
-        }
-        fft_line<N, E, DIR>(x, smem + line * C::LSTRIDE, theta, tw, sync);
-        // same rounding sequence as nb successive single accumulations: out += scale * v
-#pragma unroll
-        for (int m = 0; m < E; m++) {
-            if (EPI == ROW_ACCUM) { acc[m].x += x[m].x * o.scale; acc[m].y += x[m].y * o.scale; }   // as k_rows_fft: v = x * scale; old + v
-            else acci[m] += o.scale * (x[m].x * x[m].x + x[m].y * x[m].y);
-        }
-    }
-#pragma unroll
-    for (int m = 0; m < E; m++) {
-        const int xx = theta + m * C::T;
-        if (EPI == ROW_ACCUM) static_cast<cpx*>(out_)[rowoff + xx] = acc[m];
-        else static_cast<float*>(out_)[rowoff + xx] = acci[m];
-    }
+    vt(g.N).probe_cols(g, Psi, PSI0, shifts, batch, st);
 }
-
-void launch_rows_fft_sum(const SweepGeom& g, const cpx* in, void* out, int dir, RowEpilogue epi,
-                         const RowOpts& o, int nb, cudaStream_t st)
-{
-    FDES_DISPATCH_N(g.N, {
-        using C = RowCfg<NN>;
-        dim3 grid(NN / C::RPB);
-        if (dir > 0 && epi == ROW_ACCUM) {
-            static bool once = false;
-            if (!once) { allow_smem(k_rows_fft_sum<NN, 1, ROW_ACCUM>, C::SMEM); once = true; }
-            k_rows_fft_sum<NN, 1, ROW_ACCUM><<<grid, C::THREADS, C::SMEM, st>>>(in, out, o, nb, g.lo_end, g.hi_start, g.tw);
-        } else if (dir > 0 && epi == ROW_INTENS_ACCUM) {
-            static bool once = false;
-            if (!once) { allow_smem(k_rows_fft_sum<NN, 1, ROW_INTENS_ACCUM>, C::SMEM); once = true; }
-            k_rows_fft_sum<NN, 1, ROW_INTENS_ACCUM><<<grid, C::THREADS, C::SMEM, st>>>(in, out, o, nb, g.lo_end, g.hi_start, g.tw);
-        } else {
-            fprintf(stderr, "fdes_b200: launch_rows_fft_sum supports inverse transforms with ROW_ACCUM / ROW_INTENS_ACCUM\n");
-            abort();
-        }
-    });
-}
-
-// =============================================================================================
-// generic column sweep
-// =============================================================================================
-template <int N, int DIR, int OP>
-__global__ void __launch_bounds__(ColCfg<N>::THREADS, ColCfg<N>::MIN_CTAS)
-k_cols_fft(const cpx* __restrict__ in, void* __restrict__ out_, const void* __restrict__ table,
-           float scale, const cpx* __restrict__ tw)
-{
-    using C = ColCfg<N>;
-    extern __shared__ cpx smem[];
-    constexpr int E = C::E;
-    const ColCtx<N> ctx(smem);
-    const int theta = ctx.theta;
-    const int kx0 = blockIdx.x * C::CW, kx = kx0 + ctx.line;
-    const size_t boff = (size_t)blockIdx.y * N * N;
-    cpx x[E];
-    ctx.load(x, in + boff + kx0, KeepAll());
-    if (OP == COL_PLAIN) {
-        fft_line<N, E, DIR>(x, ctx.sm, theta, tw, ctx);
-#pragma unroll
-        for (int m = 0; m < E; m++) x[m] = make_float2(x[m].x * scale, x[m].y * scale);
-        ctx.store(x, static_cast<cpx*>(out_) + boff + kx0);
-        return;
-    }
-    fft_line<N, E, -1>(x, ctx.sm, theta, tw, ctx);
-    if (OP == COL_DP_ACCUM) {
-        // |fftshift(FFT psi)|^2 / N accumulated with weight (diffractionPattern,
-        // src/crystalMaker.cu:714-717; cufftShift2D_h, src/complexMath.cu:510-557)
-        float* out = static_cast<float*>(out_);
-        const int xs = (kx + N / 2) % N;
-#pragma unroll
-        for (int m = 0; m < E; m++) {
-            const int ys = (theta + m * C::T + N / 2) % N;
-            out[boff + (size_t)ys * N + xs] += scale * (x[m].x * x[m].x + x[m].y * x[m].y);
-        }
-        return;
-    }
-#pragma unroll
-    for (int m = 0; m < E; m++) {
-        const size_t idx = (size_t)(theta + m * C::T) * N + kx;
-        if (OP == COL_MUL_CPX_INV) {
-            // psi * CTF as in multiplyLensFunction (src/multisliceSimulation.cu:339-340)
-            const cpx w = ld_nc(static_cast<const cpx*>(table) + idx);
-            x[m] = make_float2(w.x * x[m].x - w.y * x[m].y, w.x * x[m].y + w.y * x[m].x);
-        } else {
-            const float w = ld_nc(static_cast<const float*>(table) + idx);
-            x[m] = make_float2(x[m].x * w, x[m].y * w);
-        }
-    }
-    fft_line<N, E, 1>(x, ctx.sm, theta, tw, ctx);
-#pragma unroll
-    for (int m = 0; m < E; m++) x[m] = make_float2(x[m].x * scale, x[m].y * scale);
-    ctx.store(x, static_cast<cpx*>(out_) + boff + kx0);
-}
-
-template <int N, int DIR, int OP>
-static void cols_fft_one(const SweepGeom& g, const cpx* in, void* out, const void* table,
-                         float scale, int batch, cudaStream_t st)
-{
-    using C = ColCfg<N>;
-    static bool once = false;
-    if (!once) { allow_smem(k_cols_fft<N, DIR, OP>, C::SMEM); once = true; }
-    dim3 grid(N / C::CW, batch);
-    k_cols_fft<N, DIR, OP><<<grid, C::THREADS, C::SMEM, st>>>(in, out, table, scale, g.tw);
-}
-
-void launch_cols_fft(const SweepGeom& g, const cpx* in, void* out, int dir, ColOp op,
-                     const void* table, float scale, int batch, cudaStream_t st)
-{
-    FDES_DISPATCH_N(g.N, {
-        switch (op) {
-            case COL_PLAIN:
-                if (dir < 0) cols_fft_one<NN, -1, COL_PLAIN>(g, in, out, table, scale, batch, st);
-                else cols_fft_one<NN, 1, COL_PLAIN>(g, in, out, table, scale, batch, st);
-                break;
-            case COL_MUL_CPX_INV: cols_fft_one<NN, -1, COL_MUL_CPX_INV>(g, in, out, table, scale, batch, st); break;
-            case COL_MUL_REAL_INV: cols_fft_one<NN, -1, COL_MUL_REAL_INV>(g, in, out, table, scale, batch, st); break;
-            case COL_DP_ACCUM: cols_fft_one<NN, -1, COL_DP_ACCUM>(g, in, out, table, scale, batch, st); break;
-        }
-    });
-}
-
-// =============================================================================================
-// STEM: shifted probes from the spectrum of the centred probe, and annular detectors
-// =============================================================================================
-// Psi_b(kx, y) = (1/N) IFFT_col[ PSI0(kx, ky) * exp(-2 pi i (iw(kx) sx_b + iw(ky) sy_b)) ], band
-// columns only; PSI0 = FFT_col of the centred, normalised probe in the (kx, y) domain.  shifts:
-// [batch][2] = probe position / (N * pixel size), i.e. in units of the grid period.
-template <int N>
-__global__ void __launch_bounds__(ColCfg<N>::THREADS, ColCfg<N>::MIN_CTAS)
-k_probe_cols(cpx* __restrict__ Psi, const cpx* __restrict__ PSI0, const float* __restrict__ shifts,
-             int lo_end, int hi_start, const cpx* __restrict__ tw)
-{
-    using C = ColCfg<N>;
-    extern __shared__ cpx smem[];
-    constexpr int E = C::E;
-    const ColCtx<N> ctx(smem);
-    const int theta = ctx.theta;
-    const int kx0 = band_col0(blockIdx.x * C::CW, lo_end, hi_start), kx = kx0 + ctx.line;
-    const float sx = shifts[2 * blockIdx.y], sy = shifts[2 * blockIdx.y + 1];
-    cpx x[E];
-    ctx.load(x, PSI0 + kx0, KeepAll());
-    const int i1 = kx > N / 2 ? kx - N : kx;
-    const float ax = (float)i1 * sx;
-    const float inv = 1.f / (float)N;
-#pragma unroll
-    for (int m = 0; m < E; m++) {
-        const int ky = theta + m * C::T;
-        const int i2 = ky > N / 2 ? ky - N : ky;
-        float t = ax + (float)i2 * sy;      // phase in turns
-        t -= rintf(t);
-        float sn, cs;
-        sincos_compact(-6.283185307179586f * t, sn, cs);
-        x[m] = cmul(x[m], make_float2(cs * inv, sn * inv));
-    }
-    fft_line<N, E, 1>(x, ctx.sm, theta, tw, ctx);
-    ctx.store(x, Psi + (size_t)blockIdx.y * N * N + kx0);
-}
-
-void launch_probe_cols(const SweepGeom& g, cpx* Psi, const cpx* PSI0, const float* shifts, int batch,
-                       cudaStream_t st)
-{
-    FDES_DISPATCH_N(g.N, {
-        using C = ColCfg<NN>;
-        static bool once = false;
-        if (!once) { allow_smem(k_probe_cols<NN>, C::SMEM); once = true; }
-        dim3 grid(band_cols(g) / C::CW, batch);
-        k_probe_cols<NN><<<grid, C::THREADS, C::SMEM, st>>>(Psi, PSI0, shifts, g.lo_end, g.hi_start, g.tw);
-    });
-}
-
-// partial[b][tile][d] = sum over the tile's columns and all ky of |FFT_col(Psi_b)|^2 inside the
-// annulus k_in^2 <= |k|^2 < k_out^2 of detector d (|FFT2 psi|^2 / N^2 with Psi = FFT_row(psi)/N,
-// the normalisation of diffractionPattern, src/crystalMaker.cu:714-717).  Fixed reduction order.
-template <int N>
-__global__ void __launch_bounds__(ColCfg<N>::THREADS, ColCfg<N>::MIN_CTAS)
-k_detector_cols(const cpx* __restrict__ Psi, float* __restrict__ partial, DetectorRings rings, float inv_l1,
-                float inv_l2, int lo_end, int hi_start, const cpx* __restrict__ tw)
-{
-    using C = ColCfg<N>;
-    extern __shared__ cpx smem[];
-    constexpr int E = C::E;
-    const ColCtx<N> ctx(smem);
-    const int theta = ctx.theta;
-    const int kx0 = band_col0(blockIdx.x * C::CW, lo_end, hi_start), kx = kx0 + ctx.line;
-    cpx x[E];
-    ctx.load(x, Psi + (size_t)blockIdx.y * N * N + kx0, KeepAll());
-    fft_line<N, E, -1>(x, ctx.sm, theta, tw, ctx);
-    const int i1 = kx > N / 2 ? kx - N : kx;
-    const float k1 = (float)i1 * inv_l1;
-    float acc[MAX_DETECTORS];
-#pragma unroll
-    for (int d = 0; d < MAX_DETECTORS; d++) acc[d] = 0.f;
-#pragma unroll
-    for (int m = 0; m < E; m++) {
-        const int ky = theta + m * C::T;
-        const int i2 = ky > N / 2 ? ky - N : ky;
-        const float k2v = (float)i2 * inv_l2;
-        const float ksq = k1 * k1 + k2v * k2v;
-        const float v = x[m].x * x[m].x + x[m].y * x[m].y;
-#pragma unroll
-        for (int d = 0; d < MAX_DETECTORS; d++)
-            if (d < rings.n && ksq >= rings.in2[d] && ksq < rings.out2[d]) acc[d] += v;
-    }
-    // deterministic CTA reduction: thread order within shared memory, then a serial sum
-    __syncthreads();
-    float* red = reinterpret_cast<float*>(smem);
-    for (int d = 0; d < rings.n; d++) {
-        red[threadIdx.x] = acc[d];
-        __syncthreads();
-        for (int s = C::THREADS / 2; s > 0; s >>= 1) {
-            if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * MAX_DETECTORS + d] = red[0];
-        __syncthreads();
-    }
-}
-
-// out[b][d] += weight * sum_tiles partial[b][tile][d]
-__global__ void k_detector_finish(const float* __restrict__ partial, float* __restrict__ out, int ntiles, int ndet,
-                                  int batch, float weight)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= batch * ndet) return;
-    const int b = i / ndet, d = i % ndet;
-    float s = 0.f;
-    for (int t = 0; t < ntiles; t++) s += partial[((size_t)b * ntiles + t) * MAX_DETECTORS + d];
-    out[(size_t)b * ndet + d] += weight * s;
-}
-
-int detector_tiles(const SweepGeom& g)
-{
-    FDES_DISPATCH_N(g.N, { return band_cols(g) / ColCfg<NN>::CW; });
-    return 0;
-}
-
+int detector_tiles(const SweepGeom& g) { return vt(g.N).detector_tiles(g); }
 void launch_detector_cols(const SweepGeom& g, const cpx* Psi, float* partial, float* out, const DetectorRings& rings,
                           float d1, float d2, float weight, int batch, cudaStream_t st)
 {
-    FDES_DISPATCH_N(g.N, {
-        using C = ColCfg<NN>;
-        static bool once = false;
-        if (!once) { allow_smem(k_detector_cols<NN>, C::SMEM); once = true; }
-        const int tiles = band_cols(g) / C::CW;
-        dim3 grid(tiles, batch);
-        k_detector_cols<NN><<<grid, C::THREADS, C::SMEM, st>>>(Psi, partial, rings, 1.f / ((float)NN * d1),
-                                                              1.f / ((float)NN * d2), g.lo_end, g.hi_start, g.tw);
-        const int n = batch * rings.n;
-        k_detector_finish<<<(n + 127) / 128, 128, 0, st>>>(partial, out, tiles, rings.n, batch, weight);
-    });
-}
-
-// ---------------------------------------------------------------------------------------------
-// twiddle tables (layout: fft_core.cuh) and geometry queries
-// ---------------------------------------------------------------------------------------------
-template <int N>
-static std::vector<cpx> make_twiddles_n()
-{
-    constexpr int E = LineCfg<N>::E;
-    std::vector<cpx> tw;
-    int NS = 1;
-    while (NS < N) {
-        const int rem = N / NS, R = pass_radix(rem, E);
-        if (NS > 1)
-            for (int t = 0; t < R; t++)
-                for (int k = 0; k < NS; k++) {
-                    // exp(-2 pi i t k / (NS R)), exact on the axes
-                    const long long num = (long long)t * k, den = (long long)NS * R;
-                    const long long r = num % den;
-                    cpx w;
-                    if (r == 0) w = make_float2(1.f, 0.f);
-                    else if (4 * r == den) w = make_float2(0.f, -1.f);
-                    else if (2 * r == den) w = make_float2(-1.f, 0.f);
-                    else if (4 * r == 3 * den) w = make_float2(0.f, 1.f);
-                    else {
-                        const double a = -2.0 * 3.14159265358979323846 * (double)r / (double)den;
-                        w = make_float2((float)cos(a), (float)sin(a));
-                    }
-                    tw.push_back(w);
-                }
-        NS *= R;
-    }
-    if ((int)tw.size() != twiddle_table_elems<N, E>()) { fprintf(stderr, "fdes_b200: twiddle table size mismatch\n"); abort(); }
-    if (tw.empty()) tw.push_back(make_float2(1.f, 0.f));
-    return tw;
-}
-std::vector<cpx> make_twiddles(int N)
-{
-    FDES_DISPATCH_N(N, { return make_twiddles_n<NN>(); });
-    return {};
-}
-int rows_per_block(int N)
-{
-    FDES_DISPATCH_N(N, { return RowCfg<NN>::RPB; });
-    return 0;
-}
-int cols_per_block(int N)
-{
-    FDES_DISPATCH_N(N, { return ColCfg<NN>::CW; });
-    return 0;
+    vt(g.N).detector_cols(g, Psi, partial, out, rings, d1, d2, weight, batch, st);
 }
 
 }  // namespace fdes
