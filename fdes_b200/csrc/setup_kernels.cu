@@ -18,7 +18,8 @@ __global__ void k_scattering_table(float* __restrict__ Gq, int N, KirklandRow kr
     const int Q = N / 2 + 1;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Q * Q) return;
-    const int i1 = i % Q, i2 = i / Q;
+    // stored [|kx|][|ky|] (ky fastest): a column sweep's warp reads consecutive ky of ONE kx
+    const int i2 = i % Q, i1 = i / Q;
     const int m1 = N, m2 = N;
     const float d1 = 1e10f * d1m;
     const float d2 = 1e10f * d2m;
@@ -55,7 +56,7 @@ __global__ void k_propagator_table(cpx* __restrict__ Pq, int N, float d1, float 
     const int Q = N / 2 + 1;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Q * Q) return;
-    const int i1 = i % Q, i2 = i / Q;
+    const int i2 = i % Q, i1 = i / Q;    // stored [|kx|][|ky|], ky fastest (see k_scattering_table)
     const int dim1 = N, dim2 = N;
     float d3 = d3in;
     const float t1 = ((float)(i1) / ((float)dim1)) * (d3 / d1);

@@ -16,6 +16,7 @@
 // stored, loaded nor transformed by S3..S6.
 #pragma once
 #include "fft_core.cuh"
+#include "col_pipe.cuh"
 #include "kernels.cuh"
 #include "sweep_vtable.h"
 #include <atomic>
@@ -121,16 +122,17 @@ struct ColCfg {
 
 template <int N>
 using ColCtx = ColTile<N, LineCfg<N>::E, ColCfg<N>::CW, ColCfg<N>::STAGED>;
-// Multiply x[m] (ky = theta + m*T) by the quarter table tab[min(ky, N - ky) * Q + ax]: the first
-// half of the points sits at base_lo + m*T*Q, the second at base_hi + (N - m*T)*Q with
-// base_lo = tab + ax + theta*Q and base_hi = tab + ax - theta*Q -- compile-time offsets.
+// Multiply x[m] (ky = theta + m*T) by the quarter table tab[ax * Q + min(ky, N - ky)] (|kx| slowest,
+// |ky| fastest: the T threads of a column read consecutive entries): the first half of the points
+// sits at lo + m*T, the second at hi + (N - m*T) with lo = tab + ax*Q + theta and
+// hi = tab + ax*Q - theta -- compile-time offsets.
 template <int N, int E, int M, class TabT, class F>
 __device__ __forceinline__ void quarter_table_apply(cpx (&x)[E], const TabT* lo, const TabT* hi, F f)
 {
-    constexpr int T = N / E, Q = N / 2 + 1;
+    constexpr int T = N / E;
     if constexpr (M < E) {
-        if constexpr (M < E / 2) x[M] = f(x[M], ld_nc_at<M * T * Q>(lo));
-        else x[M] = f(x[M], ld_nc_at<(N - M * T) * Q>(hi));
+        if constexpr (M < E / 2) x[M] = f(x[M], ld_nc_at<M * T>(lo));
+        else x[M] = f(x[M], ld_nc_at<N - M * T>(hi));
         quarter_table_apply<N, E, M + 1>(x, lo, hi, f);
     }
 }
@@ -148,6 +150,31 @@ __device__ __forceinline__ int band_col0(int tile_col, int lo_end, int hi_start)
 static int band_cols(const SweepGeom& g)
 {
     return g.lo_end >= g.hi_start ? g.N : g.lo_end + (g.N - g.hi_start);
+}
+
+// The pipelined form (col_pipe.cuh): persistent CTAs, tiles fed by TMA.  Tile t covers the band
+// columns [CW * (t % tiles_x), +CW) of image t / tiles_x; consecutive CTAs work on adjacent tiles.
+template <int N>
+constexpr bool pipe_supported() { return N == 512 || N == 1024; }
+// (N = 2048, 4096: tile rows are 32 / 16 bytes; the TMA store then becomes row-rate bound -- measured
+// with tools/microbench/col_bench.cu -- and the register-staged kernels are as fast)
+// FDES_B200_NO_TMA=1 selects the register-staged column kernels (A/B comparisons)
+static bool pipe_enabled()
+{
+    static const bool on = [] { const char* e = getenv("FDES_B200_NO_TMA"); return !(e && e[0] == '1'); }();
+    return on;
+}
+static int pipe_grid(int ntiles)
+{
+    static std::atomic<int> sms[64];
+    int dev = 0;
+    FDES_CUDA_CHECK(cudaGetDevice(&dev));
+    int n = sms[dev & 63].load();
+    if (n == 0) {
+        FDES_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        sms[dev & 63].store(n);
+    }
+    return ntiles < n ? ntiles : n;     // one persistent CTA per SM
 }
 
 // The reference multiplies complex fields with a 3-multiplication form (multiplyElementwise,
@@ -254,9 +281,9 @@ k_potential_cols(cpx* __restrict__ B, const cpx* __restrict__ A, const float* __
         ctx.load(x, Az, [rp, rp2](int y) { return (rp[y + 1] > rp[y]) | (rp2[y + 1] > rp2[y]); }, any);
         any = true;
         fft_line<N, E, -1>(x, ctx.sm, theta, tw, ctx);
-        const float* G = Gq + (size_t)z * Q * Q + ax;
+        const float* G = Gq + (size_t)z * Q * Q + (size_t)ax * Q;
         // acc += x * G  (tmp holds x * G; the accumulate stays a separate packed add)
-        quarter_table_apply<N, E, 0>(x, G + theta * Q, G - theta * Q,
+        quarter_table_apply<N, E, 0>(x, G + theta, G - theta,
                                      [](cpx v, float gz) { return pmul(v, make_float2(gz, gz)); });
 #pragma unroll
         for (int m = 0; m < E; m++) acc[m] = padd(acc[m], x[m]);
@@ -265,11 +292,92 @@ k_potential_cols(cpx* __restrict__ B, const cpx* __restrict__ A, const float* __
     ctx.store(acc, B + (size_t)b * N * N + kx0);
 }
 
+// Pipelined form: work items are (tile, species) pairs in the order the accumulation visits them;
+// species absent from both slices of the pair are skipped (CTA-uniform test on the row pointers).
+template <int N>
+__global__ void __launch_bounds__(PipeCfg<N>::THREADS, 1)
+k_potential_cols_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                     const float* __restrict__ Gq, const int* __restrict__ rowptr, int slice, int slice2, int nZ,
+                     size_t rp_stride, int tiles_x, int ntiles, const cpx* __restrict__ tw)
+{
+    using C = PipeCfg<N>;
+    extern __shared__ unsigned char pipe_smem[];
+    constexpr int Q = N / 2 + 1;
+    constexpr int E = C::E;
+    ColPipe<N> pipe(pipe_smem);
+    const int theta = pipe.theta;
+    auto rows_of = [=](int b, int z, int sl) { return rowptr + (size_t)b * rp_stride + (size_t)(sl * nZ + z) * N; };
+    auto present = [=](int b, int z) {
+        const int* rp = rows_of(b, z, slice);
+        const int* rp2 = slice2 >= 0 ? rows_of(b, z, slice2) : rp;
+        return rp[N] != rp[0] || rp2[N] != rp2[0];
+    };
+    // first present species at or after (t, z), walking this CTA's tiles; t >= ntiles: none left
+    auto seek = [=](int& t, int& z) {
+        while (t < ntiles) {
+            for (; z < nZ; z++)
+                if (present(t / tiles_x, z)) return;
+            t += gridDim.x; z = 0;
+        }
+    };
+    int t = blockIdx.x;
+    if (t >= ntiles) return;
+    int lt = t, lz = 0;                       // next item to load
+    seek(lt, lz);
+    if (threadIdx.x == 0) {
+        prefetch_tensormap(&mapA); prefetch_tensormap(&mapB);
+        if (lt < ntiles) pipe.issue_load(&mapA, (lt % tiles_x) * C::CW, (lt / tiles_x) * nZ + lz);
+    }
+    for (; t < ntiles; t += gridDim.x) {
+        const int kx0 = (t % tiles_x) * C::CW, kx = kx0 + pipe.line, b = t / tiles_x;
+        const int ax = min(kx, N - kx);
+        cpx acc[E];
+#pragma unroll
+        for (int m = 0; m < E; m++) acc[m] = make_float2(0.f, 0.f);
+        bool any = false;
+        while (lt == t) {                      // the landed (or landing) tile belongs to this output tile
+            const int z = lz;
+            const int* rp = rows_of(b, z, slice);
+            const int* rp2 = slice2 >= 0 ? rows_of(b, z, slice2) : rp;
+            lz++;
+            seek(lt, lz);
+            cpx x[E];
+            // rows without deposits were not written by S1: read them as zero
+            pipe.acquire(x, lt < ntiles, &mapA, (lt % tiles_x) * C::CW, (lt / tiles_x) * nZ + lz,
+                         [rp, rp2](int y) { return (rp[y + 1] > rp[y]) | (rp2[y + 1] > rp2[y]); });
+            any = true;
+            fft_line<N, E, -1>(x, pipe.sm(), theta, tw, pipe.sync());
+            const float* G = Gq + (size_t)z * Q * Q + (size_t)ax * Q;
+            quarter_table_apply<N, E, 0>(x, G + theta, G - theta,
+                                         [](cpx v, float gz) { return pmul(v, make_float2(gz, gz)); });
+#pragma unroll
+            for (int m = 0; m < E; m++) acc[m] = padd(acc[m], x[m]);
+        }
+        pipe.publish_store_drained();
+        if (any) fft_line<N, E, 1>(acc, pipe.sm(), theta, tw, pipe.sync());
+        pipe.release(acc, &mapB, kx0, b);
+    }
+    pipe.finish();
+}
+
 template <int NN>
 void launch_potential_cols_n(const SweepGeom& g, cpx* B, const cpx* A, const float* Gq,
                            const int* rowptr, int slice, int slice2, int nZ, int batch, size_t rowptr_stride,
                            cudaStream_t st)
 {
+    if constexpr (pipe_supported<NN>()) {
+        if (pipe_enabled()) {
+            using P = PipeCfg<NN>;
+            FDES_ALLOW_SMEM((k_potential_cols_tma<NN>), P::SMEM);
+            const int tiles_x = NN / P::CW, ntiles = tiles_x * batch;
+            const CUtensorMap* mapA = tile_map(A, NN, batch * nZ, P::CW, P::BR);
+            const CUtensorMap* mapB = tile_map(B, NN, batch, P::CW, P::BR);
+            k_potential_cols_tma<NN><<<pipe_grid(ntiles), P::THREADS, P::SMEM, st>>>(*mapA, *mapB, Gq, rowptr, slice, slice2,
+                                                                                  nZ, rowptr_stride, tiles_x, ntiles, g.tw);
+            FDES_LAUNCH_CHECK();
+            return;
+        }
+    }
     using C = ColCfg<NN>;
     FDES_ALLOW_SMEM((k_potential_cols<NN>), C::SMEM);
     dim3 grid(NN / C::CW, batch);
@@ -408,9 +516,63 @@ k_bandlimit_cols(cpx* __restrict__ W, int npair, int lo_end, int hi_start, const
     ctx.store(x, tile);
 }
 
+template <int N>
+__global__ void __launch_bounds__(PipeCfg<N>::THREADS, 1)
+k_bandlimit_cols_tma(const __grid_constant__ CUtensorMap map, int npair, int lo_end, int hi_start, int tiles_x,
+                     int ntiles, const cpx* __restrict__ tw)
+{
+    using C = PipeCfg<N>;
+    extern __shared__ unsigned char pipe_smem[];
+    constexpr int E = C::E;
+    ColPipe<N> pipe(pipe_smem);
+    const int theta = pipe.theta;
+    // image y of the tile list -> entry (b, p) of a [batch][2] stack (npair = 0: plain [batch])
+    auto entry = [npair](int y) { return npair == 0 ? y : (y / npair) * 2 + y % npair; };
+    int t = blockIdx.x;
+    if (t >= ntiles) return;
+    if (threadIdx.x == 0) {
+        prefetch_tensormap(&map);
+        pipe.issue_load(&map, band_col0((t % tiles_x) * C::CW, lo_end, hi_start), entry(t / tiles_x));
+    }
+    const float mind = (float)N;
+    const float alpha = 1.f / ((float)(N * N));
+    for (; t < ntiles; t += gridDim.x) {
+        const int kx0 = band_col0((t % tiles_x) * C::CW, lo_end, hi_start), kx = kx0 + pipe.line;
+        const int tn = t + gridDim.x;
+        cpx x[E];
+        pipe.acquire(x, tn < ntiles, &map, band_col0((tn % tiles_x) * C::CW, lo_end, hi_start), entry(tn / tiles_x));
+        fft_line<N, E, -1>(x, pipe.sm(), theta, tw, pipe.sync());
+        pipe.publish_store_drained();
+        const int i1 = kx > N / 2 ? kx - N : kx;
+#pragma unroll
+        for (int m = 0; m < E; m++) {
+            const int ky = theta + m * C::T;
+            const int i2 = ky > N / 2 ? ky - N : ky;
+            const bool cut = ((float)(i1 * i1 + i2 * i2) * 9.f / (mind * mind)) > 1.f;
+            x[m] = cut ? make_float2(0.f, 0.f) : make_float2(x[m].x * alpha, x[m].y * alpha);
+        }
+        fft_line<N, E, 1>(x, pipe.sm(), theta, tw, pipe.sync());
+        pipe.release(x, &map, kx0, entry(t / tiles_x));
+    }
+    pipe.finish();
+}
+
 template <int NN>
 void launch_bandlimit_cols_n(const SweepGeom& g, cpx* W, int batch, int npair, cudaStream_t st)
 {
+    if constexpr (pipe_supported<NN>()) {
+        if (pipe_enabled()) {
+            using P = PipeCfg<NN>;
+            FDES_ALLOW_SMEM((k_bandlimit_cols_tma<NN>), P::SMEM);
+            const int nimg = npair == 0 ? batch : 2 * batch;     // images in the stack
+            const int tiles_x = band_cols(g) / P::CW, ntiles = tiles_x * (npair == 0 ? batch : batch * npair);
+            const CUtensorMap* map = tile_map(W, NN, nimg, P::CW, P::BR);
+            k_bandlimit_cols_tma<NN><<<pipe_grid(ntiles), P::THREADS, P::SMEM, st>>>(*map, npair, g.lo_end, g.hi_start,
+                                                                                  tiles_x, ntiles, g.tw);
+            FDES_LAUNCH_CHECK();
+            return;
+        }
+    }
     using C = ColCfg<NN>;
     FDES_ALLOW_SMEM((k_bandlimit_cols<NN>), C::SMEM);
     dim3 grid(band_cols(g) / C::CW, npair == 0 ? batch : batch * npair);
@@ -495,15 +657,59 @@ k_propagate_cols(cpx* __restrict__ Psi, const cpx* __restrict__ Pq, int lo_end, 
     cpx x[E];
     ctx.load(x, tile, KeepAll());
     fft_line<N, E, -1>(x, ctx.sm, theta, tw, ctx);
-    const cpx* P = Pq + min(kx, N - kx);
-    quarter_table_apply<N, E, 0>(x, P + theta * Q, P - theta * Q, [](cpx v, cpx p) { return cmul(v, p); });
+    const cpx* P = Pq + (size_t)min(kx, N - kx) * Q;
+    quarter_table_apply<N, E, 0>(x, P + theta, P - theta, [](cpx v, cpx p) { return cmul(v, p); });
     fft_line<N, E, 1>(x, ctx.sm, theta, tw, ctx);
     ctx.store(x, tile);
+}
+
+template <int N>
+__global__ void __launch_bounds__(PipeCfg<N>::THREADS, 1)
+k_propagate_cols_tma(const __grid_constant__ CUtensorMap map, const cpx* __restrict__ Pq, int lo_end, int hi_start,
+                     int tiles_x, int ntiles, const cpx* __restrict__ tw)
+{
+    using C = PipeCfg<N>;
+    extern __shared__ unsigned char pipe_smem[];
+    constexpr int Q = N / 2 + 1;
+    constexpr int E = C::E;
+    ColPipe<N> pipe(pipe_smem);
+    const int theta = pipe.theta;
+    int t = blockIdx.x;
+    if (t >= ntiles) return;
+    if (threadIdx.x == 0) {
+        prefetch_tensormap(&map);
+        pipe.issue_load(&map, band_col0((t % tiles_x) * C::CW, lo_end, hi_start), t / tiles_x);
+    }
+    for (; t < ntiles; t += gridDim.x) {
+        const int kx0 = band_col0((t % tiles_x) * C::CW, lo_end, hi_start), kx = kx0 + pipe.line;
+        const int tn = t + gridDim.x;
+        cpx x[E];
+        pipe.acquire(x, tn < ntiles, &map, band_col0((tn % tiles_x) * C::CW, lo_end, hi_start), tn / tiles_x);
+        fft_line<N, E, -1>(x, pipe.sm(), theta, tw, pipe.sync());
+        pipe.publish_store_drained();
+        const cpx* P = Pq + (size_t)min(kx, N - kx) * Q;
+        quarter_table_apply<N, E, 0>(x, P + theta, P - theta, [](cpx v, cpx p) { return cmul(v, p); });
+        fft_line<N, E, 1>(x, pipe.sm(), theta, tw, pipe.sync());
+        pipe.release(x, &map, kx0, t / tiles_x);
+    }
+    pipe.finish();
 }
 
 template <int NN>
 void launch_propagate_cols_n(const SweepGeom& g, cpx* Psi, const cpx* Pq, int batch, cudaStream_t st)
 {
+    if constexpr (pipe_supported<NN>()) {
+        if (pipe_enabled()) {
+            using P = PipeCfg<NN>;
+            FDES_ALLOW_SMEM((k_propagate_cols_tma<NN>), P::SMEM);
+            const int tiles_x = band_cols(g) / P::CW, ntiles = tiles_x * batch;
+            const CUtensorMap* map = tile_map(Psi, NN, batch, P::CW, P::BR);
+            k_propagate_cols_tma<NN><<<pipe_grid(ntiles), P::THREADS, P::SMEM, st>>>(*map, Pq, g.lo_end, g.hi_start,
+                                                                                  tiles_x, ntiles, g.tw);
+            FDES_LAUNCH_CHECK();
+            return;
+        }
+    }
     using C = ColCfg<NN>;
     FDES_ALLOW_SMEM((k_propagate_cols<NN>), C::SMEM);
     dim3 grid(band_cols(g) / C::CW, batch);

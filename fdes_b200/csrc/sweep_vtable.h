@@ -9,7 +9,13 @@
 // fft_core.cuh): powers of two and the 2^a 5^b sizes of the reference's shipped examples
 #define FDES_SWEEP_SIZES(X) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(320) X(800) X(1000)
 
+struct CUtensorMap_st;   // <cuda.h>
+
 namespace fdes {
+
+// TMA descriptor (cached per device / array / geometry) of an [nimg][N][N] complex64 array with
+// boxes of [BR rows][CW columns] -- the column tiles of col_pipe.cuh (tma_map.cu)
+const CUtensorMap_st* tile_map(const void* base, int N, int nimg, int CW, int BR);
 
 struct SweepVTable {
     int N, rows_per_block, cols_per_block;
