@@ -419,10 +419,59 @@ __device__ __forceinline__ void sincos_compact(float x, float& sn, float& cs)
     sn = (k & 2) ? -a : a;
     cs = ((k + 1) & 2) ? -b : b;
 }
+// 2/3 band limit of a grid of size N, known at compile time: kb = largest |i1| that zeroHighFreq's
+// float test keeps on the axis (src/multisliceSimulation.cu:225-250), bounds rounded outwards to
+// multiples of 32 exactly as Engine::setup_tables does for SweepGeom (the launchers check that
+// the two agree).  With constant bounds the per-element band tests of the unrolled row loops fold
+// away (lo_end and hi_start are multiples of the thread count T of a line for N <= 2048).
 template <int N>
-__device__ __forceinline__ cpx transmission(float V, float imPot)
+struct Band {
+    static constexpr int kb_of()
+    {
+        int kb = 0;
+        const float mind = (float)N;
+        while (kb + 1 <= N / 2 && !(((float)((kb + 1) * (kb + 1)) * 9.f / (mind * mind)) > 1.f)) kb++;
+        return kb;
+    }
+    static constexpr int kb = kb_of();
+    static constexpr int lo0 = ((kb + 1 + 31) / 32) * 32, hi0 = ((N - kb) / 32) * 32;
+    static constexpr int lo_end = lo0 >= hi0 ? N : lo0, hi_start = lo0 >= hi0 ? N : hi0;
+    static void check(const SweepGeom& g)
+    {
+        if (g.lo_end != lo_end || g.hi_start != hi_start)
+            throw std::runtime_error("band limits of the sweep geometry differ from the compiled ones");
+    }
+};
+
+// (cos V, sin V) = exp(iV) with packed arithmetic: Cody-Waite reduction to [-pi/4, pi/4] (the
+// quadrant comes out of the mantissa of V * 2/pi + 1.5 * 2^23), the Cephes minimax polynomials of
+// sincos_compact evaluated for the cosine and the sine in the two halves of one f32x2 register,
+// then the rotation by the quadrant.  |V| must be below 1e5 (checked per thread by the caller).
+__device__ __forceinline__ cpx expi_packed(float V)
 {
-    // potential2Transmission, src/multisliceSimulation.cu:41-52, with V.x = V and V.y = imPot * V
+    const float q = fmaf(V, 0.636619772f, 12582912.f);
+    const int k = __float_as_int(q);
+    const float kf = q - 12582912.f;
+    float r = fmaf(kf, -1.57079601e+00f, V);
+    r = fmaf(kf, -3.13916473e-07f, r);
+    r = fmaf(kf, -5.39030253e-15f, r);
+    const cpx rr = pmul(make_float2(r, r), make_float2(r, 1.f));                         // (r^2, r)
+    const cpx r2 = make_float2(rr.x, rr.x);
+    cpx u = pfma(r2, make_float2(2.443315711809948e-5f, -1.9515295891e-4f), make_float2(-1.388731625493765e-3f, 8.3321608736e-3f));
+    u = pfma(u, r2, make_float2(4.166664568298827e-2f, -1.6666654611e-1f));
+    u = pmul(u, r2);
+    const cpx tail = pfma(rr, make_float2(-0.5f, 1.f), make_float2(1.f, 0.f));           // (1 - r^2/2, r)
+    u = pfma(u, rr, tail);                                                              // (cos r, sin r)
+    // rotate by k quarter turns: odd k -> (-sin, cos); k & 2 -> negate
+    const bool odd = (k & 1) != 0;
+    const float c0 = odd ? -u.y : u.x, s0 = odd ? u.x : u.y;
+    const int sgn = (k & 2) << 30;
+    return make_float2(__int_as_float(__float_as_int(c0) ^ sgn), __int_as_float(__float_as_int(s0) ^ sgn));
+}
+// potential2Transmission, src/multisliceSimulation.cu:41-52, with V.x = V and V.y = imPot * V; any
+// argument (one out-of-line copy: only taken for |V| >= 1e5 rad, which no physical slice reaches)
+static __device__ __noinline__ cpx transmission(float V, float imPot)
+{
     float sn, cs;
     sincos_compact(V, sn, cs);
     if (imPot != 0.f) {
@@ -431,14 +480,18 @@ __device__ __forceinline__ cpx transmission(float V, float imPot)
     }
     return make_float2(cs, sn);
 }
+// One copy of the forward line transform serves all three transforms of the sweep: the inverse
+// transform of W is taken as swap(FFT(swap(W))) (real and imaginary parts exchanged on the way in
+// and out), so the kernel's code is a third of the fully unrolled form and stays inside the
+// instruction cache.
 template <int N>
 __global__ void __launch_bounds__(RowCfg<N>::THREADS, RowCfg<N>::MIN_CTAS)
-k_transmit_rows(const cpx* __restrict__ W, cpx* __restrict__ D, int npair, float imPot, int lo_end,
-                int hi_start, const cpx* __restrict__ tw)
+k_transmit_rows(const cpx* __restrict__ W, cpx* __restrict__ D, int npair, float imPot, const cpx* __restrict__ tw)
 {
     using C = RowCfg<N>;
     extern __shared__ cpx smem[];
     constexpr int E = C::E;
+    constexpr int lo_end = Band<N>::lo_end, hi_start = Band<N>::hi_start;
     const int line = threadIdx.x / C::T, theta = threadIdx.x % C::T;
     const RowSync<N> sync(line);
     const size_t row = (size_t)blockIdx.x * C::RPB + line;
@@ -446,26 +499,50 @@ k_transmit_rows(const cpx* __restrict__ W, cpx* __restrict__ D, int npair, float
     cpx* sm = smem + line * C::LSTRIDE;
     float* park = reinterpret_cast<float*>(smem + C::RPB * C::LSTRIDE) + line * (2 * N);   // V_a | V_b
     cpx x[E];
-#pragma unroll
-    for (int m = 0; m < E; m++) x[m] = W[in_off + theta + m * C::T];
-    fft_line<N, E, 1>(x, sm, theta, tw, sync);
-#pragma unroll
-    for (int m = 0; m < E; m++) {
-        park[theta + m * C::T] = x[m].x;
-        park[N + theta + m * C::T] = x[m].y;
-    }
-    // one copy of the exp / forward-transform code for both slices of the pair
 #pragma unroll 1
-    for (int p = 0; p < npair; p++) {
-        const float* V = park + p * N;
+    for (int ph = 0; ph <= npair; ph++) {
+        if (ph == 0) {
 #pragma unroll
-        for (int m = 0; m < E; m++) x[m] = transmission<N>(V[theta + m * C::T], imPot);
+            for (int m = 0; m < E; m++) {
+                const cpx w = W[in_off + theta + m * C::T];
+                x[m] = make_float2(w.y, w.x);
+            }
+        } else {
+            // t0 = exp(i V (1 + i imPot)) of slice ph - 1 of the pair
+            const float* V = park + (ph - 1) * N;
+            float amax = 0.f;
+#pragma unroll
+            for (int m = 0; m < E; m++) amax = fmaxf(amax, fabsf(V[theta + m * C::T]));
+            if (amax < 1.0e5f) {
+#pragma unroll
+                for (int m = 0; m < E; m++) {
+                    const float v = V[theta + m * C::T];
+                    x[m] = expi_packed(v);
+                    if (imPot != 0.f) {
+                        const float e = __expf(-(v * imPot));
+                        x[m] = make_float2(e * x[m].x, e * x[m].y);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < E; m++) x[m] = transmission(V[theta + m * C::T], imPot);
+            }
+        }
         fft_line<N, E, -1>(x, sm, theta, tw, sync);
-        cpx* out = D + ((size_t)(blockIdx.y * 2 + p) * N + row) * N;
+        if (ph == 0) {
+            // IFFT_row(W) = swap(x) = V_a + i V_b
 #pragma unroll
-        for (int m = 0; m < E; m++) {
-            const int kx = theta + m * C::T;
-            if (in_band(kx, lo_end, hi_start)) out[kx] = x[m];
+            for (int m = 0; m < E; m++) {
+                park[theta + m * C::T] = x[m].y;
+                park[N + theta + m * C::T] = x[m].x;
+            }
+        } else {
+            cpx* out = D + ((size_t)(blockIdx.y * 2 + (ph - 1)) * N + row) * N;
+#pragma unroll
+            for (int m = 0; m < E; m++) {
+                const int kx = theta + m * C::T;
+                if (in_band(kx, lo_end, hi_start)) out[kx] = x[m];
+            }
         }
     }
 }
@@ -478,7 +555,8 @@ void launch_transmit_rows_n(const SweepGeom& g, const cpx* W, cpx* D, int npair,
     const size_t smem = C::SMEM + (size_t)C::RPB * NN * 2 * sizeof(float);
     FDES_ALLOW_SMEM((k_transmit_rows<NN>), smem);
     dim3 grid(NN / C::RPB, batch);
-    k_transmit_rows<NN><<<grid, C::THREADS, smem, st>>>(W, D, npair, imPot, g.lo_end, g.hi_start, g.tw);
+    Band<NN>::check(g);
+    k_transmit_rows<NN><<<grid, C::THREADS, smem, st>>>(W, D, npair, imPot, g.tw);
     FDES_LAUNCH_CHECK();
 }
 
@@ -583,45 +661,68 @@ void launch_bandlimit_cols_n(const SweepGeom& g, cpx* W, int batch, int npair, c
 // =============================================================================================
 // S5  multiply rows
 // =============================================================================================
+// The three transforms (two inverse, one forward) run through ONE copy of the forward transform:
+// an inverse transform is swap(FFT(swap(.))), real and imaginary parts exchanged on the way in and
+// out (see k_transmit_rows).
 template <int N>
 __global__ void __launch_bounds__(RowCfg<N>::THREADS, RowCfg<N>::MIN_CTAS)
-k_multiply_rows(cpx* __restrict__ Psi, const cpx* __restrict__ Tk, size_t e_batch_stride,
-                int lo_end, int hi_start, int psi_full, const cpx* __restrict__ tw)
+k_multiply_rows(cpx* __restrict__ Psi, const cpx* __restrict__ Tk, size_t e_batch_stride, int psi_full,
+                const cpx* __restrict__ tw)
 {
     using C = RowCfg<N>;
     extern __shared__ cpx smem[];
     constexpr int E = C::E;
+    constexpr int lo_end = Band<N>::lo_end, hi_start = Band<N>::hi_start;
     const int line = threadIdx.x / C::T, theta = threadIdx.x % C::T;
     const RowSync<N> sync(line);
     const size_t row = (size_t)blockIdx.x * C::RPB + line;
     const cpx* e = Tk + (size_t)blockIdx.y * e_batch_stride + row * N;
     cpx* p = Psi + ((size_t)blockIdx.y * N + row) * N;
     cpx* sm = smem + line * C::LSTRIDE;
-    // t = IFFT_row(Tk) is parked in shared memory while psi is transformed (two register sets of
-    // E points each would not fit)
+    // swap(t) = FFT(swap(Tk)) is parked in shared memory while psi is transformed (two register
+    // sets of E points each would not fit)
     cpx* park = smem + C::RPB * C::LSTRIDE + line * N;
     cpx x[E];
+#pragma unroll 1
+    for (int ph = 0; ph < 3; ph++) {
+        if (ph == 0) {
 #pragma unroll
-    for (int m = 0; m < E; m++) {
-        const int kx = theta + m * C::T;
-        x[m] = in_band(kx, lo_end, hi_start) ? e[kx] : make_float2(0.f, 0.f);
-    }
-    fft_line<N, E, 1>(x, sm, theta, tw, sync);
+            for (int m = 0; m < E; m++) {
+                const int kx = theta + m * C::T;
+                const cpx v = in_band(kx, lo_end, hi_start) ? e[kx] : make_float2(0.f, 0.f);
+                x[m] = make_float2(v.y, v.x);
+            }
+        } else if (ph == 1) {
+            if (psi_full) {
 #pragma unroll
-    for (int m = 0; m < E; m++) park[theta + m * C::T] = x[m];
+                for (int m = 0; m < E; m++) { const cpx v = ld_g(p + theta + m * C::T); x[m] = make_float2(v.y, v.x); }
+            } else {
 #pragma unroll
-    for (int m = 0; m < E; m++) {
-        const int kx = theta + m * C::T;
-        x[m] = (in_band(kx, lo_end, hi_start) || psi_full) ? ld_g(p + kx) : make_float2(0.f, 0.f);
-    }
-    fft_line<N, E, 1>(x, sm, theta, tw, sync);
+                for (int m = 0; m < E; m++) {
+                    const int kx = theta + m * C::T;
+                    const cpx v = in_band(kx, lo_end, hi_start) ? ld_g(p + kx) : make_float2(0.f, 0.f);
+                    x[m] = make_float2(v.y, v.x);
+                }
+            }
+        }
+        fft_line<N, E, -1>(x, sm, theta, tw, sync);
+        if (ph == 0) {
 #pragma unroll
-    for (int m = 0; m < E; m++) x[m] = cmul(park[theta + m * C::T], x[m]);
-    fft_line<N, E, -1>(x, sm, theta, tw, sync);
+            for (int m = 0; m < E; m++) park[theta + m * C::T] = x[m];
+        } else if (ph == 1) {
+            // t * psi from the swapped pairs: t = (a.y, a.x), psi = (b.y, b.x)
 #pragma unroll
-    for (int m = 0; m < E; m++) {
-        const int kx = theta + m * C::T;
-        if (in_band(kx, lo_end, hi_start)) p[kx] = x[m];
+            for (int m = 0; m < E; m++) {
+                const cpx a = park[theta + m * C::T], b = x[m];
+                x[m] = cmul(make_float2(a.y, a.x), make_float2(b.y, b.x));
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < E; m++) {
+                const int kx = theta + m * C::T;
+                if (in_band(kx, lo_end, hi_start)) p[kx] = x[m];
+            }
+        }
     }
 }
 
@@ -633,8 +734,8 @@ void launch_multiply_rows_n(const SweepGeom& g, cpx* Psi, const cpx* E, size_t e
     const size_t smem = C::SMEM + (size_t)C::RPB * NN * sizeof(cpx);
     FDES_ALLOW_SMEM((k_multiply_rows<NN>), smem);
     dim3 grid(NN / C::RPB, batch);
-    k_multiply_rows<NN><<<grid, C::THREADS, smem, st>>>(Psi, E, e_batch_stride, g.lo_end,
-                                                          g.hi_start, psi_full ? 1 : 0, g.tw);
+    Band<NN>::check(g);
+    k_multiply_rows<NN><<<grid, C::THREADS, smem, st>>>(Psi, E, e_batch_stride, psi_full ? 1 : 0, g.tw);
     FDES_LAUNCH_CHECK();
 }
 
@@ -1038,9 +1139,12 @@ k_detector_cols(const cpx* __restrict__ Psi, float* __restrict__ partial, Detect
     for (int d = 0; d < rings.n; d++) {
         red[threadIdx.x] = acc[d];
         __syncthreads();
-        for (int s = C::THREADS / 2; s > 0; s >>= 1) {
-            if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        // ceil-halving tree: correct for any thread count (320 and 200 threads at N = 800, 1000)
+        for (int n = C::THREADS; n > 1;) {
+            const int s = (n + 1) / 2;
+            if ((int)threadIdx.x + s < n) red[threadIdx.x] += red[threadIdx.x + s];
             __syncthreads();
+            n = s;
         }
         if (threadIdx.x == 0) partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * MAX_DETECTORS + d] = red[0];
         __syncthreads();
