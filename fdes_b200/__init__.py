@@ -42,6 +42,10 @@ def load_library() -> ctypes.CDLL:
     lib.fdes_b200_open_cnf.restype = vp
     lib.fdes_b200_open_cnf.argtypes = [ctypes.c_char_p, c_f, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.fdes_b200_open_multi.restype = vp
+    lib.fdes_b200_open_multi.argtypes = [ctypes.c_char_p, c_f, ctypes.c_int, c_i, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.fdes_b200_num_gpus.argtypes = [vp]
+    lib.fdes_b200_parse_gpu_list.argtypes = [ctypes.c_char_p, ctypes.c_int, c_i, ctypes.c_int]
     lib.fdes_b200_parse_cnf.argtypes = [ctypes.c_char_p, c_i, c_f, c_f, c_f, ctypes.c_int]
     lib.fdes_b200_write_used_cnf.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
     lib.fdes_b200_write_emd.argtypes = [ctypes.c_char_p, ctypes.c_char_p, c_f, c_f, ctypes.c_int, c_f]
@@ -161,19 +165,36 @@ def write_emd(input_path, emd_path, image=None, potential=None, exitwave=None):
         raise FdesError(lib.fdes_b200_last_error().decode())
 
 
+def parse_gpu_list(spec, first: int = 0):
+    """Device ordinals of an FDES_B200_GPUS / --gpus value ("4" or "0,2,5")."""
+    lib = load_library()
+    enc = None if spec is None else str(spec).encode()
+    n = lib.fdes_b200_parse_gpu_list(enc, first, None, 0)
+    out = np.zeros(max(n, 1), np.int32)
+    lib.fdes_b200_parse_gpu_list(enc, first, _ip(out), len(out))
+    return [int(v) for v in out[:n]]
+
+
 class Simulation:
-    """One .cnf simulation on one GPU (session API of include/fdes_b200.h)."""
+    """One simulation (session API of include/fdes_b200.h) on one GPU, or -- ``gpus=[...]`` -- sharded
+    over several GPUs of this process (fdes_b200_open_multi: frozen-phonon configurations, tilt series
+    or STEM probes dealt out, partial sums reduced onto the first device)."""
 
     def __init__(self, cnf_path, atoms6: Optional[np.ndarray] = None, gpu_index: int = 0, batch: int = 0,
-                 rank: int = 0, world: int = 1, want_exitwave: bool = False):
+                 rank: int = 0, world: int = 1, want_exitwave: bool = False, gpus=None):
         self._lib = load_library()
         self._h = None
         a_ptr, n_at = None, 0
         if atoms6 is not None:
             self._atoms6 = np.ascontiguousarray(atoms6, np.float32).reshape(-1, 6)
             a_ptr, n_at = _fp(self._atoms6), self._atoms6.shape[0]
-        h = self._lib.fdes_b200_open_cnf(str(cnf_path).encode(), a_ptr, n_at, gpu_index, batch, rank, world,
-                                         1 if want_exitwave else 0)
+        if gpus is not None:
+            g = np.ascontiguousarray(list(gpus), np.int32)
+            h = self._lib.fdes_b200_open_multi(str(cnf_path).encode(), a_ptr, n_at, _ip(g), len(g), batch,
+                                               1 if want_exitwave else 0)
+        else:
+            h = self._lib.fdes_b200_open_cnf(str(cnf_path).encode(), a_ptr, n_at, gpu_index, batch, rank, world,
+                                             1 if want_exitwave else 0)
         if not h:
             raise FdesError(self._lib.fdes_b200_last_error().decode())
         self._h = h
@@ -184,6 +205,7 @@ class Simulation:
         self._ck(self._lib.fdes_b200_get_scalars(h, _fp(s)))
         self.lam, self.sigma, self.gamma, self.d1, self.d2, self.d3, self.E0, self.imPot = map(float, s)
         self.want_exitwave = want_exitwave
+        self.num_gpus = int(self._lib.fdes_b200_num_gpus(h))
 
     def _ck(self, rc):
         if rc != 0:

@@ -42,13 +42,13 @@ void launch_rng_init(void* states, int n, unsigned long long seed, cudaStream_t 
 // One launch draws the displacements of `nconf` consecutive configurations: thread i advances its
 // XORWOW stream by one normal per configuration, exactly like nconf successive reference launches.
 __global__ void k_atom_jitter(float* __restrict__ out, const float* __restrict__ in,
-                              const float* __restrict__ dwf, int nAt, curandState* state, int burn,
+                              const float* __restrict__ dwf, int nAt, curandState* state, long long burn,
                               int nconf)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 3 * nAt) return;
     curandState local = state[i];
-    for (int b = 0; b < burn; b++) (void)curand_normal(&local);
+    for (long long b = 0; b < burn; b++) (void)curand_normal(&local);
     const float base = in[i];
     for (int c = 0; c < nconf; c++) {
         float x = curand_normal(&local);
@@ -59,7 +59,7 @@ __global__ void k_atom_jitter(float* __restrict__ out, const float* __restrict__
     state[i] = local;
 }
 void launch_atom_jitter(float* xyz_out, const float* xyz_in, const float* dwf, int nAt,
-                        void* states, int burn, int nconf, cudaStream_t st)
+                        void* states, long long burn, int nconf, cudaStream_t st)
 {
     k_atom_jitter<<<(3 * nAt + 127) / 128, 128, 0, st>>>(xyz_out, xyz_in, dwf, nAt,
                                                         static_cast<curandState*>(states), burn, nconf);

@@ -15,15 +15,42 @@
 #include <string>
 #include <chrono>
 #include <thread>
+#include <exception>
 
 using namespace fdes;
 
+std::vector<int> fdes_b200_gpu_list(const char* spec, int first);
+
+// A session owns one engine per GPU it runs on.  With several GPUs the work of a run is sharded
+// over the engines of this ONE process (one host thread per device while they compute):
+//   SHARD_CONFIGS   frozen-phonon configurations j of every measurement k (src/crystalMaker.cu:332);
+//                   the partial sums are reduced onto the first device (Engine::reduce_from)
+//   SHARD_REPLICAS  every engine holds the whole problem: measurements k (tilt / defocus series,
+//                   src/crystalMaker.cu:324) or STEM probe positions are dealt out, nothing to reduce
+enum { SHARD_NONE = 0, SHARD_CONFIGS = 1, SHARD_REPLICAS = 2 };
 struct fdes_b200_sim {
-    std::unique_ptr<Engine> eng;
+    std::vector<std::unique_ptr<Engine>> engs;
+    Engine* eng = nullptr;   // engs[0]: the engine of single-GPU sessions, the reduction root otherwise
+    int shard = SHARD_NONE;
     Params params;   // as read (before sub-slicing)
     Atoms atoms;
     int m3_orig = 1;
 };
+
+// f(r) for r = 0 .. n-1 on n host threads (r = 0 on the caller's); the first exception is rethrown
+template <class F>
+static void parallel_for(int n, F f)
+{
+    if (n <= 1) { if (n == 1) f(0); return; }
+    std::vector<std::exception_ptr> err(n);
+    std::vector<std::thread> th;
+    th.reserve(n - 1);
+    for (int r = 1; r < n; r++)
+        th.emplace_back([&, r] { try { f(r); } catch (...) { err[r] = std::current_exception(); } });
+    try { f(0); } catch (...) { err[0] = std::current_exception(); }
+    for (auto& t : th) t.join();
+    for (auto& e : err) if (e) std::rethrow_exception(e);
+}
 
 static thread_local std::string g_err;
 
@@ -112,10 +139,8 @@ int fdes_b200_write_emd(const char* input_path, const char* emd_path, const floa
     API_CATCH(-1)
 }
 
-fdes_b200_sim* fdes_b200_open_cnf(const char* cnf_path, const float* atoms6, int numAtoms,
-                                  int gpu_index, int batch, int rank, int world, int want_exitwave)
+static std::unique_ptr<fdes_b200_sim> read_session(const char* cnf_path, const float* atoms6, int numAtoms)
 {
-    API_TRY
     auto sim = std::make_unique<fdes_b200_sim>();
     if (!cnf_path) throw std::runtime_error("cnf_path is NULL");
     if (!read_input(cnf_path, sim->params, &sim->atoms, atoms6 != nullptr))
@@ -126,13 +151,51 @@ fdes_b200_sim* fdes_b200_open_cnf(const char* cnf_path, const float* atoms6, int
     }
     sim->params.nAt = sim->atoms.size();
     sim->m3_orig = sim->params.m3;
+    return sim;
+}
+
+fdes_b200_sim* fdes_b200_open_cnf(const char* cnf_path, const float* atoms6, int numAtoms,
+                                  int gpu_index, int batch, int rank, int world, int want_exitwave)
+{
+    API_TRY
+    auto sim = read_session(cnf_path, atoms6, numAtoms);
     EngineOptions opt;
     opt.gpu_index = gpu_index; opt.batch = batch; opt.rank = rank; opt.world = world;
     opt.want_exitwave = want_exitwave != 0;
-    sim->eng = std::make_unique<Engine>(sim->params, sim->atoms, opt);
+    sim->engs.push_back(std::make_unique<Engine>(sim->params, sim->atoms, opt));
+    sim->eng = sim->engs[0].get();
     return sim.release();
     API_CATCH(nullptr)
 }
+
+fdes_b200_sim* fdes_b200_open_multi(const char* cnf_path, const float* atoms6, int numAtoms,
+                                    const int* gpu_indices, int ngpus, int batch, int want_exitwave)
+{
+    API_TRY
+    if (!gpu_indices || ngpus < 1) throw std::runtime_error("need at least one GPU index");
+    if (ngpus > MAX_PEERS + 1) throw std::runtime_error("at most 16 GPUs per session");
+    auto sim = read_session(cnf_path, atoms6, numAtoms);
+    const Params& p = sim->params;
+    const int count = p.frPh > 0 ? p.frPh : 1;
+    int n = 1;
+    if (ngpus > 1 && count >= 2) { sim->shard = SHARD_CONFIGS; n = std::min(ngpus, count); }
+    else if (ngpus > 1 && (p.n3 >= 2 || p.mode == 2)) { sim->shard = SHARD_REPLICAS; n = ngpus; }
+    sim->engs.resize(n);
+    fdes_b200_sim* raw = sim.get();
+    parallel_for(n, [&](int r) {
+        EngineOptions opt;
+        opt.gpu_index = gpu_indices[r]; opt.batch = batch;
+        opt.rank = raw->shard == SHARD_CONFIGS ? r : 0;
+        opt.world = raw->shard == SHARD_CONFIGS ? n : 1;
+        opt.want_exitwave = want_exitwave != 0;
+        raw->engs[r] = std::make_unique<Engine>(raw->params, raw->atoms, opt);
+    });
+    sim->eng = sim->engs[0].get();
+    return sim.release();
+    API_CATCH(nullptr)
+}
+
+int fdes_b200_num_gpus(const fdes_b200_sim* sim) { return sim ? (int)sim->engs.size() : -1; }
 
 void fdes_b200_close(fdes_b200_sim* sim) { delete sim; }
 
@@ -186,10 +249,32 @@ int fdes_b200_simulate(fdes_b200_sim* sim, float* image_host, float* exitwave_ho
     API_TRY
     const Params& p = sim->eng->params();
     const size_t n12 = (size_t)p.n1 * p.n2, m12 = (size_t)p.m1 * p.m2;
-    for (int k = 0; k < p.n3; k++) {
-        sim->eng->run_k(k);
-        sim->eng->finish_k(k, image_host ? image_host + k * n12 : nullptr,
-                           exitwave_host ? exitwave_host + 2 * k * m12 : nullptr);
+    const int n = (int)sim->engs.size();
+    auto img_k = [&](int k) { return image_host ? image_host + k * n12 : nullptr; };
+    auto ew_k = [&](int k) { return exitwave_host ? exitwave_host + 2 * k * m12 : nullptr; };
+    if (n > 1 && sim->shard == SHARD_CONFIGS) {
+        // every device runs its configurations of measurement k; device 0 adds the partial sums
+        // (peer reads over NVLink) and runs the detector tail, as the reference does once per k
+        // after its j loop (src/crystalMaker.cu:332-372)
+        std::vector<Engine*> others;
+        for (int r = 1; r < n; r++) others.push_back(sim->engs[r].get());
+        for (int k = 0; k < p.n3; k++) {
+            parallel_for(n, [&](int r) { sim->engs[r]->run_k(k); });
+            sim->eng->reduce_from(others);
+            sim->eng->finish_k(k, img_k(k), ew_k(k));
+        }
+    } else if (n > 1 && sim->shard == SHARD_REPLICAS && p.n3 > 1) {
+        parallel_for(n, [&](int r) {
+            for (int k = r; k < p.n3; k += n) {
+                sim->engs[r]->run_k(k);
+                sim->engs[r]->finish_k(k, img_k(k), ew_k(k));
+            }
+        });
+    } else {
+        for (int k = 0; k < p.n3; k++) {
+            sim->eng->run_k(k);
+            sim->eng->finish_k(k, img_k(k), ew_k(k));
+        }
     }
     return 0;
     API_CATCH(-1)
@@ -249,6 +334,33 @@ double fdes_b200_stem_scan(fdes_b200_sim* sim, int k, int nprobes, const float* 
                            const float* det_mrad_host, float* out_host)
 {
     API_TRY
+    const int n = (int)sim->engs.size();
+    if (n > 1 && nprobes > 0 && ndet > 0) {
+        std::vector<double> ms(n, 0.0);
+        if (sim->shard == SHARD_CONFIGS) {
+            // every device scans all positions with its share of the frozen-phonon configurations
+            // (weights 1/count inside); the detector signals are summed here in device order
+            std::vector<std::vector<float>> part(n);
+            parallel_for(n, [&](int r) {
+                part[r].resize((size_t)nprobes * ndet);
+                sim->engs[r]->stem_scan(k, nprobes, xy_host, ndet, det_mrad_host, part[r].data(), &ms[r]);
+            });
+            for (size_t i = 0; i < (size_t)nprobes * ndet; i++) {
+                float s = part[0][i];
+                for (int r = 1; r < n; r++) s += part[r][i];
+                out_host[i] = s;
+            }
+        } else {
+            // replicas: contiguous ranges of the raster per device, gathered in place
+            parallel_for(n, [&](int r) {
+                const int i0 = (int)((long long)nprobes * r / n), i1 = (int)((long long)nprobes * (r + 1) / n);
+                if (i1 > i0)
+                    sim->engs[r]->stem_scan(k, i1 - i0, xy_host + 2 * (size_t)i0, ndet, det_mrad_host,
+                                            out_host + (size_t)i0 * ndet, &ms[r]);
+            });
+        }
+        return *std::max_element(ms.begin(), ms.end());
+    }
     double ms = 0.0;
     sim->eng->stem_scan(k, nprobes, xy_host, ndet, det_mrad_host, out_host, &ms);
     return ms;
@@ -337,6 +449,43 @@ int fdes_b200_sort_records(unsigned int* keys, int* cols, float* w, int n, int n
     API_CATCH(-1)
 }
 
+}  // extern "C"
+
+// "<count>" -> first, first + 1, ... (modulo the device count); "<i>,<j>,..." -> that list;
+// empty / NULL -> {first}
+std::vector<int> fdes_b200_gpu_list(const char* spec, int first)
+{
+    std::vector<int> out;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) ndev = 0;
+    if (!spec || !spec[0]) { out.push_back(first); return out; }
+    if (strchr(spec, ',')) {
+        const char* q = spec;
+        while (*q) {
+            char* end = nullptr;
+            const long v = strtol(q, &end, 10);
+            if (end == q) break;
+            out.push_back((int)v);
+            q = *end == ',' ? end + 1 : end;
+        }
+    } else {
+        int n = atoi(spec);
+        if (ndev > 0 && n > ndev) n = ndev;
+        for (int i = 0; i < std::max(1, n); i++) out.push_back(ndev > 0 ? (first + i) % ndev : first + i);
+    }
+    if (out.empty()) out.push_back(first);
+    return out;
+}
+
+extern "C" {
+
+int fdes_b200_parse_gpu_list(const char* spec, int first, int* out, int max_out)
+{
+    const std::vector<int> v = fdes_b200_gpu_list(spec, first);
+    for (int i = 0; i < (int)v.size() && i < max_out; i++) out[i] = v[i];
+    return (int)v.size();
+}
+
 // ---------------------------------------------------------------------------------------------
 // drop-in export (reference src/FDESExport.cu:59-178)
 // ---------------------------------------------------------------------------------------------
@@ -357,8 +506,12 @@ void FDES(int gpu_Index, int print_Level, char* input_name, char* image_name, ch
     using clk = std::chrono::steady_clock;
     const bool timing = getenv("FDES_B200_TIMING") != nullptr;
     const auto t0 = clk::now();
-    fdes_b200_sim* sim = fdes_b200_open_cnf(input_name, atomsArray, numAtoms, gpu_Index, 0, 0, 1,
-                                            print_Level > 1);
+    // FDES_B200_GPUS = "<count>" (devices gpu_Index, gpu_Index + 1, ...) or "<i>,<j>,..." shards the
+    // run over several GPUs of this process; unset: the reference's single device (gpu_Index)
+    const std::vector<int> gpus = fdes_b200_gpu_list(getenv("FDES_B200_GPUS"), gpu_Index);
+    fdes_b200_sim* sim = gpus.size() > 1
+        ? fdes_b200_open_multi(input_name, atomsArray, numAtoms, gpus.data(), (int)gpus.size(), 0, print_Level > 1)
+        : fdes_b200_open_cnf(input_name, atomsArray, numAtoms, gpus.empty() ? gpu_Index : gpus[0], 0, 0, 1, print_Level > 1);
     if (!sim) {
         fprintf(stderr, " \n fdes_b200: %s \n", fdes_b200_last_error());
         exit(EXIT_FAILURE);

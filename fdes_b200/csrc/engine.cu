@@ -47,6 +47,29 @@ static const KirklandRow kKirkland[103] = {
                                      " at " + __FILE__ + ":" + std::to_string(__LINE__));        \
     } while (0)
 
+// Every public entry point runs on the engine's own device, whatever the caller's current device
+// is (torch switching devices, several engines of one process on different GPUs), and restores
+// the caller's device on the way out.
+namespace {
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) {
+            cudaError_t e_ = cudaSetDevice(dev);
+            if (e_ != cudaSuccess)
+                throw std::runtime_error(std::string("cudaSetDevice(") + std::to_string(dev) + "): " + cudaGetErrorString(e_));
+            changed = true;
+        }
+    }
+    ~DeviceGuard() { if (changed && prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+}  // namespace
+
 // ---------------------------------------------------------------------------------------------
 // Device memory: every buffer of an Engine is a slice of ONE block, and blocks are cached per
 // process between simulations (the reference cudaMalloc/cudaFree's its buffers per call and
@@ -135,7 +158,6 @@ void release_device_cache()
 
 Engine::Engine(const Params& pin, const Atoms& atoms, const EngineOptions& opt) : p_(pin), opt_(opt)
 {
-    PhaseTimer pt;
     if (atoms.size() <= 0) throw std::runtime_error("no atoms in the specimen");
     if (p_.mode < 0 || p_.mode > 2) throw std::runtime_error("mode must be 0 (imaging), 1 (DP) or 2 (CBED)");
     if (p_.m1 != p_.m2)
@@ -147,7 +169,20 @@ Engine::Engine(const Params& pin, const Atoms& atoms, const EngineOptions& opt) 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         throw std::runtime_error("no CUDA device: fdes_b200 has no CPU fallback");
-    CK(cudaSetDevice(opt_.gpu_index));
+    if (opt_.gpu_index < 0 || opt_.gpu_index >= ndev)
+        throw std::runtime_error("gpu index " + std::to_string(opt_.gpu_index) + " out of range (" + std::to_string(ndev) + " device(s))");
+    DeviceGuard guard(opt_.gpu_index);
+    try {
+        init(atoms);
+    } catch (...) {
+        release();     // the destructor does not run for a throwing constructor
+        throw;
+    }
+}
+
+void Engine::init(const Atoms& atoms)
+{
+    PhaseTimer pt;
 
     // sub-slicing (subSliceRatio / setSubSlices, src/crystalMaker.cu:246-247, 720-743)
     m3_orig_ = p_.m3; d3_orig_ = p_.d3;
@@ -239,12 +274,21 @@ Engine::Engine(const Params& pin, const Atoms& atoms, const EngineOptions& opt) 
 
 Engine::~Engine()
 {
-    if (graph_) cudaGraphExecDestroy(graph_);
+    try {
+        DeviceGuard guard(opt_.gpu_index);
+        release();
+    } catch (...) {
+    }
+}
+
+void Engine::release()
+{
+    if (graph_) { cudaGraphExecDestroy(graph_); graph_ = nullptr; }
     if (st_) cudaStreamSynchronize(st_);
-    if (arena_) pool_release(arena_);
-    if (ev0_) cudaEventDestroy(ev0_);
-    if (ev1_) cudaEventDestroy(ev1_);
-    if (st_) cudaStreamDestroy(st_);
+    if (arena_) { pool_release(arena_); arena_ = nullptr; }
+    if (ev0_) { cudaEventDestroy(ev0_); ev0_ = nullptr; }
+    if (ev1_) { cudaEventDestroy(ev1_); ev1_ = nullptr; }
+    if (st_) { cudaStreamDestroy(st_); st_ = nullptr; }
 }
 
 void Engine::setup_tables()
@@ -372,9 +416,17 @@ void Engine::prepare_batch(int nb, const float* xyz_k)
     if (p_.frPh > 0) {
         // the XORWOW streams are consumed in the global order (k, j) of the single-GPU reference:
         // skip the normals that belong to configurations of other ranks (or other calls)
-        const long long burn = rng_target_ - rng_pos_;
-        if (burn < 0) throw std::runtime_error("frozen-phonon configurations must be visited in increasing (k, j) order");
-        launch_atom_jitter(xyzFP_, xyz_k, dwf_, nAt_, rng_, (int)burn, nb, st_);
+        long long burn = rng_target_ - rng_pos_;
+        if (burn < 0) {
+            // a configuration before the current stream position (run_k(k) repeated, k visited out
+            // of order): start the streams again, so that configuration (k, j) always sees the
+            // draws it has in the reference's (k, j) order
+            launch_rng_init(rng_, 3 * nAt_, 1ULL, st_);
+            rng_pos_ = 0;
+            burn = rng_target_;
+            tm_.kernel_launches += 1;
+        }
+        launch_atom_jitter(xyzFP_, xyz_k, dwf_, nAt_, rng_, burn, nb, st_);
         rng_pos_ = rng_target_ + nb;
         rng_target_ = rng_pos_;
         tm_.kernel_launches += 1;
@@ -487,6 +539,7 @@ void Engine::accumulate_outputs(int k, int nb)
 
 void Engine::run_k(int k)
 {
+    DeviceGuard guard(opt_.gpu_index);
     PhaseTimer pt;
     if (k < 0 || k >= p_.n3) throw std::runtime_error("measurement index out of range");
     const size_t NN = (size_t)N_ * N_;
@@ -497,7 +550,7 @@ void Engine::run_k(int k)
     make_incident(k);
     for (int j = j0_; j < j1_; j += B_) {
         const int nb = std::min(B_, j1_ - j);
-        rng_target_ = std::max(rng_pos_, (long long)k * count_ + j);   // position of configuration (k, j)
+        rng_target_ = (long long)k * count_ + j;   // position of configuration (k, j)
         prepare_batch(nb, xyzK_);
         for (int b = 0; b < nb; b++)
             CK(cudaMemcpyAsync(Psi_ + (size_t)b * NN, psi_in_, NN * sizeof(cpx), cudaMemcpyDeviceToDevice, st_));
@@ -509,8 +562,57 @@ void Engine::run_k(int k)
     pt.mark("run_k: wait");
 }
 
+// Partial sums of other engines (other GPUs of this process, frozen-phonon configurations sharded)
+// are added to this engine's accumulators.  All engines must have finished run_k (it synchronises).
+void Engine::reduce_from(const std::vector<Engine*>& others)
+{
+    DeviceGuard guard(opt_.gpu_index);
+    if (others.empty()) return;
+    if ((int)others.size() > MAX_PEERS) throw std::runtime_error("too many peer engines");
+    const size_t NN = (size_t)N_ * N_;
+    PeerSources si{}, se{};
+    bool direct = true;
+    for (Engine* o : others) {
+        if (o->N_ != N_) throw std::runtime_error("peer engines must share the grid size");
+        if (o->opt_.gpu_index != opt_.gpu_index) {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, opt_.gpu_index, o->opt_.gpu_index));
+            if (can) {
+                const cudaError_t pe = cudaDeviceEnablePeerAccess(o->opt_.gpu_index, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CK(pe);
+                cudaGetLastError();    // clear the sticky "already enabled"
+            } else {
+                direct = false;
+            }
+        }
+        si.p[si.n++] = o->I_;
+        if (ew_ && o->ew_) se.p[se.n++] = reinterpret_cast<const float*>(o->ew_);
+    }
+    if (direct) {
+        launch_peer_sum(I_, si, NN, st_);
+        if (ew_ && se.n) launch_peer_sum(reinterpret_cast<float*>(ew_), se, 2 * NN, st_);
+        tm_.kernel_launches += 1 + (ew_ && se.n ? 1 : 0);
+    } else {
+        // no peer mapping (PCIe boxes without P2P): stage each partial sum through scratch_
+        for (Engine* o : others) {
+            PeerSources one{};
+            one.n = 1;
+            CK(cudaMemcpyPeerAsync(scratch_, opt_.gpu_index, o->I_, o->opt_.gpu_index, NN * sizeof(float), st_));
+            one.p[0] = reinterpret_cast<const float*>(scratch_);
+            launch_peer_sum(I_, one, NN, st_);
+            if (ew_ && o->ew_) {
+                CK(cudaMemcpyPeerAsync(scratch_, opt_.gpu_index, o->ew_, o->opt_.gpu_index, NN * sizeof(cpx), st_));
+                launch_peer_sum(reinterpret_cast<float*>(ew_), one, 2 * NN, st_);
+            }
+            tm_.kernel_launches += 2;
+        }
+    }
+    CK(cudaStreamSynchronize(st_));
+}
+
 void Engine::finish_k(int k, float* image_host, float* exitwave_host)
 {
+    DeviceGuard guard(opt_.gpu_index);
     PhaseTimer pt;
     const size_t NN = (size_t)N_ * N_;
     // addNoiseAndMtf (src/crystalMaker.cu:579-613) + copyMiddleOut
@@ -546,6 +648,7 @@ void Engine::finish_k(int k, float* image_host, float* exitwave_host)
 
 void Engine::potential_slices(float* out_host)
 {
+    DeviceGuard guard(opt_.gpu_index);
     // untilted (offset only), phonon-free potential with the original slicing
     // (src/crystalMaker.cu:381-397).  NOTE: the reference leaves this buffer uninitialised when
     // no sub-slicing/phonons/tilt are active; here it is always computed.
@@ -574,6 +677,7 @@ void Engine::potential_slices(float* out_host)
 // ---------------------------------------------------------------------------------------------
 void Engine::next_jittered_coords(int k, float* xyz_host)
 {
+    DeviceGuard guard(opt_.gpu_index);
     CK(cudaMemcpyAsync(xyzK_, xyzTO_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
     tilt(xyzK_, p_.tiltspec[2 * k], p_.tiltspec[2 * k + 1], 0.f);
     if (p_.frPh > 0) { launch_atom_jitter(xyzFP_, xyzK_, dwf_, nAt_, rng_, 0, 1, st_); rng_pos_ += 1; rng_target_ = rng_pos_; }
@@ -584,6 +688,7 @@ void Engine::next_jittered_coords(int k, float* xyz_host)
 
 void Engine::bin_tuples(const float* xyz_host, int* bins_host)
 {
+    DeviceGuard guard(opt_.gpu_index);
     CK(cudaMemcpyAsync(xyzFP_, xyz_host, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyHostToDevice, st_));
     BinGeom bg{N_, N_, p_.m3, nZ_, p_.d1, p_.d2, p_.d3};
     launch_bin_atoms(xyzFP_, zidx_, occ_, nAt_, bg, keys_, cols_, w_, bins_, 1, st_);
@@ -593,6 +698,7 @@ void Engine::bin_tuples(const float* xyz_host, int* bins_host)
 
 void Engine::phase_grating(const float* xyz_host, int s, float* V_host)
 {
+    DeviceGuard guard(opt_.gpu_index);
     const size_t NN = (size_t)N_ * N_;
     CK(cudaMemcpyAsync(xyzFP_, xyz_host, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyHostToDevice, st_));
     bin_and_sort(0, 1, xyzFP_);
@@ -607,6 +713,7 @@ void Engine::phase_grating(const float* xyz_host, int s, float* V_host)
 
 void Engine::exit_wave(const float* xyz_host, int k, float* psi_host)
 {
+    DeviceGuard guard(opt_.gpu_index);
     const size_t NN = (size_t)N_ * N_;
     CK(cudaMemcpyAsync(xyzFP_, xyz_host, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyHostToDevice, st_));
     bin_and_sort(0, 1, xyzFP_);
@@ -624,6 +731,7 @@ void Engine::exit_wave(const float* xyz_host, int k, float* psi_host)
 
 double Engine::bench_configs(int k, int configs)
 {
+    DeviceGuard guard(opt_.gpu_index);
     const size_t NN = (size_t)N_ * N_;
     launch_fill_f32(I_, NN, 0.f, st_);
     if (ew_) launch_fill_cpx(ew_, NN, make_float2(0.f, 0.f), st_);
@@ -659,6 +767,7 @@ double Engine::bench_configs(int k, int configs)
 void Engine::stem_scan(int k, int nprobes, const float* xy_host, int ndet, const float* det_mrad_host,
                        float* out_host, double* loop_ms)
 {
+    DeviceGuard guard(opt_.gpu_index);
     if (p_.mode != 2) throw std::runtime_error("STEM scan needs mode 2 (convergent probe)");
     if (k < 0 || k >= p_.n3) throw std::runtime_error("measurement index out of range");
     if (nprobes <= 0) throw std::runtime_error("no probe positions");
@@ -700,7 +809,7 @@ void Engine::stem_scan(int k, int nprobes, const float* xy_host, int ndet, const
         CK(cudaEventRecord(ev0_, st_));
         const float weight = 1.f / (float)count_;
         for (int j = j0_; j < j1_; j++) {
-            rng_target_ = std::max(rng_pos_, (long long)k * count_ + j);
+            rng_target_ = (long long)k * count_ + j;
             prepare_batch(1, xyzK_);
             for (int s = 0; s < p_.m3; s += 2) {   // transmission stack of this configuration
                 const int npair = std::min(2, p_.m3 - s);
@@ -742,6 +851,7 @@ void Engine::stem_scan(int k, int nprobes, const float* xy_host, int ndet, const
 // bracketed by CUDA events on the engine's stream: ms6[i] = average launch duration of S(i+1).
 void Engine::time_sweeps(int k, int nb, int reps, float* ms6)
 {
+    DeviceGuard guard(opt_.gpu_index);
     const size_t NN = (size_t)N_ * N_;
     nb = std::max(1, std::min(nb, B_));
     CK(cudaMemcpyAsync(xyzK_, xyzTO_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));

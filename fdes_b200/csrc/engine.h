@@ -48,6 +48,10 @@ public:
     void run_k(int k);
     float* intensity_dev() { return I_; }
     cpx* exitwave_dev() { return ew_; }
+    // adds the partial sums of other engines of this process (possibly on other GPUs: read through
+    // NVLink peer mappings, fixed order) to this engine's accumulators; call after every engine's run_k
+    void reduce_from(const std::vector<Engine*>& others);
+    int gpu_index() const { return opt_.gpu_index; }
     // detector tail of the reference (addNoiseAndMtf + copyMiddleOut) on the (reduced) intensity:
     // image_host [n2*n1]; exitwave_host [m2*m1*2] may be null.
     void finish_k(int k, float* image_host, float* exitwave_host);
@@ -84,6 +88,8 @@ public:
     cudaStream_t stream() const { return st_; }
 
 private:
+    void init(const Atoms& atoms);                  // constructor body (device already selected)
+    void release();                                 // stream, events, arena, graph
     void setup_tables();
     void make_incident(int k);                      // psi_in_ (row space) for index k
     void prepare_batch(int nb, const float* xyz_k);  // jitter + bin + sort + rowptr of a batch

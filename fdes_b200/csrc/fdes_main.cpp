@@ -7,6 +7,7 @@
 #include "params.h"
 #include "emd.h"
 #include <getopt.h>
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -19,6 +20,7 @@ int main(int argc, char** argv)
     std::string input = "dataFDES.cnf", image = "Measurements.bin", emd = "results.emd";
     int gpu_index = 0, print_level = 0;
     bool stem_scan = false;
+    std::string gpus_spec;
     static struct option opts[] = {{"gpu_index", required_argument, 0, 0},
                                    {"input_name", required_argument, 0, 0},
                                    {"image_name", required_argument, 0, 0},
@@ -27,6 +29,7 @@ int main(int argc, char** argv)
                                    {"help", no_argument, 0, 0},
                                    {"version", no_argument, 0, 0},
                                    {"stem_scan", no_argument, 0, 0},   // extension, see below
+                                   {"gpus", required_argument, 0, 0},  // extension: shard the run over several GPUs
                                    {NULL, 0, 0, 0}};
     while (true) {
         int idx = 0;
@@ -54,10 +57,13 @@ int main(int argc, char** argv)
                         "  [ --print_level <0 images | 1 + potential slices | 2 + exit waves> ]\n"
                         "  [ --gpu_index   <CUDA device ordinal, default 0> ]\n"
                         "  [ --help ] [ --version ]\n"
+                        "  [ --gpus        extension: <count> (gpu_index, gpu_index + 1, ...) or a list i,j,... -- frozen-phonon\n"
+                        "                  configurations, tilt/defocus series or STEM probes are sharded over these GPUs ]\n"
                         "  [ --stem_scan   extension: run the probe scan a `mode: STEM` .qsc describes (scan_* and\n"
                         "                  detector: keys); image_name receives float32 [detector][x][y] ]\n");
                 return EXIT_FAILURE;
             case 7: stem_scan = true; break;
+            case 8: gpus_spec = optarg; break;
             case 6: fprintf(stderr, " \n FDES (fdes_b200) Version : %1.1f  \n", fdes_b200_version() / 100.0); return EXIT_FAILURE;
         }
     }
@@ -81,6 +87,10 @@ int main(int argc, char** argv)
         a6[6 * i + 4] = atoms.dwf[i];
         a6[6 * i + 5] = atoms.occ[i];
     }
+    // devices of the run: --gpus, else the environment (FDES_B200_GPUS, as FDES() reads it), else gpu_index
+    const char* spec = !gpus_spec.empty() ? gpus_spec.c_str() : getenv("FDES_B200_GPUS");
+    std::vector<int> gpus((size_t)std::max(1, fdes_b200_parse_gpu_list(spec, gpu_index, nullptr, 0)));
+    fdes_b200_parse_gpu_list(spec, gpu_index, gpus.data(), (int)gpus.size());
     if (stem_scan) {
         // Extension (FDES has no STEM mode): the raster and detectors of a QSTEM `mode: STEM` file, keys the
         // reference parses and drops (src/rwQsc.cu:444-466, 698-735), drive the batched probe scan.
@@ -93,7 +103,7 @@ int main(int argc, char** argv)
         const int np = nxy[0] * nxy[1];
         std::vector<float> xy(2 * (size_t)np), det(2 * (size_t)ndet), sig((size_t)np * ndet), out((size_t)np * ndet);
         fdes_b200_qsc_scan(input.c_str(), nxy, xy.data(), np, det.data(), ndet);
-        fdes_b200_sim* sim = fdes_b200_open_cnf(input.c_str(), nullptr, 0, gpu_index, 32, 0, 1, 0);
+        fdes_b200_sim* sim = fdes_b200_open_multi(input.c_str(), nullptr, 0, gpus.data(), (int)gpus.size(), 32, 0);
         if (!sim) { fprintf(stderr, " \n fdes_b200: %s \n", fdes_b200_last_error()); return EXIT_FAILURE; }
         const double ms = fdes_b200_stem_scan(sim, 0, np, xy.data(), ndet, det.data(), sig.data());
         if (ms < 0) { fprintf(stderr, " \n fdes_b200: %s \n", fdes_b200_last_error()); return EXIT_FAILURE; }
@@ -108,7 +118,7 @@ int main(int argc, char** argv)
     }
     // NOTE: FDES() truncates the occupancy to an integer like the reference's readAtomsFromArray;
     // the file path keeps fractional occupancies, so the CLI goes through the session API.
-    fdes_b200_sim* sim = fdes_b200_open_cnf(input.c_str(), nullptr, 0, gpu_index, 0, 0, 1, print_level > 1);
+    fdes_b200_sim* sim = fdes_b200_open_multi(input.c_str(), nullptr, 0, gpus.data(), (int)gpus.size(), 0, print_level > 1);
     if (!sim) { fprintf(stderr, " \n fdes_b200: %s \n", fdes_b200_last_error()); return EXIT_FAILURE; }
     int d[10];
     fdes_b200_get_dims(sim, d);

@@ -145,6 +145,12 @@ void launch_area_mask_blend(cpx* psi, int N, int dn1, int dn2, cudaStream_t st);
 // src/crystalMaker.cu:50-70); states: XORWOW streams curand_init(1 + n3, pixel, 0) (:295)
 void launch_anscombe_noise(cpx* f, size_t n, float dose, void* states, cudaStream_t st);
 
+// dst[i] += sum_r src.p[r][i] (fixed order); the sources may live on peer devices that the current
+// device can access (NVLink peer mappings)
+constexpr int MAX_PEERS = 15;
+struct PeerSources { int n; const float* p[MAX_PEERS]; };
+void launch_peer_sum(float* dst, const PeerSources& src, size_t n, cudaStream_t st);
+
 // ---- atoms: tilt, frozen phonons, binning, sort, row pointers -----------------------------
 struct BinGeom {
     int m1, m2, m3, nZ;
@@ -157,7 +163,7 @@ void launch_rng_init(void* states, int n, unsigned long long seed, cudaStream_t 
 // xyz_out[i] = xyz_in[i] + N(0,1) * 0.112539540f * sqrtf(dwf[i/3]); burn: draws to discard first
 // for nconf consecutive configurations: xyz_out [nconf][nAt][3]
 void launch_atom_jitter(float* xyz_out, const float* xyz_in, const float* dwf, int nAt,
-                        void* states, int burn, int nconf, cudaStream_t st);
+                        void* states, long long burn, int nconf, cudaStream_t st);
 // per atom: 4 deposit records (key = (i3*nZ + zidx)*m2 + row, col, weight) and the integer bin
 // tuple (i1, i2, i3, zidx; -1 when rejected) -- squareAtoms_d, src/crystalMaker.cu:73-134
 // nconf configurations per launch: xyz [nconf][nAt][3], records [nconf][4 nAt] (bins_out: nconf = 1)

@@ -3,6 +3,7 @@
 // precise expf/sinf/cosf, no fast-math) so that they agree with what the reference recomputes
 // every slice; here they are computed once per simulation and kept L2-resident.
 #include "kernels.cuh"
+#include <algorithm>
 #include <cfloat>
 #include <cstdio>
 
@@ -326,6 +327,30 @@ __global__ void k_area_mask_blend(cpx* psi, int N, int dn1, int dn2)
 void launch_area_mask_blend(cpx* psi, int N, int dn1, int dn2, cudaStream_t st)
 {
     k_area_mask_blend<<<(N * N + 255) / 256, 256, 0, st>>>(psi, N, dn1, dn2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU reduction of the per-device partial sums (frozen-phonon configurations sharded over
+// the GPUs of one process): the destination device reads the peers' buffers directly through
+// NVLink peer mappings (cudaDeviceEnablePeerAccess) and adds them in the fixed order 0 .. n-1, so
+// the result does not depend on timing.  128-bit loads; no staging copies.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_peer_sum(float4* __restrict__ dst, PeerSources src, size_t n4)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 a = dst[i];
+        for (int r = 0; r < src.n; r++) {
+            const float4 b = reinterpret_cast<const float4*>(src.p[r])[i];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        dst[i] = a;
+    }
+}
+void launch_peer_sum(float* dst, const PeerSources& src, size_t n, cudaStream_t st)
+{
+    // n is a multiple of 4 for every grid of the engine (m1 * m2 floats, m1 even)
+    const size_t n4 = n / 4;
+    k_peer_sum<<<(unsigned)std::min<size_t>((n4 + 255) / 256, 148 * 8), 256, 0, st>>>(reinterpret_cast<float4*>(dst), src, n4);
 }
 
 }  // namespace fdes

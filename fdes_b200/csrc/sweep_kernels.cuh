@@ -370,9 +370,10 @@ void launch_potential_cols_n(const SweepGeom& g, cpx* B, const cpx* A, const flo
             using P = PipeCfg<NN>;
             FDES_ALLOW_SMEM((k_potential_cols_tma<NN>), P::SMEM);
             const int tiles_x = NN / P::CW, ntiles = tiles_x * batch;
-            const CUtensorMap* mapA = tile_map(A, NN, batch * nZ, P::CW, P::BR);
-            const CUtensorMap* mapB = tile_map(B, NN, batch, P::CW, P::BR);
-            k_potential_cols_tma<NN><<<pipe_grid(ntiles), P::THREADS, P::SMEM, st>>>(*mapA, *mapB, Gq, rowptr, slice, slice2,
+            CUtensorMap mapA, mapB;
+            tile_map(&mapA, A, NN, batch * nZ, P::CW, P::BR);
+            tile_map(&mapB, B, NN, batch, P::CW, P::BR);
+            k_potential_cols_tma<NN><<<pipe_grid(ntiles), P::THREADS, P::SMEM, st>>>(mapA, mapB, Gq, rowptr, slice, slice2,
                                                                                   nZ, rowptr_stride, tiles_x, ntiles, g.tw);
             FDES_LAUNCH_CHECK();
             return;
@@ -644,8 +645,9 @@ void launch_bandlimit_cols_n(const SweepGeom& g, cpx* W, int batch, int npair, c
             FDES_ALLOW_SMEM((k_bandlimit_cols_tma<NN>), P::SMEM);
             const int nimg = npair == 0 ? batch : 2 * batch;     // images in the stack
             const int tiles_x = band_cols(g) / P::CW, ntiles = tiles_x * (npair == 0 ? batch : batch * npair);
-            const CUtensorMap* map = tile_map(W, NN, nimg, P::CW, P::BR);
-            k_bandlimit_cols_tma<NN><<<pipe_grid(ntiles), P::THREADS, P::SMEM, st>>>(*map, npair, g.lo_end, g.hi_start,
+            CUtensorMap map;
+            tile_map(&map, W, NN, nimg, P::CW, P::BR);
+            k_bandlimit_cols_tma<NN><<<pipe_grid(ntiles), P::THREADS, P::SMEM, st>>>(map, npair, g.lo_end, g.hi_start,
                                                                                   tiles_x, ntiles, g.tw);
             FDES_LAUNCH_CHECK();
             return;
@@ -804,8 +806,9 @@ void launch_propagate_cols_n(const SweepGeom& g, cpx* Psi, const cpx* Pq, int ba
             using P = PipeCfg<NN>;
             FDES_ALLOW_SMEM((k_propagate_cols_tma<NN>), P::SMEM);
             const int tiles_x = band_cols(g) / P::CW, ntiles = tiles_x * batch;
-            const CUtensorMap* map = tile_map(Psi, NN, batch, P::CW, P::BR);
-            k_propagate_cols_tma<NN><<<pipe_grid(ntiles), P::THREADS, P::SMEM, st>>>(*map, Pq, g.lo_end, g.hi_start,
+            CUtensorMap map;
+            tile_map(&map, Psi, NN, batch, P::CW, P::BR);
+            k_propagate_cols_tma<NN><<<pipe_grid(ntiles), P::THREADS, P::SMEM, st>>>(map, Pq, g.lo_end, g.hi_start,
                                                                                   tiles_x, ntiles, g.tw);
             FDES_LAUNCH_CHECK();
             return;

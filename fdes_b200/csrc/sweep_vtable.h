@@ -15,7 +15,7 @@ namespace fdes {
 
 // TMA descriptor (cached per device / array / geometry) of an [nimg][N][N] complex64 array with
 // boxes of [BR rows][CW columns] -- the column tiles of col_pipe.cuh (tma_map.cu)
-const CUtensorMap_st* tile_map(const void* base, int N, int nimg, int CW, int BR);
+void tile_map(CUtensorMap_st* out, const void* base, int N, int nimg, int CW, int BR);
 
 struct SweepVTable {
     int N, rows_per_block, cols_per_block;

@@ -33,15 +33,14 @@ std::mutex g_mutex;
 std::vector<Entry> g_cache;
 }  // namespace
 
-const CUtensorMap_st* tile_map(const void* base, int N, int nimg, int CW, int BR)
+void tile_map(CUtensorMap_st* out, const void* base, int N, int nimg, int CW, int BR)
 {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) throw std::runtime_error("cudaGetDevice failed");
     std::lock_guard<std::mutex> lk(g_mutex);
     for (const Entry& e : g_cache)
-        if (e.base == base && e.N == N && e.nimg == nimg && e.CW == CW && e.BR == BR && e.dev == dev) return &e.map;
+        if (e.base == base && e.N == N && e.nimg == nimg && e.CW == CW && e.BR == BR && e.dev == dev) { *out = e.map; return; }
     if (g_cache.size() >= 512) g_cache.clear();   // descriptors are 128 bytes; a bounded cache is enough
-    if (g_cache.capacity() < 512) g_cache.reserve(512);   // returned pointers stay valid until the clear
     Entry e{dev, base, N, nimg, CW, BR, {}};
     const cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)N, (cuuint64_t)nimg};
     const cuuint64_t strides[2] = {(cuuint64_t)N * 8, (cuuint64_t)N * N * 8};    // bytes, dimensions 1 and 2
@@ -59,7 +58,7 @@ const CUtensorMap_st* tile_map(const void* base, int N, int nimg, int CW, int BR
         throw std::runtime_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r) + " for N = " +
                                  std::to_string(N) + ", tile width " + std::to_string(CW));
     g_cache.push_back(e);
-    return &g_cache.back().map;
+    *out = e.map;
 }
 
 }  // namespace fdes

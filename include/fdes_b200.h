@@ -82,6 +82,23 @@ int fdes_b200_write_emd(const char* input_path, const char* emd_path, const floa
  * want_exitwave: keep the coherent exit-wave average (reference print_level 2). */
 fdes_b200_sim* fdes_b200_open_cnf(const char* cnf_path, const float* atoms6, int numAtoms,
                                   int gpu_index, int batch, int rank, int world, int want_exitwave);
+/* The same session on `ngpus` devices of THIS process (one engine and, while they compute, one host
+ * thread per device) -- the multi-GPU form of the seam below buildMeasurements
+ * (include/crystalMaker.h:77; the reference itself is single-GPU, cudaSetDevice at src/FDES.cu:165).
+ * What is sharded follows the reference's loop nest (src/crystalMaker.cu:324-372): with frozen phonons
+ * the configurations j of every measurement k (contiguous blocks per device, identical RNG streams +
+ * burn-in, partial intensities / exit waves summed onto gpu_indices[0] by a kernel that reads the
+ * peers' buffers over NVLink, detector tail once per k); without them the measurements k of a tilt /
+ * defocus series, or the probe positions of fdes_b200_stem_scan.  fdes_b200_simulate,
+ * fdes_b200_stem_scan and fdes_b200_close work on such a session unchanged; the building blocks further down act on
+ * the engine of gpu_indices[0].  FDES() opens its session this way when the environment variable
+ * FDES_B200_GPUS is set ("4" = gpu_Index .. gpu_Index + 3, or a list "0,2,5"); the CLI has --gpus. */
+fdes_b200_sim* fdes_b200_open_multi(const char* cnf_path, const float* atoms6, int numAtoms,
+                                    const int* gpu_indices, int ngpus, int batch, int want_exitwave);
+/* engines (GPUs) the session actually uses: min(ngpus, independent units) */
+int fdes_b200_num_gpus(const fdes_b200_sim* sim);
+/* the FDES_B200_GPUS / --gpus syntax -> device ordinals; returns how many (out may be NULL when max_out = 0) */
+int fdes_b200_parse_gpu_list(const char* spec, int first, int* out, int max_out);
 void fdes_b200_close(fdes_b200_sim* sim);
 
 /* dims[10] = n1 n2 n3 m1 m2 m3(after sub-slicing) nAt nZ phonon_configs batch */

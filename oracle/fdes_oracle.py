@@ -537,6 +537,72 @@ def forward_propagation(psi, V, p: Params, P=None, mask=None):
 
 
 # --------------------------------------------------------------------------------------
+# float64 evaluation of the same model (error budget of long slice chains)
+# --------------------------------------------------------------------------------------
+def exit_wave_fp64(p_in: Params, Z, xyz, occ) -> np.ndarray:
+    """Plane-wave exit wave (no frozen phonons, k = 0) of the SAME model evaluated in float64 /
+    complex128: identical float32 parameters (lambda, sigma, pixel sizes), identical bin decisions
+    and bilinear weights (they are exact float32 quantities, src/crystalMaker.cu:85-119), but the
+    scattering factors, exponentials and all transforms in double precision.  A float32 program that
+    follows A.2-A.4 differs from this by its accumulated rounding only, which is what the parity
+    tests of deep slice chains (400 sub-slices) compare the library and the reference against."""
+    p = p_in.copy()
+    set_sub_slices(p, sub_slice_ratio(p.d3, p.subSlTh))
+    m1, m2 = p.m1, p.m2
+    assert m1 == m2
+    f64, c128 = np.float64, np.complex128
+    Zl = list_of_elements(Z)
+    i1, i2, i3, r1, r2, ok = bin_atoms(xyz, p)
+    i1f = iw(m1).astype(f64)[None, :]
+    i2f = iw(m2).astype(f64)[:, None]
+    d1A, d2A = f64(f32(1e10) * f32(p.d1)), f64(f32(1e10) * f32(p.d2))
+    qsq = (i1f / (d1A * m1)) ** 2 + (i2f / (d2A * m2)) ** 2
+    eps = f64(FLT_EPSILON)
+    pi = f64(f32(p.pi))
+    sx = (pi * i1f / m1 + eps) / (np.sin(pi * i1f / m1) + eps)
+    sy = (pi * i2f / m2 + eps) / (np.sin(pi * i2f / m2) + eps)
+    G = {}
+    for Z0 in Zl:
+        a, b, c, d = [np.asarray(v, f64) for v in kirkland_params(Z0)]
+        fz = sum(a[k] / (qsq + b[k]) + c[k] * np.exp(-d[k] * qsq) for k in range(3))
+        G[Z0] = fz * (f64(f32(4.78776452e-9)) * f64(p.sigma)) / (d1A * d2A * f64(m1 * m2)) * sx * sy
+    i1i = iw(m1).astype(np.int64)[None, :]
+    i2i = iw(m2).astype(np.int64)[:, None]
+    mask = ~(((i1i * i1i + i2i * i2i).astype(f32) * f32(9) / f32(f32(min(m1, m2)) * f32(min(m1, m2)))).astype(f32) > f32(1))
+    d3 = f64(f32(p.d3))
+    t1 = (i1f / m1) * (d3 / f64(f32(p.d1)))
+    t2 = (i2f / m2) * (d3 / f64(f32(p.d2)))
+    P = np.exp(-1j * pi * (t1 * t1 + t2 * t2) * (f64(f32(p.lam)) / d3)) * mask / f64(m1 * m2)
+    invN = 1.0 / f64(m1 * m2)
+    fft = lambda a: sfft.fft2(a, workers=_WORKERS)
+    ifft = lambda a: sfft.ifft2(a, norm="forward", workers=_WORKERS)
+    occ64 = np.asarray(occ, f32).astype(f64)
+    psi = np.ones((m2, m1), c128)
+    Zarr = np.asarray(Z)
+    imPot = f64(f32(p.imPot))
+    for s in range(p.m3):
+        V = np.zeros((m2, m1), c128)
+        for Z0 in Zl:
+            sel = ok & (Zarr == Z0) & (i3 == s)
+            if not sel.any():
+                continue
+            a1, a2 = np.abs(r1[sel]).astype(f64), np.abs(r2[sel]).astype(f64)
+            g1 = np.where(r1[sel] < 0, -1, 1)
+            g2 = np.where(r2[sel] < 0, -1, 1)
+            j1, j2, oc = i1[sel].astype(np.int64), i2[sel].astype(np.int64), occ64[sel]
+            rho = np.zeros(m1 * m2, f64)
+            np.add.at(rho, j2 * m1 + j1, (1 - a1) * (1 - a2) * oc)
+            np.add.at(rho, (j2 + g2) * m1 + j1, (1 - a1) * a2 * oc)
+            np.add.at(rho, (j2 + g2) * m1 + j1 + g1, a1 * a2 * oc)
+            np.add.at(rho, j2 * m1 + j1 + g1, a1 * (1 - a2) * oc)
+            V += ifft(fft(rho.reshape(m2, m1) * (1 + 1j * imPot)) * G[Z0])
+        t = np.exp(-V.imag) * np.exp(1j * V.real)
+        t = ifft(fft(t) * mask) * invN
+        psi = ifft(fft(t * psi) * P)
+    return psi
+
+
+# --------------------------------------------------------------------------------------
 # incident wave, lens, detector  (src/multisliceSimulation.cu:89-156, 277-442, 563-622;
 # src/crystalMaker.cu:187-224, 579-613, 700-718; src/complexMath.cu:510-557)
 # --------------------------------------------------------------------------------------

@@ -36,6 +36,12 @@ def orc():
 
 
 @pytest.fixture(scope="session")
+def qorc(orc):
+    import qsc_oracle
+    return qsc_oracle
+
+
+@pytest.fixture(scope="session")
 def fb():
     import fdes_b200
     return fdes_b200

@@ -137,3 +137,14 @@ def test_used_cnf_atom_table_is_formatted_like_printf(fb, tmp_path):
     assert len(a) >= 2400 and len(lines) - i0 == len(a)
     for k, line in enumerate(lines[i0:]):
         assert line == "%i %14.8g %14.8g %14.8g %14.8g %14.8g " % (int(a[k, 0]), *[float(x) for x in a[k, 1:6]]), k
+
+
+def test_gpu_list_syntax(fb):
+    """FDES_B200_GPUS / --gpus values (no device needed: the count form is not clamped without one)."""
+    assert fb.parse_gpu_list(None, 3) == [3]
+    assert fb.parse_gpu_list("", 1) == [1]
+    assert fb.parse_gpu_list("0,2,5") == [0, 2, 5]
+    assert fb.parse_gpu_list("1,") == [1]
+    import torch
+    if not torch.cuda.is_available():
+        assert fb.parse_gpu_list("4", 2) == [2, 3, 4, 5]

@@ -70,7 +70,7 @@ void run_dbg(int batch, int reps)
     using Pc = PipeCfg<N>;
     CK(cudaFuncSetAttribute(k_dbg<N, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Pc::SMEM));
     const int bc = band_cols(g), tiles_x = bc / Pc::CW, ntiles = tiles_x * batch;
-    const CUtensorMap* map = tile_map(d1, N, batch, Pc::CW, Pc::BR);
+    CUtensorMap mapv; tile_map(&mapv, d1, N, batch, Pc::CW, Pc::BR); const CUtensorMap* map = &mapv;
     const int grid1 = ntiles < 148 ? ntiles : 148;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float ms1 = 0;
@@ -116,7 +116,7 @@ void run(int batch, int reps)
     const int bc = band_cols(g);
     dim3 grid0(bc / C::CW, batch);
     const int tiles_x = bc / Pc::CW, ntiles = tiles_x * batch;
-    const CUtensorMap* map = tile_map(d1, N, batch, Pc::CW, Pc::BR);
+    CUtensorMap mapv; tile_map(&mapv, d1, N, batch, Pc::CW, Pc::BR); const CUtensorMap* map = &mapv;
     int nsm = 0; CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0));
     const int grid1 = ntiles < nsm ? ntiles : nsm;
     k_propagate_cols<N><<<grid0, C::THREADS, C::SMEM>>>(d0, P, g.lo_end, g.hi_start, tw);
