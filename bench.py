@@ -5,10 +5,15 @@ Mpixel*slices/s) on N B200s of one node.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload si001_1024] [--impl reference]
 
 A *step* is one pass of the hot path over one batch of synthetic input: `configs_per_step`
-frozen-phonon configurations of the workload specimen per GPU, each a complete multislice run
-(atom jitter -> binning/sort -> per slice: projected potential, band-limited transmission, Fresnel
+frozen-phonon configurations of the workload specimen per GPU (400 for the default workload, so that
+the 20 timed steps of the driver last about two seconds), each a complete multislice run (atom
+jitter -> binning/sort -> per slice: projected potential, band-limited transmission, Fresnel
 propagation -> detector accumulation).  Frozen-phonon configurations are independent, so N GPUs
 process N x configs_per_step configurations per step with no data-path collective (weak scaling).
+With N > 1 the line also carries `job`: BASELINE configs[2] (Au 2048^2, 32 configurations) and
+configs[3] (256 x 256 STEM probes) each run as ONE job sharded over the N ranks, with the all-reduce
+of the partial intensities / the all-gather of the detector signals inside the timed region (strong
+scaling; at N = 1 the same jobs give the single-GPU reference time).
 
   value  whole-job Mpx*slices/s with the specimen resident in HBM, CUDA-event time of the steps,
          max over ranks.
@@ -16,7 +21,10 @@ process N x configs_per_step configurations per step with no data-path collectiv
          src/FDESExport.cu:59-178): parameter file + host atom array in, host image out; session
          set-up, host->device and device->host copies and the side-effect files are inside the
          timed region (wall clock).
-  roofline      dominant per-slice sweep: algorithmic bytes / its live CUDA-event time.
+  roofline      the six sweeps of one slice (one launch each over the batch): algorithmic bytes
+                (16 nZ + 80 B per pixel and slice) / the sum of their live CUDA-event launch
+                times, against the measured HBM peak and the nominal 8 TB/s of north_star; the
+                per-sweep table and the whole-step figure (value x bytes) are reported next to it.
   cpu_baseline  the numpy/pocketfft restatement (oracle/fdes_oracle.py) on this box's host cores,
                 bounded sample, rank 0 at N=1 only.  Reported baseline, not a target.
 
@@ -25,6 +33,9 @@ process N x configs_per_step configurations per step with no data-path collectiv
 has no CPU implementation -- its own implementation of this path is that single-GPU CUDA program
 -- so the reference arm runs on GPU 0 of the box (rank 0 only), whole-call wall time of the
 reference's exported flow (ref_harness e2e), which is what `e2e` of this arm is compared with.
+Its `config` is the one of our arm; a step of it is a bounded sample of that workload (16 of the 400
+configurations per call: the reference needs about 0.1 s per configuration, and 16 per call keep
+its fixed per-call cost below 5 % of the call).
 """
 import argparse
 import json
@@ -49,9 +60,12 @@ WORKLOADS = {
     "si001_1024": ("config_si001_1024", "Si[001] 11552 atoms, 1024^2 grid, 11 x 2 A slices, 100 kV (BASELINE configs[1])"),
     "au_2048": ("config_au_2048", "Au cuboctahedron 309 atoms, 2048^2 grid, 12 x 2.1 A slices, 50 kV (BASELINE configs[2])"),
     "slab_4096": ("config_random_4096_short", "random slab 4000 atoms / 3 species, 4096^2 grid, 20 x 2 A slices, 200 kV "
-                                             "(BASELINE configs[4] geometry, 20 of its 500 slices)"),
+                                             "(BASELINE configs[4] geometry, 20 of its 500 slices, same areal density)"),
+    "slab_4096_full": ("config_random_4096", "random slab 100000 atoms / 3 species, 4096^2 grid, 500 x 2 A slices, 200 kV "
+                                            "(BASELINE configs[4] at its named size)"),
 }
-DEFAULT_CONFIGS_PER_STEP = {"si001_1024": 16, "au_2048": 8, "slab_4096": 2}
+DEFAULT_CONFIGS_PER_STEP = {"si001_1024": 400, "au_2048": 80, "slab_4096": 20, "slab_4096_full": 2}
+REF_SAMPLE_CONFIGS = {"si001_1024": 16, "au_2048": 4, "slab_4096": 1, "slab_4096_full": 1}
 
 
 def peaks():
@@ -110,6 +124,14 @@ def algorithmic_bytes_per_px(nZ):
             "S4_bandlimit_cols": 16, "S5_multiply_rows": 24, "S6_propagate_cols": 16}
 
 
+def workload_config(a, cps, world):
+    """`config` of the JSON line: identical in our arm and in the reference arm."""
+    return {"workload": a.workload, "description": WORKLOADS[a.workload][1],
+            "configs_per_step_per_gpu": cps, "parallelism": f"phonon-configs x{world}",
+            "l2": "no explicit flush: every sweep streams a batched working set of several hundred MiB of wave / "
+                  "potential grids (126 MB L2) and every step draws new atom positions"}
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -158,9 +180,10 @@ def run_ours(a):
     dev_ms, t_wall = float(t[0]), float(t[1])
     value = world * px * slices_per_step * a.steps / (dev_ms * 1e-3) / 1e6
 
-    # live per-sweep kernel times (CUDA events on the engine's stream) -> roofline of the dominant one
+    # live per-sweep kernel times (CUDA events on the engine's stream) -> roofline of a slice
     sweep_ms = sim.time_sweeps(0, 0, 20)
     nZ, batch = sim.nZ, sim.batch
+    grid, slices = [sim.m1, sim.m2], sim.m3
     sim.close()
 
     # end to end: the drop-in FDES() call, host buffers in and out
@@ -198,31 +221,36 @@ def run_ours(a):
     assert np.isfinite(img).all() and img.mean() > 0.1, "FDES() returned an implausible image"
 
     stem = None if a.no_stem else run_stem(a, fb, specimens, tmp, local, world, barrier, dist, torch)
+    job = None if a.no_job else run_jobs(a, fb, specimens, tmp, local, rank, world, barrier, dist, torch)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     peak, peak_src = peaks()
-    traffic = None
-    tf = ROOT / "profiles" / "dram_traffic.json"     # per-launch dram bytes from the committed ncu capture
-    if tf.exists():
-        traffic = json.loads(tf.read_text())
+    traffic, traffic_src = None, None
+    tf = ROOT / "profiles" / "dram_traffic.json"     # per-launch dram bytes of the six sweeps from a committed ncu capture
+    if tf.exists() and a.workload == "si001_1024":
+        tj = json.loads(tf.read_text())
+        traffic_src = tj.get("source", "profiles/dram_traffic.json")
+        per = tj.get("per_launch_bytes", tj)
+        if all(n in per for n in algorithmic_bytes_per_px(nZ)):
+            # S1..S4 launches cover a slice PAIR: per slice, half of them
+            traffic = int(sum(per[n] * (0.5 if n[:2] in ("S1", "S2", "S3", "S4") else 1.0) for n in algorithmic_bytes_per_px(nZ))
+                          * batch / tj.get("batch", batch))
     ab = algorithmic_bytes_per_px(nZ)
     names = list(ab)
-    dom = int(np.argmax(sweep_ms))
-    bytes_dom = ab[names[dom]] * px * batch
-    achieved = bytes_dom / (float(sweep_ms[dom]) * 1e-3) / 1e9
     slice_bytes = sum(ab.values()) * px * batch
     slice_ms = float(np.sum(sweep_ms))
+    slice_gbs = slice_bytes / (slice_ms * 1e-3) / 1e9
+    step_gbs = value * 1e6 / world * sum(ab.values()) / 1e9      # per GPU: whole step incl. atom preparation, image formation
+    cfg = workload_config(a, cps, world)
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": round(dev_ms / a.steps, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "complex64 (f32)", "data": "synthetic",
-        "config": {"workload": a.workload, "description": WORKLOADS[a.workload][1], "grid": [sim.m1, sim.m2],
-                   "slices": sim.m3, "atoms": int(len(atoms6)), "species": nZ,
-                   "configs_per_step_per_gpu": cps, "batch": batch, "parallelism": f"phonon-configs x{world}",
-                   "l2": f"no explicit flush: the sweeps stream a batched working set of {(4 + nZ) * batch * px * 8 / 2**20:.0f} MiB "
-                         "of wave / potential grids (126 MB L2) and every step draws new atom positions"},
+        "config": cfg,
+        "shape": {"grid": grid, "slices": slices, "atoms": int(len(atoms6)), "species": nZ, "batch": batch,
+                  "batched_working_set_MiB": round((4 + nZ) * batch * px * 8 / 2**20)},
         "wall_ms_per_step": round(t_wall / a.steps, 4),
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(24 * len(atoms6)),
                 "d2h_bytes_per_step": int(img.nbytes), "ms_per_step": round(e2e_ms / a.steps, 4),
@@ -230,20 +258,24 @@ def run_ours(a):
                         "side-effect files inside the timed region (pinned caller buffers)"},
         "gpu_launches": cnt["launches"],
         "clocks": clk.summary(),
-        "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 1), "peak": peak,
-                     "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": (traffic or {}).get(names[dom]), "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": int(bytes_dom),
-                     "launch_ms": round(float(sweep_ms[dom]), 5)},
-        "sweeps": {n: {"ms": round(float(m), 5), "alg_GBps": round(ab[n] * px * batch / (float(m) * 1e-3) / 1e9, 1)}
+        "roofline": {"bound": "hbm", "kernel": "S1..S6: the six sweeps of one slice, one launch each over the batch",
+                     "achieved": round(slice_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(slice_gbs / peak, 4),
+                     "frac_of_8TBps": round(slice_gbs / 8000.0, 4),
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": int(slice_bytes), "algorithmic_bytes_per_px_slice": sum(ab.values()),
+                     "launch_ms": round(slice_ms, 5),
+                     "whole_step": {"achieved": round(step_gbs, 1), "frac": round(step_gbs / peak, 4),
+                                    "frac_of_8TBps": round(step_gbs / 8000.0, 4),
+                                    "note": "value x algorithmic bytes per pixel and slice, per GPU: atom preparation, wave "
+                                            "copies and image formation included"}},
+        "sweeps": {n: {"ms": round(float(m), 5), "alg_GBps": round(ab[n] * px * batch / (float(m) * 1e-3) / 1e9, 1),
+                       "frac": round(ab[n] * px * batch / (float(m) * 1e-3) / 1e9 / peak, 4)}
                    for n, m in zip(names, sweep_ms)},
-        "slice": {"alg_bytes_per_px": sum(ab.values()), "ms_per_slice_batch": round(slice_ms, 5),
-                  "alg_GBps": round(slice_bytes / (slice_ms * 1e-3) / 1e9, 1),
-                  "frac_of_peak": round(slice_bytes / (slice_ms * 1e-3) / 1e9 / peak, 4),
-                  "frac_of_8TBps": round(slice_bytes / (slice_ms * 1e-3) / 1e9 / 8000.0, 4)},
     }
     if stem is not None:
         line["stem"] = stem
+    if job is not None:
+        line["job"] = job
     if world == 1 and not a.no_cpu:
         line["cpu_baseline"] = cpu_baseline(cnf, a.cpu_seconds)
     print(json.dumps(line), flush=True)
@@ -284,9 +316,61 @@ def run_stem(a, fb, specimens, tmp, local, world, barrier, dist, torch):
                     "h2d_bytes_per_step": int(mine.nbytes), "d2h_bytes_per_step": int(sig.nbytes)},
             "config": {"workload": "srtio3_stem_512", "grid": [m1, m1], "slices": m3, "atoms": int(len(atoms)),
                        "probes_per_gpu": n, "batch": batch, "detectors_mrad": det.tolist()},
-            "roofline": {"bound": "hbm", "kernel": "S5+S6 per probe slice", "achieved": round(alg, 1), "peak": peak,
-                         "unit": "GB/s", "frac": round(alg / peak, 4), "algorithmic_bytes_per_px_slice": 40},
+            "roofline": {"bound": "hbm", "kernel": "S5+S6 per probe slice", "achieved": round(alg / world, 1), "peak": peak,
+                         "unit": "GB/s per GPU", "frac": round(alg / world / peak, 4), "frac_of_8TBps": round(alg / world / 8000.0, 4),
+                         "algorithmic_bytes_per_px_slice": 40},
             "haadf_mean": float(sig[:, 0].mean()), "abf_mean": float(sig[:, 1].mean())}
+
+
+def run_jobs(a, fb, specimens, tmp, local, rank, world, barrier, dist, torch):
+    """Strong scaling: ONE job sharded over the `world` ranks, collective inside the timed region.
+      au_2048_x32   BASELINE configs[2]: Au cuboctahedron 2048^2, 32 frozen-phonon configurations; the ranks
+                    run 32/world configurations each, all-reduce (NCCL) of the partial intensity, detector tail.
+      stem_256x256  BASELINE configs[3]: 65 536 probe positions on the SrTiO3 512^2 x 40-slice specimen; the ranks scan
+                    contiguous ranges of the raster, all-gather of the detector signals.
+    Wall clock between barriers (session set-up included), max over ranks."""
+    from fdes_b200.distributed import simulate_sharded, stem_scan_sharded
+    out = {}
+    cnf = tmp / "job_au_2048.cnf"
+    atoms = np.ascontiguousarray(specimens.config_au_2048(cnf, frozen_phonons=32), np.float32)
+    open_sim = lambda r, w: fb.Simulation(cnf, atoms6=atoms, gpu_index=local, rank=r, world=w)
+    simulate_sharded(open_sim)                      # warm-up (function attributes, memory pool, NCCL channels)
+    tm = {}
+    barrier()
+    t0 = time.perf_counter()
+    img, _ = simulate_sharded(open_sim, timings=tm)
+    barrier()
+    ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([ms, tm.get("collective_ms", 0.0)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, coll = float(t[0]), float(t[1])
+    assert np.isfinite(img).all() and img.mean() > 0.1
+    out["au_2048_x32"] = {"configs": 32, "grid": [2048, 2048], "slices": 12, "ms": round(ms, 3),
+                          "value": round(2048 * 2048 * 12 * 32 / (ms * 1e-3) / 1e6, 1), "unit": UNIT,
+                          "collective": "all_reduce(SUM) of the partial intensity, 2048^2 float32",
+                          "collective_ms": round(coll, 3), "collective_share": round(coll / ms, 4)}
+    if not a.no_stem:
+        cnf = tmp / "job_stem_512.cnf"
+        atoms = np.ascontiguousarray(specimens.config_srtio3_stem_512(cnf), np.float32)
+        pos = specimens.stem_raster(256)[: a.job_probes]
+        det = np.array([[70.0, 200.0], [11.0, 22.0]], np.float32)
+        open_sim = lambda r, w: fb.Simulation(cnf, atoms6=atoms, gpu_index=local, batch=a.stem_batch)
+        barrier()
+        t0 = time.perf_counter()
+        sig = stem_scan_sharded(open_sim, pos, det)
+        barrier()
+        ms = (time.perf_counter() - t0) * 1e3
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        assert sig.shape == (len(pos), 2) and np.isfinite(sig).all()
+        out["stem_256x256"] = {"probes": int(len(pos)), "grid": [512, 512], "slices": 40, "ms": round(ms, 3),
+                               "value": round(len(pos) / (ms * 1e-3), 1), "unit": "probes/s",
+                               "collective": "all_gather of the detector signals [probes][2] float32"}
+    out["scaling"] = "strong"
+    return out
 
 
 def cpu_baseline(cnf, budget_s):
@@ -321,11 +405,12 @@ def run_reference(a):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_harness not built (needs /root/reference + make -C oracle)"}))
         return
     from fdes_b200 import specimens
-    # Bounded sample: the reference needs 0.1 - 1 s per configuration of this workload, so a step
-    # is `ref_configs` configurations (default 2, not the 16 of our arm -- the metric is per
-    # pixel*slice) and the run stops after --ref-seconds even if fewer than --steps steps are done
-    # (the line reports the steps that were timed).
-    cps = a.ref_configs
+    # Bounded sample of our arm's workload: the reference needs 0.1 - 1 s per configuration, so a
+    # step of this arm is `ref_configs` configurations of the step our arm runs (the metric is per
+    # pixel*slice; 16 per call keep the reference's fixed per-call cost below 5 %), and the run stops
+    # after --ref-seconds even if fewer than --steps steps are done (the line reports the steps timed).
+    cps = a.ref_configs or REF_SAMPLE_CONFIGS[a.workload]
+    our_cps = a.configs_per_step or DEFAULT_CONFIGS_PER_STEP[a.workload]
     tmp = pathlib.Path(tempfile.mkdtemp(prefix="fdes_bench_ref_"))
     cnf = tmp / f"{a.workload}.cnf"
     atoms = getattr(specimens, WORKLOADS[a.workload][0])(cnf, frozen_phonons=cps)
@@ -346,14 +431,15 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world,
         "steps": j["reps"], "steps_requested": a.steps, "warmup": a.warmup, "ms_per_step": round(j["ms_per_call"], 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "complex64 (f32)", "data": "synthetic",
-        "config": {"workload": a.workload, "description": WORKLOADS[a.workload][1], "grid": [j["m1"], j["m2"]],
-                   "slices": j["slices"], "atoms": int(len(atoms)), "configs_per_step_per_gpu": cps,
-                   "note": "unmodified reference (cuFFT/cuBLAS build for sm_100) on ONE B200: FDES has no CPU or "
-                           "multi-GPU path; whole-call wall time of its exported flow (getParams -> "
-                           "readAtomsFromArray -> buildMeasurements -> image copy)"},
+        "config": workload_config(a, our_cps, world),
+        "shape": {"grid": [j["m1"], j["m2"]], "slices": j["slices"], "atoms": int(len(atoms))},
+        "note": "unmodified reference (cuFFT/cuBLAS build for sm_100) on ONE B200: FDES has no CPU or multi-GPU path; "
+                "whole-call wall time of its exported flow (getParams -> readAtomsFromArray -> buildMeasurements -> "
+                "image copy)",
         "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": 1, "kind": "reference",
-                         "sample": f"{j['reps']} call(s) x {cps} configurations x {j['slices']} slices (bounded to {a.ref_seconds:.0f} s); 1 host thread "
-                                   "driving 1 B200 (the reference's only implementation is CUDA)"},
+                         "sample": f"{j['reps']} call(s), each {cps} of the {our_cps} configurations of a step x {j['slices']} slices "
+                                   f"(bounded to {a.ref_seconds:.0f} s); 1 host thread driving 1 B200 (the reference's only "
+                                   "implementation is CUDA)"},
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "clocks": clk.summary(),
         "slice_loop_only": j2[-1] if j2 else None,
@@ -364,14 +450,16 @@ def run_reference(a):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="si001_1024", choices=sorted(WORKLOADS))
     ap.add_argument("--configs-per-step", type=int, default=0)
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--ref-configs", type=int, default=2)
+    ap.add_argument("--ref-configs", type=int, default=0)
+    ap.add_argument("--no-job", action="store_true")
+    ap.add_argument("--job-probes", type=int, default=65536)
     ap.add_argument("--ref-seconds", type=float, default=120.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stem", action="store_true")

@@ -205,6 +205,7 @@ class Simulation:
         self._ck(self._lib.fdes_b200_get_scalars(h, _fp(s)))
         self.lam, self.sigma, self.gamma, self.d1, self.d2, self.d3, self.E0, self.imPot = map(float, s)
         self.want_exitwave = want_exitwave
+        self.gpu_index = int(gpus[0]) if gpus is not None else int(gpu_index)
         self.num_gpus = int(self._lib.fdes_b200_num_gpus(h))
 
     def _ck(self, rc):

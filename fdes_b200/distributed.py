@@ -31,14 +31,16 @@ def shard_range(count: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def simulate_sharded(open_sim: Callable[[int, int], object], *, want_exitwave: bool = False, group=None,
-                     device=None):
+                     device=None, timings: Optional[dict] = None):
     """Run a whole simulation with the configurations sharded over the ranks of `group`.
 
     open_sim(rank, world) must return an object with the session interface of
     fdes_b200.Simulation (n1 n2 n3 m1 m2, set_accumulators, run_k, finish_k, close) that handles
     this rank's share.  Returns (image [n3, n2, n1] float32, exitwave [n3, m2, m1] complex64 | None)
-    -- identical on every rank.
+    -- identical on every rank.  `timings` (optional dict) receives "collective_ms": the time this
+    rank spent in the all-reduces (CUDA events on GPUs, wall clock on CPU).
     """
+    import time
     import torch
     import torch.distributed as dist
 
@@ -46,25 +48,46 @@ def simulate_sharded(open_sim: Callable[[int, int], object], *, want_exitwave: b
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     sim = open_sim(rank, world)
     try:
-        dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
-                                                 if torch.cuda.is_available() else torch.device("cpu"))
+        # the accumulators must live on the device the session computes on (not torch's current one)
+        if device is not None:
+            dev = torch.device(device)
+        elif torch.cuda.is_available() and getattr(sim, "gpu_index", None) is not None:
+            dev = torch.device("cuda", int(sim.gpu_index))
+        else:
+            dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
         acc_I = torch.zeros(sim.m2 * sim.m1, dtype=torch.float32, device=dev)
         acc_E = torch.zeros(sim.m2 * sim.m1 * 2, dtype=torch.float32, device=dev) if want_exitwave else None
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)        # torch's fill runs on torch's stream, the engine on its own
         sim.set_accumulators(acc_I.data_ptr(), acc_E.data_ptr() if acc_E is not None else 0)
+        coll_ms = 0.0
         image = np.zeros((sim.n3, sim.n2, sim.n1), np.float32)
         exitwave = np.zeros((sim.n3, sim.m2, sim.m1), np.complex64) if want_exitwave else None
         for k in range(sim.n3):
             sim.run_k(k)                       # partial sums of this rank's configurations
             if world > 1:
+                if dev.type == "cuda":
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    with torch.cuda.device(dev):
+                        e0.record()
+                else:
+                    t0 = time.perf_counter()
                 dist.all_reduce(acc_I, op=dist.ReduceOp.SUM, group=group)
                 if acc_E is not None:
                     dist.all_reduce(acc_E, op=dist.ReduceOp.SUM, group=group)
                 if dev.type == "cuda":
+                    with torch.cuda.device(dev):
+                        e1.record()
                     torch.cuda.synchronize(dev)
+                    coll_ms += e0.elapsed_time(e1)
+                else:
+                    coll_ms += (time.perf_counter() - t0) * 1e3
             img, ew = sim.finish_k(k)          # detector tail on the reduced intensity
             image[k] = img
             if exitwave is not None:
                 exitwave[k] = ew
+        if timings is not None:
+            timings["collective_ms"] = coll_ms
         return image, exitwave
     finally:
         sim.close()
