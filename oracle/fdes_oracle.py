@@ -539,8 +539,9 @@ def forward_propagation(psi, V, p: Params, P=None, mask=None):
 # --------------------------------------------------------------------------------------
 # float64 evaluation of the same model (error budget of long slice chains)
 # --------------------------------------------------------------------------------------
-def exit_wave_fp64(p_in: Params, Z, xyz, occ) -> np.ndarray:
-    """Plane-wave exit wave (no frozen phonons, k = 0) of the SAME model evaluated in float64 /
+def exit_wave_fp64(p_in: Params, Z, xyz, occ, psi0: Optional[np.ndarray] = None) -> np.ndarray:
+    """Exit wave (no frozen phonons, k = 0; plane wave, or the incident wave psi0 -- e.g. the float32
+    probe of incoming_wave -- taken as exact) of the SAME model evaluated in float64 /
     complex128: identical float32 parameters (lambda, sigma, pixel sizes), identical bin decisions
     and bilinear weights (they are exact float32 quantities, src/crystalMaker.cu:85-119), but the
     scattering factors, exponentials and all transforms in double precision.  A float32 program that
@@ -577,7 +578,7 @@ def exit_wave_fp64(p_in: Params, Z, xyz, occ) -> np.ndarray:
     fft = lambda a: sfft.fft2(a, workers=_WORKERS)
     ifft = lambda a: sfft.ifft2(a, norm="forward", workers=_WORKERS)
     occ64 = np.asarray(occ, f32).astype(f64)
-    psi = np.ones((m2, m1), c128)
+    psi = np.ones((m2, m1), c128) if psi0 is None else np.asarray(psi0).astype(c128)
     Zarr = np.asarray(Z)
     imPot = f64(f32(p.imPot))
     for s in range(p.m3):
