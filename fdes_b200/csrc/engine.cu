@@ -165,7 +165,7 @@ Engine::Engine(const Params& pin, const Atoms& atoms, const EngineOptions& opt) 
                                  "uses a transposed cuFFT plan for m1 != m2, src/crystalMaker.cu:575)");
     if (!fft_size_supported(p_.m1))
         throw std::runtime_error("grid size " + std::to_string(p_.m1) +
-                                 " unsupported: sample size (image + 2*border) must be a power of two in [64, 4096] or 320, 800, 1000");
+                                 " unsupported: sample size (image + 2*border) must be even and between 8 and 8192");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         throw std::runtime_error("no CUDA device: fdes_b200 has no CPU fallback");
@@ -307,6 +307,9 @@ void Engine::setup_tables()
     g_.lo_end = ((kb + 1 + 31) / 32) * 32;
     g_.hi_start = ((N_ - kb) / 32) * 32;
     if (g_.lo_end >= g_.hi_start) { g_.lo_end = N_; g_.hi_start = N_; }
+    // sizes without a register-resident instantiation run on the generic sweeps, which transform
+    // every column (the band limit is applied by the mask alone)
+    if (!fft_size_is_fast(N_)) { g_.lo_end = N_; g_.hi_start = N_; }
 
     launch_propagator_table(Pq_, N_, p_.d1, p_.d2, p_.d3, p_.lambda, p_.cst_pi, st_);
     const size_t Q = (size_t)(N_ / 2 + 1);

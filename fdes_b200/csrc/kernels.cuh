@@ -21,6 +21,7 @@ struct SweepGeom {
 std::vector<cpx> make_twiddles(int N);
 
 bool fft_size_supported(int N);
+bool fft_size_is_fast(int N);   // register-resident kernels (else the generic run-time-N sweeps)
 int rows_per_block(int N);
 int cols_per_block(int N);
 

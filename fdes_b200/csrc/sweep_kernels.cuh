@@ -1192,7 +1192,7 @@ void launch_detector_cols_n(const SweepGeom& g, const cpx* Psi, float* partial, 
 // twiddle tables (layout: fft_core.cuh) and geometry queries
 // ---------------------------------------------------------------------------------------------
 template <int N>
-std::vector<cpx> make_twiddles_n()
+std::vector<cpx> make_twiddles_n(int = 0)
 {
     constexpr int E = LineCfg<N>::E;
     std::vector<cpx> tw;

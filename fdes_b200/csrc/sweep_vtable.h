@@ -31,8 +31,14 @@ struct SweepVTable {
     void (*probe_cols)(const SweepGeom&, cpx*, const cpx*, const float*, int, cudaStream_t);
     int (*detector_tiles)(const SweepGeom&);
     void (*detector_cols)(const SweepGeom&, const cpx*, float*, float*, const DetectorRings&, float, float, float, int, cudaStream_t);
-    std::vector<cpx> (*make_twiddles)();
+    std::vector<cpx> (*make_twiddles)(int N);
 };
+
+// any other even size: mixed-radix line transforms in shared memory with run-time N (generic_sweeps.cu)
+bool generic_size_supported(int N);
+const SweepVTable* generic_sweep_vtable();
+// true when N runs on the register-resident kernels (band-limited column range, pair packing ...)
+bool fft_size_is_fast(int N);
 
 // one per size, defined in that size's translation unit
 #define FDES_DECLARE_VT(N_) const SweepVTable* sweep_vtable_##N_();

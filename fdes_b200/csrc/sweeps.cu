@@ -8,7 +8,7 @@
 
 namespace fdes {
 
-static const SweepVTable* find_vtable(int N)
+static const SweepVTable* find_fast_vtable(int N)
 {
     switch (N) {
 #define FDES_VT_CASE(N_) case N_: return sweep_vtable_##N_();
@@ -17,15 +17,21 @@ static const SweepVTable* find_vtable(int N)
         default: return nullptr;
     }
 }
+static const SweepVTable* find_vtable(int N)
+{
+    if (const SweepVTable* t = find_fast_vtable(N)) return t;
+    return generic_size_supported(N) ? generic_sweep_vtable() : nullptr;
+}
 static const SweepVTable& vt(int N)
 {
     const SweepVTable* t = find_vtable(N);
-    if (!t) throw std::runtime_error("grid size " + std::to_string(N) + " has no fast sweep instantiation");
+    if (!t) throw std::runtime_error("grid size " + std::to_string(N) + " unsupported: sample size (image + 2*border) must be even, 8 .. 8192");
     return *t;
 }
 
 bool fft_size_supported(int N) { return find_vtable(N) != nullptr; }
-std::vector<cpx> make_twiddles(int N) { return vt(N).make_twiddles(); }
+bool fft_size_is_fast(int N) { return find_fast_vtable(N) != nullptr; }
+std::vector<cpx> make_twiddles(int N) { return vt(N).make_twiddles(N); }
 int rows_per_block(int N) { return vt(N).rows_per_block; }
 int cols_per_block(int N) { return vt(N).cols_per_block; }
 

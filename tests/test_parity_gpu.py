@@ -22,7 +22,8 @@ HARNESS = ROOT / "oracle" / "_ref" / "ref_harness"
 # ---------------------------------------------------------------------------------------------
 # building blocks
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048, 4096, 320, 800, 1000])
+@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048, 4096, 320, 800, 1000,
+                               8, 30, 96, 250, 600, 686, 1022, 1536, 2500])     # second line: generic run-time-N sweeps
 def test_fft2d_against_numpy(n, fb):
     rng = np.random.default_rng(n)
     a = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(np.complex64)
@@ -200,9 +201,9 @@ def test_cli_binary(orc, tmp_path, oracle_runs):
 
 def test_unsupported_inputs_fail_loudly(fb, tmp_path):
     from fdes_b200 import specimens
-    specimens.write_cnf(tmp_path / "odd.cnf", image_size=40, border_size=20, slices=2, pixel_size=0.25e-10,
+    specimens.write_cnf(tmp_path / "odd.cnf", image_size=41, border_size=20, slices=2, pixel_size=0.25e-10,
                         slice_thickness=2e-10, atoms=specimens.au_cuboctahedron(1))
-    with pytest.raises(fb.FdesError, match="power of two"):
+    with pytest.raises(fb.FdesError, match="must be even"):
         fb.Simulation(tmp_path / "odd.cnf")
     with pytest.raises(fb.FdesError, match="cannot read"):
         fb.Simulation(tmp_path / "missing.cnf")
@@ -292,10 +293,13 @@ def test_random_4096_against_oracle(fb, orc, tmp_path):
     _oracle_vs_library(cnf, fb, orc)
 
 
-@pytest.mark.parametrize("n,border,mode", [(320, 80, 0), (800, 200, 0), (1000, 170, 0), (320, 0, 2), (800, 100, 1)])
+@pytest.mark.parametrize("n,border,mode", [(320, 80, 0), (800, 200, 0), (1000, 170, 0), (320, 0, 2), (800, 100, 1),
+                                           (600, 100, 0), (384, 64, 0), (250, 25, 2), (686, 43, 1), (146, 13, 0)])
 def test_mixed_radix_grids_against_oracle(n, border, mode, fb, orc, tmp_path):
-    """The 2^a 5^b grids of the reference's shipped examples (Au 320^2, SrTiO3 800^2, Si 1000^2):
-    radix-5 passes, lines of 16 / 40 / 50 threads."""
+    """The 2^a 5^b grids of the reference's shipped examples (Au 320^2, SrTiO3 800^2, Si 1000^2:
+    radix-5 passes, lines of 16 / 40 / 50 threads) and sizes without a register-resident instantiation,
+    which run on the generic run-time-N sweeps (generic_sweeps.cu): 600 = 2^3 3 5^2, 384 = 2^7 3,
+    250 = 2 5^3, 686 = 2 7^3, 146 = 2 * 73 (a radix-73 pass)."""
     from fdes_b200 import specimens
     cnf = tmp_path / f"g{n}.cnf"
     d = 0.2e-10

@@ -127,3 +127,30 @@ def test_srtio3_800_400_subslices_error_budget(fb, orc, qorc, tmp_path):
     assert d["ours-ref"] < TOL_WAVE or d["ours-fp64"] <= 1.25 * d["ref-fp64"], d
     assert d["ours-fp64"] < 3 * TOL_WAVE
     assert d["image ours-ref"] < TOL_INTENSITY
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_random_grid_sizes_against_live_reference(seed, fb, tmp_path):
+    """Any even sample size the reference accepts (m = n + 2 dn, src/paramStructure.cu:650-651): random
+    image / border sizes, random mode, 3 species, against the unmodified reference run on the same input.
+    Sizes without a register-resident instantiation take the generic run-time-N sweeps."""
+    from fdes_b200 import specimens
+    rng = np.random.default_rng(1000 + seed)
+    n = 2 * int(rng.integers(32, 500))
+    dn = int(rng.integers(0, 200))
+    m = n + 2 * dn
+    mode = int(rng.integers(0, 3))
+    d = 0.2e-10
+    atoms = specimens.random_slab(120, m * d, 6 * 2e-10, seed=seed, species=(79, 14, 8))
+    cnf = specimens.write_cnf(tmp_path / f"g{m}.cnf", image_size=n, border_size=dn, slices=6, pixel_size=d,
+                              slice_thickness=2e-10, atoms=atoms, voltage=150e3, mode=mode, absorptive=0.04,
+                              objective_aperture=0.012, frozen_phonons=2 if mode == 0 else 0, mtf=(0.58, 0.42, 2.7, 15.5),
+                              aberrations={"C1": (-2e-8, 0.0), "C3": (3e-4, 0.0)})
+    with fb.Simulation(cnf, want_exitwave=True) as sim:
+        assert sim.m1 == m
+        img, ew = sim.simulate()
+    rimg, rew = _ref_run(cnf, tmp_path / "ref", img.shape, ew.shape)
+    d_ew, d_img = rel_l2(ew, rew), rel_l2(img, rimg)
+    print(f"grid {m} = {n} + 2 x {dn}, mode {mode}: exit wave {d_ew:.3e}, image {d_img:.3e}")
+    assert d_ew < TOL_WAVE and d_img < TOL_INTENSITY
