@@ -218,8 +218,14 @@ void Engine::init(const Atoms& atoms)
 
     pt.mark("ctor: host prep");
     CK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&st_prep_, cudaStreamNonBlocking));
     CK(cudaEventCreate(&ev0_));
     CK(cudaEventCreate(&ev1_));
+    CK(cudaEventCreateWithFlags(&ev_ready_, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) {
+        CK(cudaEventCreateWithFlags(&ev_prep_[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_used_[i], cudaEventDisableTiming));
+    }
 
     const size_t NN = (size_t)N_ * N_, Q = (size_t)(N_ / 2 + 1);
     tw_host_ = make_twiddles(N_);
@@ -232,10 +238,15 @@ void Engine::init(const Atoms& atoms)
     plan.add(J_, (size_t)p_.n1 * p_.n2);
     if (opt_.want_exitwave) plan.add(ew_own_, NN);
     plan.add(xyz0_, 3 * (size_t)nAt_); plan.add(xyzTO_, 3 * (size_t)nAt_); plan.add(xyzK_, 3 * (size_t)nAt_);
-    plan.add(xyzFP_, (size_t)B_ * 3 * nAt_); plan.add(dwf_, nAt_); plan.add(occ_, nAt_); plan.add(zidx_, nAt_);
-    plan.add(keys_, (size_t)B_ * nrec_); plan.add(cols_, (size_t)B_ * nrec_); plan.add(w_, (size_t)B_ * nrec_);
+    plan.add(dwf_, nAt_); plan.add(occ_, nAt_); plan.add(zidx_, nAt_);
+    // two sets of per-batch atom records: the records of batch i+1 are prepared on a second stream
+    // while the sweeps of batch i read theirs
+    for (RecordSet& r : rs_) {
+        plan.add(r.xyzFP, (size_t)B_ * 3 * nAt_);
+        plan.add(r.keys, (size_t)B_ * nrec_); plan.add(r.cols, (size_t)B_ * nrec_); plan.add(r.w, (size_t)B_ * nrec_);
+        plan.add(r.rowptr, (size_t)B_ * rp_stride_);
+    }
     plan.add(keys_tmp_, (size_t)B_ * nrec_); plan.add(cols_tmp_, (size_t)B_ * nrec_); plan.add(w_tmp_, (size_t)B_ * nrec_);
-    plan.add(rowptr_, (size_t)B_ * rp_stride_);
     plan.add(bins_, 4 * (size_t)nAt_);
     plan.add(hist_, (size_t)B_ * 256 * sort_num_blocks(nrec_));
     plan.add(norm_partial_, 256); plan.add(norm_result_, 1);
@@ -285,11 +296,18 @@ Engine::~Engine()
 
 void Engine::release()
 {
-    if (graph_) { cudaGraphExecDestroy(graph_); graph_ = nullptr; }
+    for (cudaGraphExec_t& g : graph_) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    if (st_prep_) cudaStreamSynchronize(st_prep_);
     if (st_) cudaStreamSynchronize(st_);
     if (arena_) { pool_release(arena_); arena_ = nullptr; }
     if (ev0_) { cudaEventDestroy(ev0_); ev0_ = nullptr; }
     if (ev1_) { cudaEventDestroy(ev1_); ev1_ = nullptr; }
+    if (ev_ready_) { cudaEventDestroy(ev_ready_); ev_ready_ = nullptr; }
+    for (int i = 0; i < 2; i++) {
+        if (ev_prep_[i]) { cudaEventDestroy(ev_prep_[i]); ev_prep_[i] = nullptr; }
+        if (ev_used_[i]) { cudaEventDestroy(ev_used_[i]); ev_used_[i] = nullptr; }
+    }
+    if (st_prep_) { cudaStreamDestroy(st_prep_); st_prep_ = nullptr; }
     if (st_) { cudaStreamDestroy(st_); st_ = nullptr; }
 }
 
@@ -400,24 +418,31 @@ void Engine::make_incident(int k)
     incident_k_ = k;
 }
 
-// records of `nconf` configurations (slots b0 .. b0+nconf-1) from coordinates [nconf][nAt][3]
-void Engine::bin_and_sort(int b0, int nconf, const float* xyz_dev)
+// records of `nconf` configurations (slots b0 .. b0+nconf-1) from coordinates [nconf][nAt][3], into
+// record set `set` (default: the active one) on stream `st` (default: the engine's)
+void Engine::bin_and_sort(int b0, int nconf, const float* xyz_dev, int set, cudaStream_t st)
 {
+    if (set < 0) set = act_;
+    if (!st) st = st_;
+    const RecordSet& r = rs_[set];
     BinGeom bg{N_, N_, p_.m3, nZ_, p_.d1, p_.d2, p_.d3};
-    uint32_t* keys = keys_ + (size_t)b0 * nrec_;
-    int* cols = cols_ + (size_t)b0 * nrec_;
-    float* w = w_ + (size_t)b0 * nrec_;
-    launch_bin_atoms(xyz_dev, zidx_, occ_, nAt_, bg, keys, cols, w, nullptr, nconf, st_);
+    uint32_t* keys = r.keys + (size_t)b0 * nrec_;
+    int* cols = r.cols + (size_t)b0 * nrec_;
+    float* w = r.w + (size_t)b0 * nrec_;
+    launch_bin_atoms(xyz_dev, zidx_, occ_, nAt_, bg, keys, cols, w, nullptr, nconf, st);
     SortBuffers sb{keys, keys_tmp_, cols, cols_tmp_, w, w_tmp_, hist_};
-    launch_radix_sort(sb, nrec_, key_bits_, nconf, st_);
-    launch_row_pointers(keys, nrec_, rowptr_ + (size_t)b0 * rp_stride_, nkeys_, nconf, st_);
+    launch_radix_sort(sb, nrec_, key_bits_, nconf, st);
+    launch_row_pointers(keys, nrec_, r.rowptr + (size_t)b0 * rp_stride_, nkeys_, nconf, st);
     int passes = (key_bits_ + 7) / 8; if (passes & 1) passes++; if (!passes) passes = 2;
     tm_.kernel_launches += 2 + 3 * passes;
 }
 
 // jitter + bin + sort + row pointers for the configurations of one batch (slots 0 .. nb-1)
-void Engine::prepare_batch(int nb, const float* xyz_k)
+void Engine::prepare_batch(int nb, const float* xyz_k, int set, cudaStream_t st)
 {
+    if (set < 0) set = act_;
+    if (!st) st = st_;
+    float* xyzFP = rs_[set].xyzFP;
     if (p_.frPh > 0) {
         // the XORWOW streams are consumed in the global order (k, j) of the single-GPU reference:
         // skip the normals that belong to configurations of other ranks (or other calls)
@@ -426,20 +451,62 @@ void Engine::prepare_batch(int nb, const float* xyz_k)
             // a configuration before the current stream position (run_k(k) repeated, k visited out
             // of order): start the streams again, so that configuration (k, j) always sees the
             // draws it has in the reference's (k, j) order
-            launch_rng_init(rng_, 3 * nAt_, 1ULL, st_);
+            launch_rng_init(rng_, 3 * nAt_, 1ULL, st);
             rng_pos_ = 0;
             burn = rng_target_;
             tm_.kernel_launches += 1;
         }
-        launch_atom_jitter(xyzFP_, xyz_k, dwf_, nAt_, rng_, burn, nb, st_);
+        launch_atom_jitter(xyzFP, xyz_k, dwf_, nAt_, rng_, burn, nb, st);
         rng_pos_ = rng_target_ + nb;
         rng_target_ = rng_pos_;
         tm_.kernel_launches += 1;
     } else {
         for (int b = 0; b < nb; b++)
-            CK(cudaMemcpyAsync(xyzFP_ + (size_t)b * 3 * nAt_, xyz_k, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
+            CK(cudaMemcpyAsync(xyzFP + (size_t)b * 3 * nAt_, xyz_k, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
-    bin_and_sort(0, nb, xyzFP_);
+    bin_and_sort(0, nb, xyzFP, set, st);
+}
+
+// Configurations [jb, je) of measurement k in batches of B_, with the atom preparation (jitter, binning,
+// radix sort, row pointers: a dozen small launches) of batch i+1 running on the second stream while the
+// sweeps of batch i occupy the GPU.  reference_order: configuration j takes the draws it has in the
+// reference's (k, j) order (run_k); otherwise the streams simply continue (bench_configs).
+void Engine::run_batches(int k, int jb, int je, bool reference_order)
+{
+    const size_t NN = (size_t)N_ * N_;
+    if (je <= jb) return;
+    // xyzK_ and the incident wave were enqueued on st_: the preparation stream starts after them; both
+    // record sets are free (every earlier use was followed by a synchronisation of st_)
+    CK(cudaEventRecord(ev_ready_, st_));
+    CK(cudaStreamWaitEvent(st_prep_, ev_ready_, 0));
+    auto prepare = [&](int j, int set) {
+        const int nb = std::min(B_, je - j);
+        if (reference_order) rng_target_ = (long long)k * count_ + j;   // position of configuration (k, j)
+        prepare_batch(nb, xyzK_, set, st_prep_);
+        CK(cudaEventRecord(ev_prep_[set], st_prep_));
+    };
+    int set = 0;
+    prepare(jb, set);
+    for (int j = jb; j < je; j += B_, set ^= 1) {
+        const int nb = std::min(B_, je - j);
+        if (j + B_ < je) {
+            // the other set was last read by the sweeps of batch i-1
+            if (j > jb) CK(cudaStreamWaitEvent(st_prep_, ev_used_[set ^ 1], 0));
+            prepare(j + B_, set ^ 1);
+        }
+        CK(cudaStreamWaitEvent(st_, ev_prep_[set], 0));
+        act_ = set;
+        if (p_.mode != 2 && !p_.doBeamTilt) {
+            launch_plane_wave_rowspace(Psi_, N_, nb, st_);     // psi_in_ is the plane wave: write it directly
+        } else {
+            for (int b = 0; b < nb; b++)
+                CK(cudaMemcpyAsync(Psi_ + (size_t)b * NN, psi_in_, NN * sizeof(cpx), cudaMemcpyDeviceToDevice, st_));
+        }
+        slice_loop(nb);
+        CK(cudaEventRecord(ev_used_[set], st_));
+        accumulate_outputs(k, nb);
+    }
+    act_ = 0;
 }
 
 void Engine::run_slices_plain(int nb)
@@ -451,8 +518,8 @@ void Engine::run_slices_plain(int nb)
     for (int s = 0; s < p_.m3; s += 2) {
         const int npair = std::min(2, p_.m3 - s);
         const int s2 = npair > 1 ? s + 1 : -1;
-        launch_density_rows(g_, A_, rowptr_, cols_, w_, s, s2, nZ_, nb, rec_stride_, rp_stride_, st_);
-        launch_potential_cols(g_, W_, A_, Gq_, rowptr_, s, s2, nZ_, nb, rp_stride_, st_);
+        launch_density_rows(g_, A_, rs_[act_].rowptr, rs_[act_].cols, rs_[act_].w, s, s2, nZ_, nb, rec_stride_, rp_stride_, st_);
+        launch_potential_cols(g_, W_, A_, Gq_, rs_[act_].rowptr, s, s2, nZ_, nb, rp_stride_, st_);
         launch_transmit_rows(g_, W_, D_, npair, p_.imPot, nb, st_);
         launch_bandlimit_cols(g_, D_, nb, npair, st_);
         for (int p = 0; p < npair; p++) {
@@ -470,6 +537,8 @@ void Engine::slice_loop(int nb)
     // a CUDA graph pays off when the sweeps are launch-bound (small grids, small batches); its
     // capture + instantiation costs about a millisecond, more than it saves on large launches
     if (!opt_.use_graph || (size_t)nb * N_ * N_ > ((size_t)1 << 21)) { run_slices_plain(nb); return; }
+    cudaGraphExec_t& graph_ = this->graph_[act_];     // the captured launches carry the record pointers of a set
+    int& graph_nb_ = this->graph_nb_[act_];
     if (!graph_ || graph_nb_ != nb) {
         if (graph_) { cudaGraphExecDestroy(graph_); graph_ = nullptr; }
         // first use of each kernel must happen outside capture (function attributes are set there)
@@ -553,16 +622,9 @@ void Engine::run_k(int k)
     CK(cudaMemcpyAsync(xyzK_, xyzTO_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
     tilt(xyzK_, p_.tiltspec[2 * k], p_.tiltspec[2 * k + 1], 0.f);
     make_incident(k);
-    for (int j = j0_; j < j1_; j += B_) {
-        const int nb = std::min(B_, j1_ - j);
-        rng_target_ = (long long)k * count_ + j;   // position of configuration (k, j)
-        prepare_batch(nb, xyzK_);
-        for (int b = 0; b < nb; b++)
-            CK(cudaMemcpyAsync(Psi_ + (size_t)b * NN, psi_in_, NN * sizeof(cpx), cudaMemcpyDeviceToDevice, st_));
-        slice_loop(nb);
-        accumulate_outputs(k, nb);
-    }
+    run_batches(k, j0_, j1_, true);
     pt.mark("run_k: enqueue");
+    CK(cudaStreamSynchronize(st_prep_));
     CK(cudaStreamSynchronize(st_));
     pt.mark("run_k: wait");
 }
@@ -666,8 +728,8 @@ void Engine::potential_slices(float* out_host)
     bin_and_sort(0, 1, xyzTO_);
     RowOpts ro; ro.scale = 1.f;
     for (int s = 0; s < m3_orig_; s++) {
-        launch_density_rows(g_, A_, rowptr_, cols_, w_, s, -1, nZ_, 1, rec_stride_, rp_stride_, st_);
-        launch_potential_cols(g_, W_, A_, Gq_, rowptr_, s, -1, nZ_, 1, rp_stride_, st_);
+        launch_density_rows(g_, A_, rs_[act_].rowptr, rs_[act_].cols, rs_[act_].w, s, -1, nZ_, 1, rec_stride_, rp_stride_, st_);
+        launch_potential_cols(g_, W_, A_, Gq_, rs_[act_].rowptr, s, -1, nZ_, 1, rp_stride_, st_);
         launch_rows_fft(g_, W_, scratch_, +1, ROW_STORE, ro, 1, st_);
         launch_absorptive_factor(scratch_, NN, p_.imPot, st_);
         CK(cudaMemcpyAsync(out_host + (size_t)s * 2 * NN, scratch_, NN * sizeof(cpx), cudaMemcpyDeviceToHost, st_));
@@ -685,18 +747,18 @@ void Engine::next_jittered_coords(int k, float* xyz_host)
     DeviceGuard guard(opt_.gpu_index);
     CK(cudaMemcpyAsync(xyzK_, xyzTO_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
     tilt(xyzK_, p_.tiltspec[2 * k], p_.tiltspec[2 * k + 1], 0.f);
-    if (p_.frPh > 0) { launch_atom_jitter(xyzFP_, xyzK_, dwf_, nAt_, rng_, 0, 1, st_); rng_pos_ += 1; rng_target_ = rng_pos_; }
-    else CK(cudaMemcpyAsync(xyzFP_, xyzK_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
-    CK(cudaMemcpyAsync(xyz_host, xyzFP_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToHost, st_));
+    if (p_.frPh > 0) { launch_atom_jitter(rs_[act_].xyzFP, xyzK_, dwf_, nAt_, rng_, 0, 1, st_); rng_pos_ += 1; rng_target_ = rng_pos_; }
+    else CK(cudaMemcpyAsync(rs_[act_].xyzFP, xyzK_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
+    CK(cudaMemcpyAsync(xyz_host, rs_[act_].xyzFP, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToHost, st_));
     CK(cudaStreamSynchronize(st_));
 }
 
 void Engine::bin_tuples(const float* xyz_host, int* bins_host)
 {
     DeviceGuard guard(opt_.gpu_index);
-    CK(cudaMemcpyAsync(xyzFP_, xyz_host, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyHostToDevice, st_));
+    CK(cudaMemcpyAsync(rs_[act_].xyzFP, xyz_host, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyHostToDevice, st_));
     BinGeom bg{N_, N_, p_.m3, nZ_, p_.d1, p_.d2, p_.d3};
-    launch_bin_atoms(xyzFP_, zidx_, occ_, nAt_, bg, keys_, cols_, w_, bins_, 1, st_);
+    launch_bin_atoms(rs_[act_].xyzFP, zidx_, occ_, nAt_, bg, rs_[act_].keys, rs_[act_].cols, rs_[act_].w, bins_, 1, st_);
     CK(cudaMemcpyAsync(bins_host, bins_, 4 * (size_t)nAt_ * sizeof(int), cudaMemcpyDeviceToHost, st_));
     CK(cudaStreamSynchronize(st_));
 }
@@ -705,10 +767,10 @@ void Engine::phase_grating(const float* xyz_host, int s, float* V_host)
 {
     DeviceGuard guard(opt_.gpu_index);
     const size_t NN = (size_t)N_ * N_;
-    CK(cudaMemcpyAsync(xyzFP_, xyz_host, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyHostToDevice, st_));
-    bin_and_sort(0, 1, xyzFP_);
-    launch_density_rows(g_, A_, rowptr_, cols_, w_, s, -1, nZ_, 1, rec_stride_, rp_stride_, st_);
-    launch_potential_cols(g_, W_, A_, Gq_, rowptr_, s, -1, nZ_, 1, rp_stride_, st_);
+    CK(cudaMemcpyAsync(rs_[act_].xyzFP, xyz_host, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyHostToDevice, st_));
+    bin_and_sort(0, 1, rs_[act_].xyzFP);
+    launch_density_rows(g_, A_, rs_[act_].rowptr, rs_[act_].cols, rs_[act_].w, s, -1, nZ_, 1, rec_stride_, rp_stride_, st_);
+    launch_potential_cols(g_, W_, A_, Gq_, rs_[act_].rowptr, s, -1, nZ_, 1, rp_stride_, st_);
     RowOpts ro;
     launch_rows_fft(g_, W_, scratch_, +1, ROW_STORE, ro, 1, st_);
     launch_absorptive_factor(scratch_, NN, p_.imPot, st_);
@@ -720,8 +782,8 @@ void Engine::exit_wave(const float* xyz_host, int k, float* psi_host)
 {
     DeviceGuard guard(opt_.gpu_index);
     const size_t NN = (size_t)N_ * N_;
-    CK(cudaMemcpyAsync(xyzFP_, xyz_host, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyHostToDevice, st_));
-    bin_and_sort(0, 1, xyzFP_);
+    CK(cudaMemcpyAsync(rs_[act_].xyzFP, xyz_host, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyHostToDevice, st_));
+    bin_and_sort(0, 1, rs_[act_].xyzFP);
     make_incident(k);
     CK(cudaMemcpyAsync(Psi_, psi_in_, NN * sizeof(cpx), cudaMemcpyDeviceToDevice, st_));
     const bool ug = opt_.use_graph;
@@ -745,18 +807,12 @@ double Engine::bench_configs(int k, int configs)
     make_incident(k);
     CK(cudaStreamSynchronize(st_));
     CK(cudaEventRecord(ev0_, st_));
-    for (int j = 0; j < configs; j += B_) {
-        const int nb = std::min(B_, configs - j);
-        prepare_batch(nb, xyzK_);
-        for (int b = 0; b < nb; b++)
-            CK(cudaMemcpyAsync(Psi_ + (size_t)b * NN, psi_in_, NN * sizeof(cpx), cudaMemcpyDeviceToDevice, st_));
-        slice_loop(nb);
-        accumulate_outputs(k, nb);
-    }
+    run_batches(k, 0, configs, false);
     CK(cudaEventRecord(ev1_, st_));
     CK(cudaEventSynchronize(ev1_));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    CK(cudaStreamSynchronize(st_prep_));
     tm_.slice_loop_ms += ms;
     return (double)ms;
 }
@@ -819,8 +875,8 @@ void Engine::stem_scan(int k, int nprobes, const float* xy_host, int ndet, const
             for (int s = 0; s < p_.m3; s += 2) {   // transmission stack of this configuration
                 const int npair = std::min(2, p_.m3 - s);
                 const int s2 = npair > 1 ? s + 1 : -1;
-                launch_density_rows(g_, A_, rowptr_, cols_, w_, s, s2, nZ_, 1, rec_stride_, rp_stride_, st_);
-                launch_potential_cols(g_, W_, A_, Gq_, rowptr_, s, s2, nZ_, 1, rp_stride_, st_);
+                launch_density_rows(g_, A_, rs_[act_].rowptr, rs_[act_].cols, rs_[act_].w, s, s2, nZ_, 1, rec_stride_, rp_stride_, st_);
+                launch_potential_cols(g_, W_, A_, Gq_, rs_[act_].rowptr, s, s2, nZ_, 1, rp_stride_, st_);
                 launch_transmit_rows(g_, W_, tstack + (size_t)s * NN, npair, p_.imPot, 1, st_);
                 launch_bandlimit_cols(g_, tstack + (size_t)s * NN, 1, npair, st_);
             }
@@ -862,7 +918,7 @@ void Engine::time_sweeps(int k, int nb, int reps, float* ms6)
     CK(cudaMemcpyAsync(xyzK_, xyzTO_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
     make_incident(k);
     for (int b = 0; b < nb; b++) {
-        float* fp = xyzFP_ + (size_t)b * 3 * nAt_;
+        float* fp = rs_[act_].xyzFP + (size_t)b * 3 * nAt_;
         CK(cudaMemcpyAsync(fp, xyzK_, 3 * (size_t)nAt_ * sizeof(float), cudaMemcpyDeviceToDevice, st_));
         bin_and_sort(b, 1, fp);
         CK(cudaMemcpyAsync(Psi_ + (size_t)b * NN, psi_in_, NN * sizeof(cpx), cudaMemcpyDeviceToDevice, st_));
@@ -876,8 +932,8 @@ void Engine::time_sweeps(int k, int nb, int reps, float* ms6)
         for (int r = -1; r < reps; r++) {   // r = -1: untimed warm-up launch
             if (r == 0) CK(cudaEventRecord(ev0_, st_));
             switch (i) {
-                case 0: launch_density_rows(g_, A_, rowptr_, cols_, w_, s, s2, nZ_, nb, rec_stride_, rp_stride_, st_); break;
-                case 1: launch_potential_cols(g_, W_, A_, Gq_, rowptr_, s, s2, nZ_, nb, rp_stride_, st_); break;
+                case 0: launch_density_rows(g_, A_, rs_[act_].rowptr, rs_[act_].cols, rs_[act_].w, s, s2, nZ_, nb, rec_stride_, rp_stride_, st_); break;
+                case 1: launch_potential_cols(g_, W_, A_, Gq_, rs_[act_].rowptr, s, s2, nZ_, nb, rp_stride_, st_); break;
                 case 2: launch_transmit_rows(g_, W_, D_, npair, p_.imPot, nb, st_); break;
                 case 3: launch_bandlimit_cols(g_, D_, nb, npair, st_); break;
                 case 4: launch_multiply_rows(g_, Psi_, D_, 2 * NN, nb, false, st_); break;

@@ -92,8 +92,10 @@ private:
     void release();                                 // stream, events, arena, graph
     void setup_tables();
     void make_incident(int k);                      // psi_in_ (row space) for index k
-    void prepare_batch(int nb, const float* xyz_k);  // jitter + bin + sort + rowptr of a batch
-    void bin_and_sort(int b0, int nconf, const float* xyz_dev);
+    // jitter + bin + sort + rowptr of a batch into record set `set` (-1: the active one) on stream st (null: st_)
+    void prepare_batch(int nb, const float* xyz_k, int set = -1, cudaStream_t st = nullptr);
+    void bin_and_sort(int b0, int nconf, const float* xyz_dev, int set = -1, cudaStream_t st = nullptr);
+    void run_batches(int k, int jb, int je, bool reference_order);   // batches of configurations, preparation overlapped
     void slice_loop(int nb);                        // S1..S6 for all slices, batch nb
     void run_slices_plain(int nb);
     void accumulate_outputs(int k, int nb);
@@ -105,13 +107,22 @@ private:
     int m3_orig_ = 1; float d3_orig_ = 0.f;
     std::vector<int> Zlist_;
     SweepGeom g_{};
-    cudaStream_t st_ = nullptr;
+    cudaStream_t st_ = nullptr, st_prep_ = nullptr;     // sweeps; atom preparation of the next batch
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+    cudaEvent_t ev_ready_ = nullptr, ev_prep_[2] = {nullptr, nullptr}, ev_used_[2] = {nullptr, nullptr};
+    // per-batch atom records (deposit records sorted by (slice, species, row), row pointers, jittered coordinates)
+    struct RecordSet {
+        uint32_t* keys = nullptr;
+        int *cols = nullptr, *rowptr = nullptr;
+        float *w = nullptr, *xyzFP = nullptr;
+    };
+    RecordSet rs_[2];
+    int act_ = 0;               // record set the sweeps read
     // device memory
     cpx *tw_ = nullptr, *Pq_ = nullptr, *psi_in_ = nullptr, *Psi_ = nullptr, *W_ = nullptr, *D_ = nullptr, *A_ = nullptr;
     cpx *ew_ = nullptr, *ew_own_ = nullptr, *lens_ = nullptr, *scratch_ = nullptr;
     float *Gq_ = nullptr, *I_ = nullptr, *I_own_ = nullptr, *det_ = nullptr, *J_ = nullptr;
-    float *xyz0_ = nullptr, *xyzTO_ = nullptr, *xyzK_ = nullptr, *xyzFP_ = nullptr, *dwf_ = nullptr, *occ_ = nullptr;
+    float *xyz0_ = nullptr, *xyzTO_ = nullptr, *xyzK_ = nullptr, *dwf_ = nullptr, *occ_ = nullptr;
     int* zidx_ = nullptr;
     void* rng_ = nullptr;
     unsigned char* rng_bytes_ = nullptr;
@@ -120,16 +131,16 @@ private:
     std::vector<cpx> tw_host_;
     long long rng_pos_ = 0;     // normals every XORWOW stream has produced so far
     long long rng_target_ = 0;  // position of the next configuration in the reference's (k, j) order
-    uint32_t *keys_ = nullptr, *keys_tmp_ = nullptr;
-    int *cols_ = nullptr, *cols_tmp_ = nullptr, *rowptr_ = nullptr, *bins_ = nullptr;
-    float *w_ = nullptr, *w_tmp_ = nullptr;
+    uint32_t* keys_tmp_ = nullptr;
+    int *cols_tmp_ = nullptr, *bins_ = nullptr;
+    float* w_tmp_ = nullptr;
     unsigned int* hist_ = nullptr;
     double *norm_partial_ = nullptr, *norm_result_ = nullptr;
     size_t rec_stride_ = 0, rp_stride_ = 0;
     int nkeys_ = 0, key_bits_ = 0, nrec_ = 0;
     int lens_k_ = -1, incident_k_ = -1;
-    cudaGraphExec_t graph_ = nullptr;
-    int graph_nb_ = 0;
+    cudaGraphExec_t graph_[2] = {nullptr, nullptr};     // slice loop of a batch, per record set
+    int graph_nb_[2] = {0, 0};
     bool warmed_ = false;
     EngineTimings tm_;
 };
