@@ -560,7 +560,7 @@ void Engine::accumulate_outputs(int k, int nb)
     const float alpha = 1.f / ((float)count_);
     if (p_.mode == 0 && lens_k_ != k) {
         // CTF with the 1/N of applyLensFunction folded in (src/multisliceSimulation.cu:614-622)
-        launch_lens_table(lens_, N_, lens_params(p_, k, 0), 1.f, st_);
+        launch_lens_table(lens_, N_, lens_params(p_, k, 0), 1.f, st_, /*transposed=*/true);
         lens_k_ = k;
         tm_.kernel_launches += 1;
     }
@@ -573,8 +573,10 @@ void Engine::accumulate_outputs(int k, int nb)
     }
     if (p_.mode == 0) {
         // W_ is free after the slice loop: CTF-filtered waves of the whole batch
+        // (band columns only where the sweep is pipelined: the wave has no others, and the row sweep below
+        // reads none)
         launch_cols_fft(g_, Psi_, W_, -1, COL_MUL_CPX_INV, lens_, 1.f / ((float)N_), nb, st_);
-        RowOpts ro; ro.scale = alpha;
+        RowOpts ro; ro.scale = alpha; ro.band_only_in = true;
         launch_rows_fft_sum(g_, W_, I_, +1, ROW_INTENS_ACCUM, ro, nb, st_);
         tm_.kernel_launches += 2;
         return;

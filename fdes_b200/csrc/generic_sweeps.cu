@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(GT) g_cols_fft(const cpx* in, void* out_, int 
         const size_t idx = (size_t)i * N + kx0 + l;
         const cpx v = x[l * N + i];
         if (op == COL_MUL_CPX_INV) {
-            const cpx w = static_cast<const cpx*>(table)[idx];
+            const cpx w = static_cast<const cpx*>(table)[(size_t)(kx0 + l) * N + i];     // stored [kx][ky]
             x[l * N + i] = make_float2(w.x * v.x - w.y * v.y, w.x * v.y + w.y * v.x);
         } else {
             const float w = static_cast<const float*>(table)[idx];

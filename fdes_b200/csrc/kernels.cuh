@@ -89,7 +89,8 @@ void launch_rows_fft_sum(const SweepGeom& g, const cpx* in, void* out, int dir, 
 
 enum ColOp {
     COL_PLAIN = 0,        // out = FFT_dir(in)
-    COL_MUL_CPX_INV = 1,  // out = IFFT( FFT(in) * tab_c[ky][kx] )      (lens function / CTF)
+    COL_MUL_CPX_INV = 1,  // out = IFFT( FFT(in) * tab_c[kx][ky] )      (lens function / CTF; table stored ky-fastest;
+                          // `in` must be zero outside the band columns, and only those columns of `out` are defined)
     COL_MUL_REAL_INV = 2, // out = IFFT( FFT(in) * tab_r[ky][kx] )      (MTF / incoherence)
     COL_DP_ACCUM = 3      // outI[fftshift(ky,kx)] += scale * |FFT(in)|^2   (diffraction pattern)
 };
@@ -113,7 +114,8 @@ struct LensParams {
 };
 // full [N][N] complex table of multiplyLensFunction (src/multisliceSimulation.cu:277-343);
 // 0 outside the aperture; extra_scale folded in.
-void launch_lens_table(cpx* tab, int N, const LensParams& lp, float extra_scale, cudaStream_t st);
+// transposed: entry (kx, ky) at kx * N + ky -- the layout COL_MUL_CPX_INV reads (a column's threads walk ky)
+void launch_lens_table(cpx* tab, int N, const LensParams& lp, float extra_scale, cudaStream_t st, bool transposed = false);
 // full [N][N] real table: MTF * (optional spatial incoherence) * scale
 // (src/multisliceSimulation.cu:362-442)
 struct DetectorParams {

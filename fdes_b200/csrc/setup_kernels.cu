@@ -82,11 +82,13 @@ void launch_propagator_table(cpx* Pq, int N, float d1, float d2, float d3, float
 // lens function (multiplyLensFunction, src/multisliceSimulation.cu:277-343): full table, the
 // factor the wave is multiplied with; zero outside the objective aperture.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_lens_table(cpx* __restrict__ tab, int N, LensParams lp, float extra_scale)
+// transposed: the entry of (kx, ky) is stored at kx * N + ky (ky fastest), the order in which the T
+// threads of a column sweep read it (COL_MUL_CPX_INV); otherwise at ky * N + kx like an image
+__global__ void k_lens_table(cpx* __restrict__ tab, int N, LensParams lp, float extra_scale, int transposed)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N * N) return;
-    int i1 = i % N, i2 = i / N;
+    int i1 = transposed ? i / N : i % N, i2 = transposed ? i % N : i / N;
     if (i1 > N / 2) i1 -= N;
     if (i2 > N / 2) i2 -= N;
     i2 = -i2;  // row index points up
@@ -106,24 +108,24 @@ __global__ void k_lens_table(cpx* __restrict__ tab, int N, LensParams lp, float 
             + nu * (0.2f * (a0[7] * cosf(5.f * (phi - a1[7])) + a0[8] * cosf(phi - a1[8]) + a0[9] * cosf(3.f * (phi - a1[9])))
             + nu * (1.f / 6.f * (a0[11] * cosf(6.f * (phi - a1[11])) + a0[12] * cosf(4.f * (phi - a1[12]))
                                  + a0[13] * cosf(2.f * (phi - a1[13])) + a0[10]))))));
-        nu2 = lp.lambda;
-        float damp = 1.f;
+        // aperture * temporal-coherence envelope * exp(-i chi), chi = 2 pi W / lambda
+        float envelope = 1.f;
         if (lp.mode == 0) {
-            damp = lp.defocspread * nu * nu / nu2;
-            damp = expf(-2.f * damp * damp);
+            const float spread = lp.defocspread * nu * nu / lp.lambda;
+            envelope = expf(-2.f * spread * spread);
         }
-        nu = lp.pi;
-        phi = damp * cosf(2.f * nu * (W / nu2));
-        damp = damp * sinf(-2.f * nu * (W / nu2));
-        out = make_float2(phi * extra_scale, damp * extra_scale);
+        const float chi_over_2pi = W / lp.lambda;
+        const float re = envelope * cosf(2.f * lp.pi * chi_over_2pi);
+        const float im = envelope * sinf(-2.f * lp.pi * chi_over_2pi);
+        out = make_float2(re * extra_scale, im * extra_scale);
     }
     tab[i] = out;
 }
 
-void launch_lens_table(cpx* tab, int N, const LensParams& lp, float extra_scale, cudaStream_t st)
+void launch_lens_table(cpx* tab, int N, const LensParams& lp, float extra_scale, cudaStream_t st, bool transposed)
 {
     const int n = N * N;
-    k_lens_table<<<(n + 255) / 256, 256, 0, st>>>(tab, N, lp, extra_scale);
+    k_lens_table<<<(n + 255) / 256, 256, 0, st>>>(tab, N, lp, extra_scale, transposed ? 1 : 0);
 }
 
 // ---------------------------------------------------------------------------------------------

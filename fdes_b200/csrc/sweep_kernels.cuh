@@ -1015,8 +1015,9 @@ k_cols_fft(const cpx* __restrict__ in, void* __restrict__ out_, const void* __re
     for (int m = 0; m < E; m++) {
     const size_t idx = (size_t)(theta + m * C::T) * N + kx;
     if (OP == COL_MUL_CPX_INV) {
-        // psi * CTF as in multiplyLensFunction (src/multisliceSimulation.cu:339-340)
-        const cpx w = ld_nc(static_cast<const cpx*>(table) + idx);
+        // psi * CTF as in multiplyLensFunction (src/multisliceSimulation.cu:339-340); the table is stored
+        // [kx][ky], so the threads of a column read consecutive entries
+        const cpx w = ld_nc(static_cast<const cpx*>(table) + (size_t)kx * N + (theta + m * C::T));
         x[m] = make_float2(w.x * x[m].x - w.y * x[m].y, w.x * x[m].y + w.y * x[m].x);
     } else {
         const float w = ld_nc(static_cast<const float*>(table) + idx);
@@ -1040,10 +1041,64 @@ static void cols_fft_one(const SweepGeom& g, const cpx* in, void* out, const voi
     FDES_LAUNCH_CHECK();
 }
 
+// COL_MUL_CPX_INV on the band columns only, pipelined (col_pipe.cuh): out = scale * IFFT_col( FFT_col(in) * tab ),
+// tab stored [kx][ky].  Columns outside the band are not written (the consumer reads band columns only).
+template <int N>
+__global__ void __launch_bounds__(PipeCfg<N>::THREADS, 1)
+k_ctf_cols_tma(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_out,
+               const cpx* __restrict__ table, float scale, int lo_end, int hi_start, int tiles_x, int ntiles,
+               const cpx* __restrict__ tw)
+{
+    using C = PipeCfg<N>;
+    extern __shared__ unsigned char pipe_smem[];
+    constexpr int E = C::E;
+    ColPipe<N> pipe(pipe_smem);
+    const int theta = pipe.theta;
+    int t = blockIdx.x;
+    if (t >= ntiles) return;
+    if (threadIdx.x == 0) {
+        prefetch_tensormap(&map_in); prefetch_tensormap(&map_out);
+        pipe.issue_load(&map_in, band_col0((t % tiles_x) * C::CW, lo_end, hi_start), t / tiles_x);
+    }
+    for (; t < ntiles; t += gridDim.x) {
+        const int kx0 = band_col0((t % tiles_x) * C::CW, lo_end, hi_start), kx = kx0 + pipe.line;
+        const int tn = t + gridDim.x;
+        cpx x[E];
+        pipe.acquire(x, tn < ntiles, &map_in, band_col0((tn % tiles_x) * C::CW, lo_end, hi_start), tn / tiles_x);
+        fft_line<N, E, -1>(x, pipe.sm(), theta, tw, pipe.sync());
+        pipe.publish_store_drained();
+        const cpx* tab = table + (size_t)kx * N + theta;
+#pragma unroll
+        for (int m = 0; m < E; m++) {
+            const cpx w = ld_nc(tab + m * C::T);
+            x[m] = make_float2(w.x * x[m].x - w.y * x[m].y, w.x * x[m].y + w.y * x[m].x);
+        }
+        fft_line<N, E, 1>(x, pipe.sm(), theta, tw, pipe.sync());
+#pragma unroll
+        for (int m = 0; m < E; m++) x[m] = make_float2(x[m].x * scale, x[m].y * scale);
+        pipe.release(x, &map_out, kx0, t / tiles_x);
+    }
+    pipe.finish();
+}
+
 template <int NN>
 void launch_cols_fft_n(const SweepGeom& g, const cpx* in, void* out, int dir, ColOp op,
                      const void* table, float scale, int batch, cudaStream_t st)
 {
+    if constexpr (pipe_supported<NN>()) {
+        if (op == COL_MUL_CPX_INV && pipe_enabled() && g.lo_end < g.hi_start) {
+            using P = PipeCfg<NN>;
+            FDES_ALLOW_SMEM((k_ctf_cols_tma<NN>), P::SMEM);
+            const int tiles_x = band_cols(g) / P::CW, ntiles = tiles_x * batch;
+            CUtensorMap map_in, map_out;
+            tile_map(&map_in, in, NN, batch, P::CW, P::BR);
+            tile_map(&map_out, out, NN, batch, P::CW, P::BR);
+            k_ctf_cols_tma<NN><<<pipe_grid(ntiles), P::THREADS, P::SMEM, st>>>(map_in, map_out, static_cast<const cpx*>(table),
+                                                                            scale, g.lo_end, g.hi_start, tiles_x, ntiles, g.tw);
+            FDES_LAUNCH_CHECK();
+            return;
+        }
+    }
     switch (op) {
         case COL_PLAIN:
             if (dir < 0) cols_fft_one<NN, -1, COL_PLAIN>(g, in, out, table, scale, batch, st);
