@@ -98,7 +98,9 @@ struct PipeCfg {
     static constexpr int SWZ_MASK = ROWB >= 128 ? 7 : (ROWB == 64 ? 3 : (ROWB == 32 ? 1 : 0));   // CU_TENSOR_MAP_SWIZZLE_*
     static constexpr int LSTRIDE = line_smem_elems<E>(N) + 16 / CW;   // padded exchange line [elements]
     static constexpr int X_BYTES = CW * LSTRIDE * 8;
-    static constexpr int OFF_L = 0, OFF_S = TILE_BYTES, OFF_X = 2 * TILE_BYTES, OFF_BAR = OFF_X + ((X_BYTES + 15) & ~15);
+    static constexpr int TW_ELEMS = twiddle_table_elems<N, E>();          // pass twiddle tables, copied to shared memory
+    static constexpr int OFF_L = 0, OFF_S = TILE_BYTES, OFF_X = 2 * TILE_BYTES, OFF_TW = OFF_X + ((X_BYTES + 15) & ~15),
+                         OFF_BAR = OFF_TW + TW_ELEMS * 8;
     static constexpr size_t SMEM = OFF_BAR + 64 + 1024;   // + slack to align the base to 1024 B
     static constexpr bool WARP_SYNC = (T <= 32);
     static_assert(N >= 512 && (N & (N - 1)) == 0 && N <= 4096, "pipelined column tiles: N = 512 .. 4096, power of two");
@@ -135,7 +137,8 @@ struct ColPipe {
     uint32_t it = 0;           // tiles stored so far by this CTA
     uint32_t nload = 0;        // tiles acquired so far (several loads may feed one stored tile)
 
-    __device__ __forceinline__ explicit ColPipe(unsigned char* smem_raw)
+    // tw: the pass twiddle tables of the line transform (global); a copy is placed in shared memory
+    __device__ __forceinline__ ColPipe(unsigned char* smem_raw, const cpx* __restrict__ tw_global)
     {
         base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
         full = reinterpret_cast<uint64_t*>(base + C::OFF_BAR);
@@ -151,8 +154,11 @@ struct ColPipe {
             mbar_init(sfree, 1);
             fence_mbar_init();
         }
+        cpx* tws = reinterpret_cast<cpx*>(base + C::OFF_TW);
+        for (int i = threadIdx.x; i < C::TW_ELEMS; i += C::THREADS) tws[i] = tw_global[i];
         __syncthreads();
     }
+    __device__ __forceinline__ TwShared tw() const { return TwShared{smem_u32(base + C::OFF_TW)}; }
     __device__ __forceinline__ cpx* sm() const { return reinterpret_cast<cpx*>(base + C::OFF_X) + line * C::LSTRIDE; }
     __device__ __forceinline__ PipeSync<N> sync() const { return PipeSync<N>{line + 1}; }
 

@@ -23,6 +23,7 @@
 // src/crystalMaker.cu:527,531 and src/multisliceSimulation.cu:554,556,608,610).
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdint>
 
 namespace fdes {
 
@@ -323,20 +324,38 @@ __host__ __device__ constexpr int twiddle_offset()
     else return (NS > 1 ? P::R * NS : 0) + twiddle_offset<N, E, NS_TARGET, NS * P::R>();
 }
 
-// v[t] *= tab[t * NS] (or its conjugate for the inverse transform), t = T0 .. R-1
-template <int R, int NS, int DIR, int T0>
-__device__ __forceinline__ void apply_pass_twiddles(cpx (&v)[R], const cpx* __restrict__ tab)
+// Where the pass twiddle tables live: global memory (read-only path, L1/L2 resident) or a copy in
+// shared memory (the pipelined column kernels, whose tile buffers leave little L1: LDS instead of LDG
+// takes the twiddle reads out of the global load queue).  at<OFF>(i) = table[i + OFF].
+struct TwGlobal {
+    const cpx* p;
+    template <int OFF>
+    __device__ __forceinline__ cpx at(int i) const { return ld_nc_at<OFF>(p + i); }
+};
+struct TwShared {
+    uint32_t addr;       // shared-window byte address of the table
+    template <int OFF>
+    __device__ __forceinline__ cpx at(int i) const
+    {
+        cpx v;
+        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(addr + (uint32_t)i * 8u), "n"(OFF * 8));
+        return v;
+    }
+};
+
+// v[t] *= tab[i0 + t * NS] (or its conjugate for the inverse transform), t = T0 .. R-1
+template <int R, int NS, int DIR, int T0, class TW>
+__device__ __forceinline__ void apply_pass_twiddles(cpx (&v)[R], TW tab, int i0)
 {
     if constexpr (T0 < R) {
-        const cpx w = ld_nc_at<T0 * NS>(tab);
+        const cpx w = tab.template at<T0 * NS>(i0);
         v[T0] = DIR < 0 ? cmul(v[T0], w) : cmul_conj(v[T0], w);
-        apply_pass_twiddles<R, NS, DIR, T0 + 1>(v, tab);
+        apply_pass_twiddles<R, NS, DIR, T0 + 1>(v, tab, i0);
     }
 }
 
-template <int N, int E, int R, int NS, int DIR, bool LAST, class Sync>
-__device__ __forceinline__ void fft_pass(cpx (&x)[E], cpx* __restrict__ sm, int theta,
-                                         const cpx* __restrict__ tw, Sync sync)
+template <int N, int E, int R, int NS, int DIR, bool LAST, class Sync, class TW>
+__device__ __forceinline__ void fft_pass(cpx (&x)[E], cpx* __restrict__ sm, int theta, TW tw, Sync sync)
 {
     constexpr int T = N / E, U = E / R;
 #pragma unroll
@@ -346,7 +365,7 @@ __device__ __forceinline__ void fft_pass(cpx (&x)[E], cpx* __restrict__ sm, int 
         cpx v[R];
 #pragma unroll
         for (int t = 0; t < R; t++) v[t] = x[u + t * U];
-        if constexpr (NS > 1) apply_pass_twiddles<R, NS, DIR, 1>(v, tw + twiddle_offset<N, E, NS>() + k);
+        if constexpr (NS > 1) apply_pass_twiddles<R, NS, DIR, 1>(v, tw, twiddle_offset<N, E, NS>() + k);
         Dft<R, DIR>::run(v);
         if constexpr (LAST) {
 #pragma unroll
@@ -365,23 +384,28 @@ __device__ __forceinline__ void fft_pass(cpx (&x)[E], cpx* __restrict__ sm, int 
     }
 }
 
-template <int N, int E, int NS, int DIR, class Sync>
+template <int N, int E, int NS, int DIR, class Sync, class TW>
 struct LinePasses {
-    __device__ __forceinline__ static void run(cpx (&x)[E], cpx* sm, int theta, const cpx* tw, Sync sync)
+    __device__ __forceinline__ static void run(cpx (&x)[E], cpx* sm, int theta, TW tw, Sync sync)
     {
         using P = PassInfo<N, E, NS>;
-        fft_pass<N, E, P::R, NS, DIR, P::last, Sync>(x, sm, theta, tw, sync);
-        if constexpr (!P::last) LinePasses<N, E, NS * P::R, DIR, Sync>::run(x, sm, theta, tw, sync);
+        fft_pass<N, E, P::R, NS, DIR, P::last, Sync, TW>(x, sm, theta, tw, sync);
+        if constexpr (!P::last) LinePasses<N, E, NS * P::R, DIR, Sync, TW>::run(x, sm, theta, tw, sync);
     }
 };
 
 // Transform one line held as x[m] = f[theta + m*N/E].  All threads sharing the line buffer must
 // call it together.  sm: this line's line_smem_elems<E>(N) slots; tw: tables described above.
+template <int N, int E, int DIR, class Sync, class TW>
+__device__ __forceinline__ void fft_line_tw(cpx (&x)[E], cpx* sm, int theta, TW tw, Sync sync)
+{
+    static_assert(N >= E && N % E == 0, "line length must be a multiple of E");
+    LinePasses<N, E, 1, DIR, Sync, TW>::run(x, sm, theta, tw, sync);
+}
 template <int N, int E, int DIR, class Sync>
 __device__ __forceinline__ void fft_line(cpx (&x)[E], cpx* sm, int theta, const cpx* tw, Sync sync)
 {
-    static_assert(N >= E && N % E == 0, "line length must be a multiple of E");
-    LinePasses<N, E, 1, DIR, Sync>::run(x, sm, theta, tw, sync);
+    fft_line_tw<N, E, DIR, Sync, TwGlobal>(x, sm, theta, TwGlobal{tw}, sync);
 }
 
 // ---------------------------------------------------------------------------------------------

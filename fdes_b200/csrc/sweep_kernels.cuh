@@ -304,7 +304,7 @@ k_potential_cols_tma(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     extern __shared__ unsigned char pipe_smem[];
     constexpr int Q = N / 2 + 1;
     constexpr int E = C::E;
-    ColPipe<N> pipe(pipe_smem);
+    ColPipe<N> pipe(pipe_smem, tw);
     const int theta = pipe.theta;
     auto rows_of = [=](int b, int z, int sl) { return rowptr + (size_t)b * rp_stride + (size_t)(sl * nZ + z) * N; };
     auto present = [=](int b, int z) {
@@ -346,7 +346,7 @@ k_potential_cols_tma(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             pipe.acquire(x, lt < ntiles, &mapA, (lt % tiles_x) * C::CW, (lt / tiles_x) * nZ + lz,
                          [rp, rp2](int y) { return (rp[y + 1] > rp[y]) | (rp2[y + 1] > rp2[y]); });
             any = true;
-            fft_line<N, E, -1>(x, pipe.sm(), theta, tw, pipe.sync());
+            fft_line_tw<N, E, -1>(x, pipe.sm(), theta, pipe.tw(), pipe.sync());
             const float* G = Gq + (size_t)z * Q * Q + (size_t)ax * Q;
             quarter_table_apply<N, E, 0>(x, G + theta, G - theta,
                                          [](cpx v, float gz) { return pmul(v, make_float2(gz, gz)); });
@@ -354,7 +354,7 @@ k_potential_cols_tma(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             for (int m = 0; m < E; m++) acc[m] = padd(acc[m], x[m]);
         }
         pipe.publish_store_drained();
-        if (any) fft_line<N, E, 1>(acc, pipe.sm(), theta, tw, pipe.sync());
+        if (any) fft_line_tw<N, E, 1>(acc, pipe.sm(), theta, pipe.tw(), pipe.sync());
         pipe.release(acc, &mapB, kx0, b);
     }
     pipe.finish();
@@ -603,7 +603,7 @@ k_bandlimit_cols_tma(const __grid_constant__ CUtensorMap map, int npair, int lo_
     using C = PipeCfg<N>;
     extern __shared__ unsigned char pipe_smem[];
     constexpr int E = C::E;
-    ColPipe<N> pipe(pipe_smem);
+    ColPipe<N> pipe(pipe_smem, tw);
     const int theta = pipe.theta;
     // image y of the tile list -> entry (b, p) of a [batch][2] stack (npair = 0: plain [batch])
     auto entry = [npair](int y) { return npair == 0 ? y : (y / npair) * 2 + y % npair; };
@@ -620,7 +620,7 @@ k_bandlimit_cols_tma(const __grid_constant__ CUtensorMap map, int npair, int lo_
         const int tn = t + gridDim.x;
         cpx x[E];
         pipe.acquire(x, tn < ntiles, &map, band_col0((tn % tiles_x) * C::CW, lo_end, hi_start), entry(tn / tiles_x));
-        fft_line<N, E, -1>(x, pipe.sm(), theta, tw, pipe.sync());
+        fft_line_tw<N, E, -1>(x, pipe.sm(), theta, pipe.tw(), pipe.sync());
         pipe.publish_store_drained();
         const int i1 = kx > N / 2 ? kx - N : kx;
 #pragma unroll
@@ -630,7 +630,7 @@ k_bandlimit_cols_tma(const __grid_constant__ CUtensorMap map, int npair, int lo_
             const bool cut = ((float)(i1 * i1 + i2 * i2) * 9.f / (mind * mind)) > 1.f;
             x[m] = cut ? make_float2(0.f, 0.f) : make_float2(x[m].x * alpha, x[m].y * alpha);
         }
-        fft_line<N, E, 1>(x, pipe.sm(), theta, tw, pipe.sync());
+        fft_line_tw<N, E, 1>(x, pipe.sm(), theta, pipe.tw(), pipe.sync());
         pipe.release(x, &map, kx0, entry(t / tiles_x));
     }
     pipe.finish();
@@ -775,7 +775,7 @@ k_propagate_cols_tma(const __grid_constant__ CUtensorMap map, const cpx* __restr
     extern __shared__ unsigned char pipe_smem[];
     constexpr int Q = N / 2 + 1;
     constexpr int E = C::E;
-    ColPipe<N> pipe(pipe_smem);
+    ColPipe<N> pipe(pipe_smem, tw);
     const int theta = pipe.theta;
     int t = blockIdx.x;
     if (t >= ntiles) return;
@@ -788,11 +788,11 @@ k_propagate_cols_tma(const __grid_constant__ CUtensorMap map, const cpx* __restr
         const int tn = t + gridDim.x;
         cpx x[E];
         pipe.acquire(x, tn < ntiles, &map, band_col0((tn % tiles_x) * C::CW, lo_end, hi_start), tn / tiles_x);
-        fft_line<N, E, -1>(x, pipe.sm(), theta, tw, pipe.sync());
+        fft_line_tw<N, E, -1>(x, pipe.sm(), theta, pipe.tw(), pipe.sync());
         pipe.publish_store_drained();
         const cpx* P = Pq + (size_t)min(kx, N - kx) * Q;
         quarter_table_apply<N, E, 0>(x, P + theta, P - theta, [](cpx v, cpx p) { return cmul(v, p); });
-        fft_line<N, E, 1>(x, pipe.sm(), theta, tw, pipe.sync());
+        fft_line_tw<N, E, 1>(x, pipe.sm(), theta, pipe.tw(), pipe.sync());
         pipe.release(x, &map, kx0, t / tiles_x);
     }
     pipe.finish();
@@ -1052,7 +1052,7 @@ k_ctf_cols_tma(const __grid_constant__ CUtensorMap map_in, const __grid_constant
     using C = PipeCfg<N>;
     extern __shared__ unsigned char pipe_smem[];
     constexpr int E = C::E;
-    ColPipe<N> pipe(pipe_smem);
+    ColPipe<N> pipe(pipe_smem, tw);
     const int theta = pipe.theta;
     int t = blockIdx.x;
     if (t >= ntiles) return;
@@ -1065,7 +1065,7 @@ k_ctf_cols_tma(const __grid_constant__ CUtensorMap map_in, const __grid_constant
         const int tn = t + gridDim.x;
         cpx x[E];
         pipe.acquire(x, tn < ntiles, &map_in, band_col0((tn % tiles_x) * C::CW, lo_end, hi_start), tn / tiles_x);
-        fft_line<N, E, -1>(x, pipe.sm(), theta, tw, pipe.sync());
+        fft_line_tw<N, E, -1>(x, pipe.sm(), theta, pipe.tw(), pipe.sync());
         pipe.publish_store_drained();
         const cpx* tab = table + (size_t)kx * N + theta;
 #pragma unroll
@@ -1073,7 +1073,7 @@ k_ctf_cols_tma(const __grid_constant__ CUtensorMap map_in, const __grid_constant
             const cpx w = ld_nc(tab + m * C::T);
             x[m] = make_float2(w.x * x[m].x - w.y * x[m].y, w.x * x[m].y + w.y * x[m].x);
         }
-        fft_line<N, E, 1>(x, pipe.sm(), theta, tw, pipe.sync());
+        fft_line_tw<N, E, 1>(x, pipe.sm(), theta, pipe.tw(), pipe.sync());
 #pragma unroll
         for (int m = 0; m < E; m++) x[m] = make_float2(x[m].x * scale, x[m].y * scale);
         pipe.release(x, &map_out, kx0, t / tiles_x);

@@ -19,7 +19,7 @@ k_dbg(const __grid_constant__ CUtensorMap map, const cpx* __restrict__ Pq, int l
     extern __shared__ unsigned char pipe_smem[];
     constexpr int Q = N / 2 + 1;
     constexpr int E = C::E;
-    ColPipe<N, DBG> pipe(pipe_smem);
+    ColPipe<N, DBG> pipe(pipe_smem, tw);
     const int theta = pipe.theta;
     int t = blockIdx.x;
     if (t >= ntiles) return;
@@ -34,13 +34,13 @@ k_dbg(const __grid_constant__ CUtensorMap map, const cpx* __restrict__ Pq, int l
         if (!(DBG & 1)) mbar_wait(pipe.full, pipe.nload & 1);
         c_full += clock64() - c0;
         pipe.acquire(x, tn < ntiles, &map, band_col0((tn % tiles_x) * C::CW, lo_end, hi_start), tn / tiles_x);
-        fft_line<N, E, -1>(x, pipe.sm(), theta, tw, pipe.sync());
+        fft_line_tw<N, E, -1>(x, pipe.sm(), theta, pipe.tw(), pipe.sync());
         c0 = clock64();
         pipe.publish_store_drained();
         c_drain += clock64() - c0;
         const cpx* P = Pq + (size_t)min(kx, N - kx) * Q;
         quarter_table_apply<N, E, 0>(x, P + theta, P - theta, [](cpx v, cpx p) { return cmul(v, p); });
-        fft_line<N, E, 1>(x, pipe.sm(), theta, tw, pipe.sync());
+        fft_line_tw<N, E, 1>(x, pipe.sm(), theta, pipe.tw(), pipe.sync());
         c0 = clock64();
         pipe.release(x, &map, kx0, t / tiles_x);
         c_rel += clock64() - c0;
