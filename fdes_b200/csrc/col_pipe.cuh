@@ -101,7 +101,7 @@ struct PipeCfg {
     static constexpr int TW_ELEMS = twiddle_table_elems<N, E>();          // pass twiddle tables, copied to shared memory
     static constexpr int OFF_L = 0, OFF_S = TILE_BYTES, OFF_X = 2 * TILE_BYTES, OFF_TW = OFF_X + ((X_BYTES + 15) & ~15),
                          OFF_BAR = OFF_TW + TW_ELEMS * 8;
-    static constexpr size_t SMEM = OFF_BAR + 64 + 1024;   // + slack to align the base to 1024 B
+    static constexpr size_t SMEM = OFF_BAR + 64;
     static constexpr bool WARP_SYNC = (T <= 32);
     static_assert(N >= 512 && (N & (N - 1)) == 0 && N <= 4096, "pipelined column tiles: N = 512 .. 4096, power of two");
     static_assert(T % 8 == 0, "swizzle phase of a thread must not depend on m");
@@ -140,7 +140,11 @@ struct ColPipe {
     // tw: the pass twiddle tables of the line transform (global); a copy is placed in shared memory
     __device__ __forceinline__ ColPipe(unsigned char* smem_raw, const cpx* __restrict__ tw_global)
     {
-        base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+        // the dynamic shared-memory array is declared __align__(1024) (swizzle atoms repeat every 1024
+        // bytes); no pointer arithmetic through integers here, so that the compiler keeps the shared
+        // address space (LDS / STS instead of generic LD / ST)
+        base = smem_raw;
+        if ((smem_u32(base) & 1023u) != 0) __trap();
         full = reinterpret_cast<uint64_t*>(base + C::OFF_BAR);
         sfree = full + 1;
         line = threadIdx.x / T;

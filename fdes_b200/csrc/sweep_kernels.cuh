@@ -301,7 +301,7 @@ k_potential_cols_tma(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                      size_t rp_stride, int tiles_x, int ntiles, const cpx* __restrict__ tw)
 {
     using C = PipeCfg<N>;
-    extern __shared__ unsigned char pipe_smem[];
+    extern __shared__ __align__(1024) unsigned char pipe_smem[];
     constexpr int Q = N / 2 + 1;
     constexpr int E = C::E;
     ColPipe<N> pipe(pipe_smem, tw);
@@ -601,7 +601,7 @@ k_bandlimit_cols_tma(const __grid_constant__ CUtensorMap map, int npair, int lo_
                      int ntiles, const cpx* __restrict__ tw)
 {
     using C = PipeCfg<N>;
-    extern __shared__ unsigned char pipe_smem[];
+    extern __shared__ __align__(1024) unsigned char pipe_smem[];
     constexpr int E = C::E;
     ColPipe<N> pipe(pipe_smem, tw);
     const int theta = pipe.theta;
@@ -772,7 +772,7 @@ k_propagate_cols_tma(const __grid_constant__ CUtensorMap map, const cpx* __restr
                      int tiles_x, int ntiles, const cpx* __restrict__ tw)
 {
     using C = PipeCfg<N>;
-    extern __shared__ unsigned char pipe_smem[];
+    extern __shared__ __align__(1024) unsigned char pipe_smem[];
     constexpr int Q = N / 2 + 1;
     constexpr int E = C::E;
     ColPipe<N> pipe(pipe_smem, tw);
@@ -1050,7 +1050,7 @@ k_ctf_cols_tma(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                const cpx* __restrict__ tw)
 {
     using C = PipeCfg<N>;
-    extern __shared__ unsigned char pipe_smem[];
+    extern __shared__ __align__(1024) unsigned char pipe_smem[];
     constexpr int E = C::E;
     ColPipe<N> pipe(pipe_smem, tw);
     const int theta = pipe.theta;

@@ -16,7 +16,7 @@ k_dbg(const __grid_constant__ CUtensorMap map, const cpx* __restrict__ Pq, int l
       int tiles_x, int ntiles, const cpx* __restrict__ tw, long long* dbg)
 {
     using C = PipeCfg<N>;
-    extern __shared__ unsigned char pipe_smem[];
+    extern __shared__ __align__(1024) unsigned char pipe_smem[];
     constexpr int Q = N / 2 + 1;
     constexpr int E = C::E;
     ColPipe<N, DBG> pipe(pipe_smem, tw);
