@@ -404,7 +404,8 @@ struct H5In {
 
     uint64_t u(uint64_t pos, int n) const
     {
-        if (pos + n > b.size()) throw std::runtime_error("EMD reader: read beyond end of file");
+        // overflow-safe: an undefined address (0xFFFF...FFFF) stored in the file must not wrap the sum
+        if (pos > b.size() || (uint64_t)n > b.size() - pos) throw std::runtime_error("EMD reader: read beyond end of file");
         uint64_t v = 0;
         for (int i = 0; i < n; i++) v |= (uint64_t)b[pos + i] << (8 * i);
         return v;
@@ -453,14 +454,18 @@ struct H5In {
         while (s < b.size() && b[s]) r.push_back((char)b[s++]);
         return r;
     }
-    void tree_links(uint64_t tree, uint64_t heap, std::vector<std::pair<std::string, uint64_t>>& out) const
+    void tree_links(uint64_t tree, uint64_t heap, std::vector<std::pair<std::string, uint64_t>>& out, int depth = 0) const
     {
-        if (memcmp(&b.at(tree), "TREE", 4) != 0 || u(tree + 4, 1) != 0) throw std::runtime_error("EMD reader: bad group B-tree");
+        // a crafted file may contain cycles or absurdly deep trees: bound the recursion
+        if (depth > 32) throw std::runtime_error("EMD reader: group B-tree nested too deeply");
+        u(tree, 8);      // bounds check of the signature + header start
+        if (memcmp(&b[tree], "TREE", 4) != 0 || u(tree + 4, 1) != 0) throw std::runtime_error("EMD reader: bad group B-tree");
         const int level = (int)u(tree + 5, 1), used = (int)u(tree + 6, 2);
         for (int i = 0; i < used; i++) {
             const uint64_t child = u(tree + 24 + 16 * i + 8, 8);
-            if (level > 0) { tree_links(child, heap, out); continue; }
-            if (memcmp(&b.at(child), "SNOD", 4) != 0) throw std::runtime_error("EMD reader: bad symbol node");
+            if (level > 0) { tree_links(child, heap, out, depth + 1); continue; }
+            u(child, 8);
+            if (memcmp(&b[child], "SNOD", 4) != 0) throw std::runtime_error("EMD reader: bad symbol node");
             const int nsym = (int)u(child + 6, 2);
             for (int j = 0; j < nsym; j++)
                 out.emplace_back(heap_name(heap, u(child + 8 + 40 * j, 8)), u(child + 8 + 40 * j + 8, 8));
@@ -532,7 +537,9 @@ struct H5In {
             auto pad = [&](uint64_t n) { return ver == 1 ? (n + 7) & ~7ull : n; };
             const uint64_t nsz = u(m.pos + 2, 2), tsz = u(m.pos + 4, 2), ssz = u(m.pos + 6, 2);
             uint64_t p = m.pos + 8 + (ver == 3 ? 1 : 0);
-            if (std::string((const char*)&b.at(p)) != name) continue;
+            u(p, 1);                                           // p inside the file
+            const uint64_t room = std::min<uint64_t>(nsz, b.size() - p);   // the name may not run past its field or the file
+            if (std::string((const char*)&b[p], strnlen((const char*)&b[p], room)) != name) continue;
             p += pad(nsz);
             t = datatype(p);
             p += pad(tsz);
@@ -574,7 +581,9 @@ struct H5In {
             }
         }
         if (!have_t || !have_s || !have_l || t.cls == 3) return false;
-        if (bytes != n * t.size) throw std::runtime_error("EMD reader: dataset size mismatch");
+        if (t.size == 0 || n > b.size() / t.size || bytes != n * t.size)     // n * size cannot overflow; data must fit the file
+            throw std::runtime_error("EMD reader: dataset size mismatch");
+        if (addr != UNDEF) u(addr, 0), u(addr + bytes - (bytes ? 1 : 0), bytes ? 1 : 0);
         out.resize(n);
         for (uint64_t i = 0; i < n; i++) out[i] = addr == UNDEF ? T(0) : (T)number(t, addr + i * t.size);
         return true;

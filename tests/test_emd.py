@@ -209,3 +209,24 @@ def test_array_layouts_with_several_measurements(fb, tmp_path):
     assert "potential_slices" not in f.root["data"].children
     np.testing.assert_array_equal(f.root["imaging/specimen_tilt_x"].data, r["tiltspec"][:, 0])
     np.testing.assert_array_equal(f.root["imaging/defoci"].data, r["defoci"])
+
+
+def test_reader_survives_corrupted_files(fb, tmp_path):
+    """The .emd input path is reachable from FDES() and the CLI: truncated or corrupted HDF5 bytes
+    (undefined addresses 0xFF..FF, broken B-tree / heap offsets, unterminated names) must end in an error
+    code or in parsed values, never in an out-of-bounds read."""
+    import shipped_cases as sc
+    lib = fb.load_library()
+    src = (sc.SHIPPED / "ExampleSpecimens" / "Au_cubeoctahedron_emd" / "Auparticle.emd").read_bytes()
+    rng = np.random.default_rng(0)
+    rejected = 0
+    for i in range(120):
+        b = bytearray(src[: (len(src) if i % 2 else int(rng.integers(100, 6000)))])
+        for _ in range(int(rng.integers(1, 8))):
+            j = int(rng.integers(0, min(len(b), 6000)))
+            b[j] = int(rng.integers(0, 256)) if rng.random() < 0.5 else 0xFF
+        f = tmp_path / "c.emd"
+        f.write_bytes(bytes(b))
+        rc = lib.fdes_b200_parse_cnf(str(f).encode(), None, None, None, None, 0)
+        rejected += rc < 0
+    assert rejected > 20
