@@ -103,14 +103,29 @@ __device__ __forceinline__ cpx ld_g(const cpx* p)     // data written by earlier
 
 __device__ __forceinline__ cpx cadd(cpx a, cpx b) { return padd(a, b); }
 __device__ __forceinline__ cpx csub(cpx a, cpx b) { return psub(a, b); }
-// a * (c + i s): FMUL2 + FFMA2 (the scalar broadcasts and the pair swap are operand modifiers)
+// a * (c + i s) = a * (c, c) + (-a.y, a.x) * (s, s): exactly FMUL2 + FFMA2 -- the broadcasts (R.F32), the
+// pair swap and the lane signs (R.F32x2.LO_HI.NP) are operand modifiers in SASS.  (Written as
+// a.x * (c, s) + a.y * (-s, c) the second multiplier needs a new register pair: MOV + FADD per multiply,
+// which doubled the instruction count of every twiddle and table multiplication.)
 __device__ __forceinline__ cpx cmul_cs(cpx a, float c, float s)
 {
-    return pfma(make_float2(a.x, a.x), make_float2(c, s), pmul(make_float2(a.y, a.y), make_float2(-s, c)));
+    return pfma(make_float2(-a.y, a.x), make_float2(s, s), pmul(a, make_float2(c, c)));
 }
 __device__ __forceinline__ cpx cmul(cpx a, cpx b) { return cmul_cs(a, b.x, b.y); }
+// a * conj(b) = a * (b.x, b.x) + (a.y, -a.x) * (b.y, b.y)
+__device__ __forceinline__ cpx cmul_conj(cpx a, cpx b)
+{
+    return pfma(make_float2(a.y, -a.x), make_float2(b.y, b.y), pmul(a, make_float2(b.x, b.x)));
+}
+// a * (c + i s) for COMPILE-TIME c, s: a * (c, c) + swap(a) * (-s, s).  In SASS the swap and the signs are
+// operand modifiers (R.F32x2.LO_HI.NP), c is an immediate and (s, s) one uniform register pair, where the
+// broadcast form of cmul_cs needs two different constant pairs in vector registers (2 extra MOVs per
+// multiply -- a quarter of the instructions of a row sweep were such moves).
+__device__ __forceinline__ cpx cmul_const(cpx a, float c, float s)
+{
+    return pfma(make_float2(a.y, a.x), make_float2(-s, s), pmul(a, make_float2(c, c)));
+}
 // a * conj(b)
-__device__ __forceinline__ cpx cmul_conj(cpx a, cpx b) { return cmul_cs(a, b.x, -b.y); }
 // a + (DIR * i) * d   and   a - (DIR * i) * d      (DIR = -1: forward transform, W4 = -i)
 template <int DIR>
 __device__ __forceinline__ cpx add_di(cpx a, cpx d)
@@ -154,7 +169,7 @@ __device__ __forceinline__ cpx mul_w32(cpx a)
     else if constexpr (n == 8) return mul_di<DIR>(a);
     else if constexpr (n == 16) return make_float2(-a.x, -a.y);
     else if constexpr (n == 24) return mul_di<-DIR>(a);
-    else return cmul_cs(a, cos32(n), DIR < 0 ? -sin32(n) : sin32(n));
+    else return cmul_const(a, cos32(n), DIR < 0 ? -sin32(n) : sin32(n));
 }
 
 // cos / sin of 2 pi n / 20, for the radix-5 family (5, 10, 20)
@@ -175,7 +190,7 @@ __device__ __forceinline__ cpx mul_w20(cpx a)
     else if constexpr (n == 5) return mul_di<DIR>(a);
     else if constexpr (n == 10) return make_float2(-a.x, -a.y);
     else if constexpr (n == 15) return mul_di<-DIR>(a);
-    else return cmul_cs(a, cos20(n), DIR < 0 ? -sin20(n) : sin20(n));
+    else return cmul_const(a, cos20(n), DIR < 0 ? -sin20(n) : sin20(n));
 }
 // v *= exp(DIR * 2 pi i * n / R) with compile-time n; R divides 32 or 20
 template <int DIR, int R, int n>
