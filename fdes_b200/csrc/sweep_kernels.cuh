@@ -61,6 +61,33 @@ struct DeviceOnce {
         }                                                                                        \
     } while (0)
 
+// Programmatic dependent launch for the sweeps of the slice loop (about sixty dependent launches per
+// batch): a sweep is launched with programmatic stream serialisation, signals at its very start that its
+// dependents may be scheduled, and waits for its own prerequisites before it touches memory.  The CTAs of
+// sweep i+1 are then resident (index arithmetic, barrier set-up done) when the last CTAs of sweep i drain,
+// instead of being launched after the grid has completed.  FDES_B200_NO_PDL=1 switches it off.
+__device__ __forceinline__ void pdl_prologue()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+static bool pdl_enabled()
+{
+    static const bool on = [] { const char* e = getenv("FDES_B200_NO_PDL"); return !(e && e[0] == '1'); }();
+    return on;
+}
+template <class... KArgs, class... Args>
+void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    FDES_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+
 // register budget per thread that __launch_bounds__ asks the compiler to respect
 #ifndef FDES_ROW_MIN_CTAS
 #define FDES_ROW_MIN_CTAS 3
@@ -196,6 +223,7 @@ k_density_rows(cpx* __restrict__ A, const int* __restrict__ rowptr, const int* _
                const float* __restrict__ rec_w, int slice, int slice2, int nZ, size_t rec_stride,
                size_t rp_stride, const cpx* __restrict__ tw)
 {
+    pdl_prologue();
     using C = RowCfg<N>;
     extern __shared__ cpx smem[];
     constexpr int E = C::E;
@@ -243,7 +271,7 @@ void launch_density_rows_n(const SweepGeom& g, cpx* A, const int* rowptr, const 
     const size_t smem = C::SMEM + (size_t)C::RPB * NN * sizeof(cpx);
     FDES_ALLOW_SMEM((k_density_rows<NN>), smem);
     dim3 grid(NN / C::RPB, nZ, batch);
-    k_density_rows<NN><<<grid, C::THREADS, smem, st>>>(A, rowptr, rec_col, rec_w, slice, slice2, nZ,
+    launch_pdl(k_density_rows<NN>, dim3(grid), dim3(C::THREADS), smem, st, A, rowptr, rec_col, rec_w, slice, slice2, nZ,
                                                       rec_stride, rowptr_stride, g.tw);
     FDES_LAUNCH_CHECK();
 }
@@ -257,6 +285,7 @@ k_potential_cols(cpx* __restrict__ B, const cpx* __restrict__ A, const float* __
                  const int* __restrict__ rowptr, int slice, int slice2, int nZ, size_t rp_stride,
                  const cpx* __restrict__ tw)
 {
+    pdl_prologue();
     using C = ColCfg<N>;
     extern __shared__ cpx smem[];
     constexpr int Q = N / 2 + 1;
@@ -300,6 +329,7 @@ k_potential_cols_tma(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                      const float* __restrict__ Gq, const int* __restrict__ rowptr, int slice, int slice2, int nZ,
                      size_t rp_stride, int tiles_x, int ntiles, const cpx* __restrict__ tw)
 {
+    pdl_prologue();
     using C = PipeCfg<N>;
     extern __shared__ __align__(1024) unsigned char pipe_smem[];
     constexpr int Q = N / 2 + 1;
@@ -373,7 +403,7 @@ void launch_potential_cols_n(const SweepGeom& g, cpx* B, const cpx* A, const flo
             CUtensorMap mapA, mapB;
             tile_map(&mapA, A, NN, batch * nZ, P::CW, P::BR);
             tile_map(&mapB, B, NN, batch, P::CW, P::BR);
-            k_potential_cols_tma<NN><<<pipe_grid(ntiles), P::THREADS, P::SMEM, st>>>(mapA, mapB, Gq, rowptr, slice, slice2,
+            launch_pdl(k_potential_cols_tma<NN>, dim3(pipe_grid(ntiles)), dim3(P::THREADS), P::SMEM, st, mapA, mapB, Gq, rowptr, slice, slice2,
                                                                                   nZ, rowptr_stride, tiles_x, ntiles, g.tw);
             FDES_LAUNCH_CHECK();
             return;
@@ -382,7 +412,7 @@ void launch_potential_cols_n(const SweepGeom& g, cpx* B, const cpx* A, const flo
     using C = ColCfg<NN>;
     FDES_ALLOW_SMEM((k_potential_cols<NN>), C::SMEM);
     dim3 grid(NN / C::CW, batch);
-    k_potential_cols<NN><<<grid, C::THREADS, C::SMEM, st>>>(B, A, Gq, rowptr, slice, slice2, nZ,
+    launch_pdl(k_potential_cols<NN>, dim3(grid), dim3(C::THREADS), C::SMEM, st, B, A, Gq, rowptr, slice, slice2, nZ,
                                                            rowptr_stride, g.tw);
     FDES_LAUNCH_CHECK();
 }
@@ -489,6 +519,7 @@ template <int N>
 __global__ void __launch_bounds__(RowCfg<N>::THREADS, RowCfg<N>::MIN_CTAS)
 k_transmit_rows(const cpx* __restrict__ W, cpx* __restrict__ D, int npair, float imPot, const cpx* __restrict__ tw)
 {
+    pdl_prologue();
     using C = RowCfg<N>;
     extern __shared__ cpx smem[];
     constexpr int E = C::E;
@@ -557,7 +588,7 @@ void launch_transmit_rows_n(const SweepGeom& g, const cpx* W, cpx* D, int npair,
     FDES_ALLOW_SMEM((k_transmit_rows<NN>), smem);
     dim3 grid(NN / C::RPB, batch);
     Band<NN>::check(g);
-    k_transmit_rows<NN><<<grid, C::THREADS, smem, st>>>(W, D, npair, imPot, g.tw);
+    launch_pdl(k_transmit_rows<NN>, dim3(grid), dim3(C::THREADS), smem, st, W, D, npair, imPot, g.tw);
     FDES_LAUNCH_CHECK();
 }
 
@@ -568,6 +599,7 @@ template <int N>
 __global__ void __launch_bounds__(ColCfg<N>::THREADS, LineCfg<N>::T <= 32 ? 2 : ColCfg<N>::MIN_CTAS)
 k_bandlimit_cols(cpx* __restrict__ W, int npair, int lo_end, int hi_start, const cpx* __restrict__ tw)
 {
+    pdl_prologue();
     using C = ColCfg<N>;
     extern __shared__ cpx smem[];
     constexpr int E = C::E;
@@ -600,6 +632,7 @@ __global__ void __launch_bounds__(PipeCfg<N>::THREADS, 1)
 k_bandlimit_cols_tma(const __grid_constant__ CUtensorMap map, int npair, int lo_end, int hi_start, int tiles_x,
                      int ntiles, const cpx* __restrict__ tw)
 {
+    pdl_prologue();
     using C = PipeCfg<N>;
     extern __shared__ __align__(1024) unsigned char pipe_smem[];
     constexpr int E = C::E;
@@ -647,7 +680,7 @@ void launch_bandlimit_cols_n(const SweepGeom& g, cpx* W, int batch, int npair, c
             const int tiles_x = band_cols(g) / P::CW, ntiles = tiles_x * (npair == 0 ? batch : batch * npair);
             CUtensorMap map;
             tile_map(&map, W, NN, nimg, P::CW, P::BR);
-            k_bandlimit_cols_tma<NN><<<pipe_grid(ntiles), P::THREADS, P::SMEM, st>>>(map, npair, g.lo_end, g.hi_start,
+            launch_pdl(k_bandlimit_cols_tma<NN>, dim3(pipe_grid(ntiles)), dim3(P::THREADS), P::SMEM, st, map, npair, g.lo_end, g.hi_start,
                                                                                   tiles_x, ntiles, g.tw);
             FDES_LAUNCH_CHECK();
             return;
@@ -656,7 +689,7 @@ void launch_bandlimit_cols_n(const SweepGeom& g, cpx* W, int batch, int npair, c
     using C = ColCfg<NN>;
     FDES_ALLOW_SMEM((k_bandlimit_cols<NN>), C::SMEM);
     dim3 grid(band_cols(g) / C::CW, npair == 0 ? batch : batch * npair);
-    k_bandlimit_cols<NN><<<grid, C::THREADS, C::SMEM, st>>>(W, npair, g.lo_end, g.hi_start, g.tw);
+    launch_pdl(k_bandlimit_cols<NN>, dim3(grid), dim3(C::THREADS), C::SMEM, st, W, npair, g.lo_end, g.hi_start, g.tw);
     FDES_LAUNCH_CHECK();
 }
 
@@ -671,6 +704,7 @@ __global__ void __launch_bounds__(RowCfg<N>::THREADS, RowCfg<N>::MIN_CTAS)
 k_multiply_rows(cpx* __restrict__ Psi, const cpx* __restrict__ Tk, size_t e_batch_stride, int psi_full,
                 const cpx* __restrict__ tw)
 {
+    pdl_prologue();
     using C = RowCfg<N>;
     extern __shared__ cpx smem[];
     constexpr int E = C::E;
@@ -737,7 +771,7 @@ void launch_multiply_rows_n(const SweepGeom& g, cpx* Psi, const cpx* E, size_t e
     FDES_ALLOW_SMEM((k_multiply_rows<NN>), smem);
     dim3 grid(NN / C::RPB, batch);
     Band<NN>::check(g);
-    k_multiply_rows<NN><<<grid, C::THREADS, smem, st>>>(Psi, E, e_batch_stride, psi_full ? 1 : 0, g.tw);
+    launch_pdl(k_multiply_rows<NN>, dim3(grid), dim3(C::THREADS), smem, st, Psi, E, e_batch_stride, psi_full ? 1 : 0, g.tw);
     FDES_LAUNCH_CHECK();
 }
 
@@ -749,6 +783,7 @@ __global__ void __launch_bounds__(ColCfg<N>::THREADS, ColCfg<N>::MIN_CTAS)
 k_propagate_cols(cpx* __restrict__ Psi, const cpx* __restrict__ Pq, int lo_end, int hi_start,
                  const cpx* __restrict__ tw)
 {
+    pdl_prologue();
     using C = ColCfg<N>;
     extern __shared__ cpx smem[];
     constexpr int Q = N / 2 + 1;
@@ -771,6 +806,7 @@ __global__ void __launch_bounds__(PipeCfg<N>::THREADS, 1)
 k_propagate_cols_tma(const __grid_constant__ CUtensorMap map, const cpx* __restrict__ Pq, int lo_end, int hi_start,
                      int tiles_x, int ntiles, const cpx* __restrict__ tw)
 {
+    pdl_prologue();
     using C = PipeCfg<N>;
     extern __shared__ __align__(1024) unsigned char pipe_smem[];
     constexpr int Q = N / 2 + 1;
@@ -808,7 +844,7 @@ void launch_propagate_cols_n(const SweepGeom& g, cpx* Psi, const cpx* Pq, int ba
             const int tiles_x = band_cols(g) / P::CW, ntiles = tiles_x * batch;
             CUtensorMap map;
             tile_map(&map, Psi, NN, batch, P::CW, P::BR);
-            k_propagate_cols_tma<NN><<<pipe_grid(ntiles), P::THREADS, P::SMEM, st>>>(map, Pq, g.lo_end, g.hi_start,
+            launch_pdl(k_propagate_cols_tma<NN>, dim3(pipe_grid(ntiles)), dim3(P::THREADS), P::SMEM, st, map, Pq, g.lo_end, g.hi_start,
                                                                                   tiles_x, ntiles, g.tw);
             FDES_LAUNCH_CHECK();
             return;
@@ -817,7 +853,7 @@ void launch_propagate_cols_n(const SweepGeom& g, cpx* Psi, const cpx* Pq, int ba
     using C = ColCfg<NN>;
     FDES_ALLOW_SMEM((k_propagate_cols<NN>), C::SMEM);
     dim3 grid(band_cols(g) / C::CW, batch);
-    k_propagate_cols<NN><<<grid, C::THREADS, C::SMEM, st>>>(Psi, Pq, g.lo_end, g.hi_start, g.tw);
+    launch_pdl(k_propagate_cols<NN>, dim3(grid), dim3(C::THREADS), C::SMEM, st, Psi, Pq, g.lo_end, g.hi_start, g.tw);
     FDES_LAUNCH_CHECK();
 }
 
