@@ -98,7 +98,11 @@ struct PipeCfg {
     static constexpr int SWZ_MASK = ROWB >= 128 ? 7 : (ROWB == 64 ? 3 : (ROWB == 32 ? 1 : 0));   // CU_TENSOR_MAP_SWIZZLE_*
     static constexpr int LSTRIDE = line_smem_elems<E>(N) + 16 / CW;   // padded exchange line [elements]
     static constexpr int X_BYTES = CW * LSTRIDE * 8;
-    static constexpr int TW_ELEMS = twiddle_table_elems<N, E>();          // pass twiddle tables, copied to shared memory
+    // pass twiddle tables: copied to shared memory when they fit next to the three tile buffers (8 KB at
+    // 1024, 24 KB at 2048; the 40 KB of a 4096-point line do not, they stay in global memory / L1)
+    static constexpr int TW_TABLE = twiddle_table_elems<N, E>();
+    static constexpr bool TW_SHARED = 2 * TILE_BYTES + ((X_BYTES + 15) & ~15) + TW_TABLE * 8 + 64 <= 227 * 1024;
+    static constexpr int TW_ELEMS = TW_SHARED ? TW_TABLE : 0;
     static constexpr int OFF_L = 0, OFF_S = TILE_BYTES, OFF_X = 2 * TILE_BYTES, OFF_TW = OFF_X + ((X_BYTES + 15) & ~15),
                          OFF_BAR = OFF_TW + TW_ELEMS * 8;
     static constexpr size_t SMEM = OFF_BAR + 64;
@@ -132,6 +136,7 @@ struct ColPipe {
     static constexpr int E = C::E, T = C::T;
     unsigned char* base;       // 1024-byte aligned shared memory
     uint64_t *full, *sfree;
+    const cpx* tw_global_;
     int line, theta;
     uint32_t tile_off;         // byte offset of this thread's (row theta, column line) inside a tile buffer
     uint32_t it = 0;           // tiles stored so far by this CTA
@@ -158,11 +163,16 @@ struct ColPipe {
             mbar_init(sfree, 1);
             fence_mbar_init();
         }
+        tw_global_ = tw_global;
         cpx* tws = reinterpret_cast<cpx*>(base + C::OFF_TW);
         for (int i = threadIdx.x; i < C::TW_ELEMS; i += C::THREADS) tws[i] = tw_global[i];
         __syncthreads();
     }
-    __device__ __forceinline__ TwShared tw() const { return TwShared{smem_u32(base + C::OFF_TW)}; }
+    __device__ __forceinline__ auto tw() const
+    {
+        if constexpr (C::TW_SHARED) return TwShared{smem_u32(base + C::OFF_TW)};
+        else return TwGlobal{tw_global_};
+    }
     __device__ __forceinline__ cpx* sm() const { return reinterpret_cast<cpx*>(base + C::OFF_X) + line * C::LSTRIDE; }
     __device__ __forceinline__ PipeSync<N> sync() const { return PipeSync<N>{line + 1}; }
 

@@ -182,9 +182,10 @@ static int band_cols(const SweepGeom& g)
 // The pipelined form (col_pipe.cuh): persistent CTAs, tiles fed by TMA.  Tile t covers the band
 // columns [CW * (t % tiles_x), +CW) of image t / tiles_x; consecutive CTAs work on adjacent tiles.
 template <int N>
-constexpr bool pipe_supported() { return N == 512 || N == 1024; }
-// (N = 2048, 4096: tile rows are 32 / 16 bytes; the TMA store then becomes row-rate bound -- measured
-// with tools/microbench/col_bench.cu -- and the register-staged kernels are as fast)
+constexpr bool pipe_supported() { return N == 512 || N == 1024 || N == 2048 || N == 4096; }
+// (N = 2048 / 4096: tile rows of 32 / 16 bytes.  With generic LD/ST, 255 registers and four-instruction
+// complex multiplies the pipelined kernels were no faster than the register-staged ones there; since those
+// were fixed they are 21 % / 35 % faster: tools/microbench/col_bench.cu, profiles/r2_v4_col_bench.txt)
 // FDES_B200_NO_TMA=1 selects the register-staged column kernels (A/B comparisons)
 static bool pipe_enabled()
 {

@@ -158,6 +158,7 @@ int main(int argc, char** argv)
     run<4096>(2, reps);
     run<512>(32, reps);
     run_dbg<1024, 0>(8, reps); run_dbg<1024, 1>(8, reps); run_dbg<1024, 2>(8, reps); run_dbg<1024, 3>(8, reps);
+    run_dbg<2048, 0>(8, reps); run_dbg<2048, 1>(8, reps); run_dbg<2048, 2>(8, reps); run_dbg<2048, 3>(8, reps);
     run_dbg<4096, 0>(2, reps); run_dbg<4096, 1>(2, reps); run_dbg<4096, 2>(2, reps); run_dbg<4096, 3>(2, reps);
     return 0;
 }
