@@ -172,6 +172,26 @@ __device__ __forceinline__ cpx mul_w32(cpx a)
     else return cmul_const(a, cos32(n), DIR < 0 ? -sin32(n) : sin32(n));
 }
 
+// cos / sin of 2 pi n / 64, n = 0..16 (radix-64 butterflies: a 2048-point row inside one warp)
+__device__ __forceinline__ constexpr float cos64(int n)
+{
+    constexpr float c[17] = {1.00000000000000000000f, 0.99518472667219692873f, 0.98078528040323043058f, 0.95694033573220882438f, 0.92387953251128673848f, 0.88192126434835504956f, 0.83146961230254523567f, 0.77301045336273699338f, 0.70710678118654757274f, 0.63439328416364548779f, 0.55557023301960228867f, 0.47139673682599780857f, 0.38268343236508983729f, 0.29028467725446233105f, 0.19509032201612833135f, 0.09801714032956077016f, 0.00000000000000006123f};
+    n &= 63;
+    if (n > 32) n = 64 - n;          // cos is even
+    return n <= 16 ? c[n] : -c[32 - n];
+}
+__device__ __forceinline__ constexpr float sin64(int n) { return cos64(n - 16); }
+template <int DIR, int n64>
+__device__ __forceinline__ cpx mul_w64(cpx a)
+{
+    constexpr int n = ((n64 % 64) + 64) % 64;
+    if constexpr (n == 0) return a;
+    else if constexpr (n == 16) return mul_di<DIR>(a);
+    else if constexpr (n == 32) return make_float2(-a.x, -a.y);
+    else if constexpr (n == 48) return mul_di<-DIR>(a);
+    else return cmul_const(a, cos64(n), DIR < 0 ? -sin64(n) : sin64(n));
+}
+
 // cos / sin of 2 pi n / 20, for the radix-5 family (5, 10, 20)
 __device__ __forceinline__ constexpr float cos20(int n)
 {
@@ -192,11 +212,12 @@ __device__ __forceinline__ cpx mul_w20(cpx a)
     else if constexpr (n == 15) return mul_di<-DIR>(a);
     else return cmul_const(a, cos20(n), DIR < 0 ? -sin20(n) : sin20(n));
 }
-// v *= exp(DIR * 2 pi i * n / R) with compile-time n; R divides 32 or 20
+// v *= exp(DIR * 2 pi i * n / R) with compile-time n; R divides 32 or 20, or is 64
 template <int DIR, int R, int n>
 __device__ __forceinline__ cpx mul_wR(cpx a)
 {
-    if constexpr (32 % R == 0) return mul_w32<DIR, (32 / R) * n>(a);
+    if constexpr (R == 64) return mul_w64<DIR, n>(a);
+    else if constexpr (32 % R == 0) return mul_w32<DIR, (32 / R) * n>(a);
     else return mul_w20<DIR, (20 / R) * n>(a);
 }
 
@@ -251,7 +272,7 @@ struct Dft<5, DIR> {
 template <int R, int DIR>
 struct Dft {
     static constexpr int R1 = R % 4 == 0 ? 4 : (R % 5 == 0 ? 5 : 2), R2 = R / R1;
-    static_assert(R == 8 || R == 16 || R == 32 || R == 10 || R == 20, "radix 2, 4, 5, 8, 10, 16, 20, 32");
+    static_assert(R == 8 || R == 16 || R == 32 || R == 64 || R == 10 || R == 20, "radix 2, 4, 5, 8, 10, 16, 20, 32, 64");
     __device__ __forceinline__ static void run(cpx (&v)[R])
     {
         cpx y[R1][R2];

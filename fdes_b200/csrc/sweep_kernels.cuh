@@ -105,28 +105,37 @@ struct LineCfg {
     static constexpr int T = N / E;                     // threads per line
     static constexpr int LS = line_smem_elems<E>(N);    // padded line buffer [elements]
 };
-template <int N>
-struct RowCfg {
-    using L = LineCfg<N>;
-    static constexpr int E = L::E, T = L::T;
-    static constexpr int RPB = (T & (T - 1)) != 0 ? 4 : ((128 / T) > 0 ? (128 / T) : 1);   // lines (rows) per CTA
+template <int N, int E_>
+struct RowCfgE {
+    static constexpr int E = E_, T = N / E_;
+    // lines (rows) per CTA; with 64 points per thread a line's buffers are 16 KB + 16 KB, two lines per CTA
+    static constexpr int RPB = E == 64 ? 2 : ((T & (T - 1)) != 0 ? 4 : ((128 / T) > 0 ? (128 / T) : 1));
     static constexpr int THREADS = RPB * T;
-    static constexpr int LSTRIDE = L::LS;
+    static constexpr int LSTRIDE = line_smem_elems<E>(N);
     static constexpr size_t SMEM = (size_t)RPB * LSTRIDE * sizeof(cpx);
     static constexpr bool WARP_SYNC = (32 % T == 0);   // a line lives inside one warp
     static constexpr bool NAMED_SYNC = (T % 32 == 0);  // a line is a whole number of warps
     static constexpr int MIN_CTAS = (N >= 2048 || !WARP_SYNC) ? 2 : FDES_ROW_MIN_CTAS;   // long lines need the registers
 };
+template <int N>
+using RowCfg = RowCfgE<N, LineCfg<N>::E>;
+// S5 at 2048: 64 points per thread -- the 2048-point row is 64 x 32 (two passes, one exchange, the whole row
+// inside ONE warp) instead of 32 x 32 x 2 with named barriers between two warps: 16 % faster although only six
+// warps fit an SM.  (Measured and not adopted: the same for S3, S6 and for 4096-point lines)
+template <int N>
+struct MultiplyRowsCfg { using type = RowCfg<N>; };
+template <>
+struct MultiplyRowsCfg<2048> { using type = RowCfgE<2048, 64>; };
 // threads of one row line: warp-level sync when the line fits a warp, a named barrier when it is a
 // whole number of warps, else (T = 40, 50: lines straddle warps) the whole CTA
-template <int N>
+template <int N, class C = RowCfg<N>>
 struct RowSync {
     int id;
     __device__ __forceinline__ explicit RowSync(int line) : id(line + 1) {}
     __device__ __forceinline__ void operator()() const
     {
-        if constexpr (RowCfg<N>::WARP_SYNC) __syncwarp();
-        else if constexpr (RowCfg<N>::NAMED_SYNC) asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(RowCfg<N>::T) : "memory");
+        if constexpr (C::WARP_SYNC) __syncwarp();
+        else if constexpr (C::NAMED_SYNC) asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(C::T) : "memory");
         else __syncthreads();
     }
 };
@@ -701,17 +710,17 @@ void launch_bandlimit_cols_n(const SweepGeom& g, cpx* W, int batch, int npair, c
 // an inverse transform is swap(FFT(swap(.))), real and imaginary parts exchanged on the way in and
 // out (see k_transmit_rows).
 template <int N>
-__global__ void __launch_bounds__(RowCfg<N>::THREADS, RowCfg<N>::MIN_CTAS)
+__global__ void __launch_bounds__(MultiplyRowsCfg<N>::type::THREADS, MultiplyRowsCfg<N>::type::MIN_CTAS)
 k_multiply_rows(cpx* __restrict__ Psi, const cpx* __restrict__ Tk, size_t e_batch_stride, int psi_full,
                 const cpx* __restrict__ tw)
 {
     pdl_prologue();
-    using C = RowCfg<N>;
+    using C = typename MultiplyRowsCfg<N>::type;
     extern __shared__ cpx smem[];
     constexpr int E = C::E;
     constexpr int lo_end = Band<N>::lo_end, hi_start = Band<N>::hi_start;
     const int line = threadIdx.x / C::T, theta = threadIdx.x % C::T;
-    const RowSync<N> sync(line);
+    const RowSync<N, C> sync(line);
     const size_t row = (size_t)blockIdx.x * C::RPB + line;
     const cpx* e = Tk + (size_t)blockIdx.y * e_batch_stride + row * N;
     cpx* p = Psi + ((size_t)blockIdx.y * N + row) * N;
@@ -767,12 +776,14 @@ template <int NN>
 void launch_multiply_rows_n(const SweepGeom& g, cpx* Psi, const cpx* E, size_t e_batch_stride,
                           int batch, bool psi_full, cudaStream_t st)
 {
-    using C = RowCfg<NN>;
+    using C = typename MultiplyRowsCfg<NN>::type;
     const size_t smem = C::SMEM + (size_t)C::RPB * NN * sizeof(cpx);
     FDES_ALLOW_SMEM((k_multiply_rows<NN>), smem);
     dim3 grid(NN / C::RPB, batch);
     Band<NN>::check(g);
-    launch_pdl(k_multiply_rows<NN>, dim3(grid), dim3(C::THREADS), smem, st, Psi, E, e_batch_stride, psi_full ? 1 : 0, g.tw);
+    // the table of this kernel's points-per-thread follows the common one (make_twiddles_n)
+    const cpx* tw = g.tw + (C::E != LineCfg<NN>::E ? twiddle_table_elems<NN, LineCfg<NN>::E>() : 0);
+    launch_pdl(k_multiply_rows<NN>, dim3(grid), dim3(C::THREADS), smem, st, Psi, E, e_batch_stride, psi_full ? 1 : 0, tw);
     FDES_LAUNCH_CHECK();
 }
 
@@ -1283,11 +1294,11 @@ void launch_detector_cols_n(const SweepGeom& g, const cpx* Psi, float* partial, 
 // ---------------------------------------------------------------------------------------------
 // twiddle tables (layout: fft_core.cuh) and geometry queries
 // ---------------------------------------------------------------------------------------------
-template <int N>
-std::vector<cpx> make_twiddles_n(int = 0)
+// pass twiddle tables of a line of N points with E points per thread, appended to tw
+template <int N, int E>
+void append_twiddles(std::vector<cpx>& tw)
 {
-    constexpr int E = LineCfg<N>::E;
-    std::vector<cpx> tw;
+    const size_t before = tw.size();
     int NS = 1;
     while (NS < N) {
         const int rem = N / NS, R = pass_radix(rem, E);
@@ -1310,7 +1321,16 @@ std::vector<cpx> make_twiddles_n(int = 0)
                 }
         NS *= R;
     }
-    if ((int)tw.size() != twiddle_table_elems<N, E>()) throw std::runtime_error("twiddle table size mismatch");
+    if ((int)(tw.size() - before) != twiddle_table_elems<N, E>()) throw std::runtime_error("twiddle table size mismatch");
+}
+// The tables a SweepGeom::tw of size N points to: the one of LineCfg<N>::E, followed by the table of S5's own
+// points-per-thread where that differs (MultiplyRowsCfg).
+template <int N>
+std::vector<cpx> make_twiddles_n(int = 0)
+{
+    std::vector<cpx> tw;
+    append_twiddles<N, LineCfg<N>::E>(tw);
+    if constexpr (MultiplyRowsCfg<N>::type::E != LineCfg<N>::E) append_twiddles<N, MultiplyRowsCfg<N>::type::E>(tw);
     if (tw.empty()) tw.push_back(make_float2(1.f, 0.f));
     return tw;
 }
