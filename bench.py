@@ -464,7 +464,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stem", action="store_true")
     ap.add_argument("--stem-probes", type=int, default=8192)
-    ap.add_argument("--stem-batch", type=int, default=32)
+    ap.add_argument("--stem-batch", type=int, default=37)   # 24 column tiles x 37 probes = 6.0 waves of 148 SMs
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":

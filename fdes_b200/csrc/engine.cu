@@ -517,6 +517,17 @@ void Engine::run_slices_plain(int nb)
     // share one complex transform); S5/S6 then advance the wave through the two slices in turn.
     for (int s = 0; s < p_.m3; s += 2) {
         const int npair = std::min(2, p_.m3 - s);
+        if (npair == 1 && nb % 2 == 0) {
+            // odd slice count: the last slices of configurations 2j and 2j + 1 share one complex transform
+            // through S1 / S2 / S3 (instead of nb half-empty pairs); S3 writes t of configuration b to D[b]
+            launch_density_rows(g_, A_, rs_[act_].rowptr, rs_[act_].cols, rs_[act_].w, s, s, nZ_, nb / 2, rec_stride_, rp_stride_, st_, 2, 1);
+            launch_potential_cols(g_, W_, A_, Gq_, rs_[act_].rowptr, s, s, nZ_, nb / 2, rp_stride_, st_, 2, 1);
+            launch_transmit_rows(g_, W_, D_, 2, p_.imPot, nb / 2, st_);
+            launch_bandlimit_cols(g_, D_, nb, 0, st_);
+            launch_multiply_rows(g_, Psi_, D_, NN, nb, first_full && s == 0, st_);
+            launch_propagate_cols(g_, Psi_, Pq_, nb, st_);
+            break;
+        }
         const int s2 = npair > 1 ? s + 1 : -1;
         launch_density_rows(g_, A_, rs_[act_].rowptr, rs_[act_].cols, rs_[act_].w, s, s2, nZ_, nb, rec_stride_, rp_stride_, st_);
         launch_potential_cols(g_, W_, A_, Gq_, rs_[act_].rowptr, s, s2, nZ_, nb, rp_stride_, st_);

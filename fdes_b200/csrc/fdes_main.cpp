@@ -103,7 +103,7 @@ int main(int argc, char** argv)
         const int np = nxy[0] * nxy[1];
         std::vector<float> xy(2 * (size_t)np), det(2 * (size_t)ndet), sig((size_t)np * ndet), out((size_t)np * ndet);
         fdes_b200_qsc_scan(input.c_str(), nxy, xy.data(), np, det.data(), ndet);
-        fdes_b200_sim* sim = fdes_b200_open_multi(input.c_str(), nullptr, 0, gpus.data(), (int)gpus.size(), 32, 0);
+        fdes_b200_sim* sim = fdes_b200_open_multi(input.c_str(), nullptr, 0, gpus.data(), (int)gpus.size(), 37, 0);   // 37 probes per launch: whole waves of 148 SMs at 512^2
         if (!sim) { fprintf(stderr, " \n fdes_b200: %s \n", fdes_b200_last_error()); return EXIT_FAILURE; }
         const double ms = fdes_b200_stem_scan(sim, 0, np, xy.data(), ndet, det.data(), sig.data());
         if (ms < 0) { fprintf(stderr, " \n fdes_b200: %s \n", fdes_b200_last_error()); return EXIT_FAILURE; }

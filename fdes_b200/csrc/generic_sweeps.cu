@@ -112,26 +112,29 @@ struct Smem3 {
 // ---- S1 -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GT) g_density_rows(cpx* A, const int* rowptr, const int* rec_col, const float* rec_w,
                                                      int slice, int slice2, int nZ, size_t rec_stride, size_t rp_stride,
-                                                     GPlan pl, const cpx* W)
+                                                     int cfg_stride, int cfg_off2, GPlan pl, const cpx* W)
 {
     extern __shared__ cpx gsm[];
     const int N = pl.N, row = blockIdx.x, z = blockIdx.y, b = blockIdx.z;
     cpx *x = gsm, *y = gsm + N;
-    const int* rp = rowptr + (size_t)b * rp_stride + (size_t)(slice * nZ + z) * N;
+    const int bA = b * cfg_stride, bB = bA + cfg_off2;      // configurations of the two parts (sweep_kernels.cuh)
+    const int* rp = rowptr + (size_t)bA * rp_stride + (size_t)(slice * nZ + z) * N;
     const int lo = rp[row], hi = rp[row + 1];
     int lo2 = 0, hi2 = 0;
     if (slice2 >= 0) {
-        const int* rp2 = rowptr + (size_t)b * rp_stride + (size_t)(slice2 * nZ + z) * N;
+        const int* rp2 = rowptr + (size_t)bB * rp_stride + (size_t)(slice2 * nZ + z) * N;
         lo2 = rp2[row]; hi2 = rp2[row + 1];
     }
     if (hi <= lo && hi2 <= lo2) return;       // S2 reads such rows as zero
     for (int i = threadIdx.x; i < N; i += GT) x[i] = make_float2(0.f, 0.f);
     __syncthreads();
     if (threadIdx.x == 0) {                   // sorted order: deterministic sums
-        const int* cc = rec_col + (size_t)b * rec_stride;
-        const float* ww = rec_w + (size_t)b * rec_stride;
+        const int* cc = rec_col + (size_t)bA * rec_stride;
+        const float* ww = rec_w + (size_t)bA * rec_stride;
         for (int i = lo; i < hi; i++) x[cc[i]].x += ww[i];
-        for (int i = lo2; i < hi2; i++) x[cc[i]].y += ww[i];
+        const int* cc2 = rec_col + (size_t)bB * rec_stride;
+        const float* ww2 = rec_w + (size_t)bB * rec_stride;
+        for (int i = lo2; i < hi2; i++) x[cc2[i]].y += ww2[i];
     }
     __syncthreads();
     g_fft(x, y, pl, 1, W, -1);
@@ -141,7 +144,8 @@ __global__ void __launch_bounds__(GT) g_density_rows(cpx* A, const int* rowptr, 
 
 // ---- S2 -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GT) g_potential_cols(cpx* B, const cpx* A, const float* Gq, const int* rowptr, int slice,
-                                                       int slice2, int nZ, size_t rp_stride, int L, GPlan pl, const cpx* W)
+                                                       int slice2, int nZ, size_t rp_stride, int cfg_stride, int cfg_off2, int L,
+                                                       GPlan pl, const cpx* W)
 {
     extern __shared__ cpx gsm[];
     const int N = pl.N, Q = N / 2 + 1, kx0 = blockIdx.x * L, b = blockIdx.y;
@@ -150,8 +154,9 @@ __global__ void __launch_bounds__(GT) g_potential_cols(cpx* B, const cpx* A, con
     g_foreach<true>(N, L, [&](int i, int l) { acc[l * N + i] = make_float2(0.f, 0.f); });
     bool any = false;
     for (int z = 0; z < nZ; z++) {
-        const int* rp = rowptr + (size_t)b * rp_stride + (size_t)(slice * nZ + z) * N;
-        const int* rp2 = slice2 >= 0 ? rowptr + (size_t)b * rp_stride + (size_t)(slice2 * nZ + z) * N : rp;
+        const int bA = b * cfg_stride, bB = bA + cfg_off2;
+        const int* rp = rowptr + (size_t)bA * rp_stride + (size_t)(slice * nZ + z) * N;
+        const int* rp2 = slice2 >= 0 ? rowptr + (size_t)bB * rp_stride + (size_t)(slice2 * nZ + z) * N : rp;
         if (rp[N] == rp[0] && rp2[N] == rp2[0]) continue;
         const cpx* Az = A + (size_t)(b * nZ + z) * N * N + kx0;
         __syncthreads();
@@ -492,21 +497,22 @@ void check_geom(const SweepGeom& g)
 #define GEN_LAUNCHED() GEN_CHECK(cudaGetLastError())
 
 void gen_density_rows(const SweepGeom& g, cpx* A, const int* rowptr, const int* rec_col, const float* rec_w, int slice, int slice2,
-                  int nZ, int batch, size_t rec_stride, size_t rp_stride, cudaStream_t st)
+                  int nZ, int batch, size_t rec_stride, size_t rp_stride, int cfg_stride, int cfg_off2, cudaStream_t st)
 {
     const size_t sm = 2 * (size_t)g.N * sizeof(cpx);
     allow(g_density_rows, sm);
     g_density_rows<<<dim3(g.N, nZ, batch), GT, sm, st>>>(A, rowptr, rec_col, rec_w, slice, slice2, nZ, rec_stride, rp_stride,
-                                                        make_plan(g.N), g.tw);
+                                                        cfg_stride, cfg_off2, make_plan(g.N), g.tw);
     GEN_LAUNCHED();
 }
 void gen_potential_cols(const SweepGeom& g, cpx* B, const cpx* A, const float* Gq, const int* rowptr, int slice, int slice2, int nZ,
-                    int batch, size_t rp_stride, cudaStream_t st)
+                    int batch, size_t rp_stride, int cfg_stride, int cfg_off2, cudaStream_t st)
 {
     const int L = col_width(g.N, 3);
     const size_t sm = 3 * (size_t)L * g.N * sizeof(cpx);
     allow(g_potential_cols, sm);
-    g_potential_cols<<<dim3(g.N / L, batch), GT, sm, st>>>(B, A, Gq, rowptr, slice, slice2, nZ, rp_stride, L, make_plan(g.N), g.tw);
+    g_potential_cols<<<dim3(g.N / L, batch), GT, sm, st>>>(B, A, Gq, rowptr, slice, slice2, nZ, rp_stride, cfg_stride, cfg_off2, L,
+                                                           make_plan(g.N), g.tw);
     GEN_LAUNCHED();
 }
 void gen_transmit_rows(const SweepGeom& g, const cpx* Wf, cpx* D, int npair, float imPot, int batch, cudaStream_t st)

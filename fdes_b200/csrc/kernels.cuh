@@ -28,14 +28,17 @@ int cols_per_block(int N);
 // ---- per-slice sweeps (S1..S6) -------------------------------------------
 // The potential sweeps S1..S3 work on slice PAIRS: the densities of slice and slice2 travel as the
 // real and imaginary part of one complex field (slice2 < 0: no partner).
+// Image b of a launch packs slice `slice` of configuration bA = b * cfg_stride (real part) and slice `slice2`
+// of configuration bB = bA + cfg_off2 (imaginary part): (1, 0) = two consecutive slices of one configuration;
+// (2, 1) with slice2 == slice = the odd last slices of two configurations sharing a transform.
 // S1: per-species density rows from the sorted deposit records -> row FFT -> A
 void launch_density_rows(const SweepGeom& g, cpx* A, const int* rowptr, const int* rec_col,
                          const float* rec_w, int slice, int slice2, int nZ, int batch, size_t rec_stride,
-                         size_t rowptr_stride, cudaStream_t st);
+                         size_t rowptr_stride, cudaStream_t st, int cfg_stride = 1, int cfg_off2 = 0);
 // S2: column FFT of every species, x scattering factor, species sum, inverse column FFT -> B
 void launch_potential_cols(const SweepGeom& g, cpx* B, const cpx* A, const float* Gq,
                            const int* rowptr, int slice, int slice2, int nZ, int batch, size_t rowptr_stride,
-                           cudaStream_t st);
+                           cudaStream_t st, int cfg_stride = 1, int cfg_off2 = 0);
 // S3: inverse row FFT of W -> V_a + i V_b; per slice p < npair: exp(i V_p (1 + i imPot)) -> row FFT
 //     -> D[2 b + p] (band columns only)
 void launch_transmit_rows(const SweepGeom& g, const cpx* W, cpx* D, int npair, float imPot, int batch,

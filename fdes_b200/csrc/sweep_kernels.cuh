@@ -231,7 +231,7 @@ template <int N>
 __global__ void __launch_bounds__(RowCfg<N>::THREADS, RowCfg<N>::MIN_CTAS)
 k_density_rows(cpx* __restrict__ A, const int* __restrict__ rowptr, const int* __restrict__ rec_col,
                const float* __restrict__ rec_w, int slice, int slice2, int nZ, size_t rec_stride,
-               size_t rp_stride, const cpx* __restrict__ tw)
+               size_t rp_stride, int cfg_stride, int cfg_off2, const cpx* __restrict__ tw)
 {
     pdl_prologue();
     using C = RowCfg<N>;
@@ -241,11 +241,15 @@ k_density_rows(cpx* __restrict__ A, const int* __restrict__ rowptr, const int* _
     const RowSync<N> sync(line);
     const int z = blockIdx.y, b = blockIdx.z;
     const int row = blockIdx.x * C::RPB + line;
-    const int* rp = rowptr + (size_t)b * rp_stride + (size_t)(slice * nZ + z) * N;
+    // image b of this launch carries slice `slice` of configuration bA (real part) and slice `slice2` of
+    // configuration bB (imaginary part): bA = bB = b for a pair of consecutive slices, bA = 2b, bB = 2b + 1
+    // when the odd last slices of two configurations share a transform
+    const int bA = b * cfg_stride, bB = bA + cfg_off2;
+    const int* rp = rowptr + (size_t)bA * rp_stride + (size_t)(slice * nZ + z) * N;
     const int lo = rp[row], hi = rp[row + 1];
     int lo2 = 0, hi2 = 0;
     if (slice2 >= 0) {
-        const int* rp2 = rowptr + (size_t)b * rp_stride + (size_t)(slice2 * nZ + z) * N;
+        const int* rp2 = rowptr + (size_t)bB * rp_stride + (size_t)(slice2 * nZ + z) * N;
         lo2 = rp2[row]; hi2 = rp2[row + 1];
     }
     // rows without deposits are never read by S2 (it consults the same row pointers)
@@ -257,10 +261,12 @@ k_density_rows(cpx* __restrict__ A, const int* __restrict__ rowptr, const int* _
     if (theta == 0) {
         // sorted, stable order -> the summation order is fixed (deterministic, unlike the
         // float atomicAdd of squareAtoms_d, src/crystalMaker.cu:100-119)
-        const int* cc = rec_col + (size_t)b * rec_stride;
-        const float* ww = rec_w + (size_t)b * rec_stride;
+        const int* cc = rec_col + (size_t)bA * rec_stride;
+        const float* ww = rec_w + (size_t)bA * rec_stride;
         for (int i = lo; i < hi; i++) dens[cc[i]].x += ww[i];
-        for (int i = lo2; i < hi2; i++) dens[cc[i]].y += ww[i];
+        const int* cc2 = rec_col + (size_t)bB * rec_stride;
+        const float* ww2 = rec_w + (size_t)bB * rec_stride;
+        for (int i = lo2; i < hi2; i++) dens[cc2[i]].y += ww2[i];
     }
     __syncthreads();
     cpx x[E];
@@ -275,14 +281,14 @@ k_density_rows(cpx* __restrict__ A, const int* __restrict__ rowptr, const int* _
 template <int NN>
 void launch_density_rows_n(const SweepGeom& g, cpx* A, const int* rowptr, const int* rec_col,
                          const float* rec_w, int slice, int slice2, int nZ, int batch, size_t rec_stride,
-                         size_t rowptr_stride, cudaStream_t st)
+                         size_t rowptr_stride, int cfg_stride, int cfg_off2, cudaStream_t st)
 {
     using C = RowCfg<NN>;
     const size_t smem = C::SMEM + (size_t)C::RPB * NN * sizeof(cpx);
     FDES_ALLOW_SMEM((k_density_rows<NN>), smem);
     dim3 grid(NN / C::RPB, nZ, batch);
     launch_pdl(k_density_rows<NN>, dim3(grid), dim3(C::THREADS), smem, st, A, rowptr, rec_col, rec_w, slice, slice2, nZ,
-                                                      rec_stride, rowptr_stride, g.tw);
+                                                      rec_stride, rowptr_stride, cfg_stride, cfg_off2, g.tw);
     FDES_LAUNCH_CHECK();
 }
 
@@ -293,7 +299,7 @@ template <int N>
 __global__ void __launch_bounds__(ColCfg<N>::THREADS, ColCfg<N>::MIN_CTAS)
 k_potential_cols(cpx* __restrict__ B, const cpx* __restrict__ A, const float* __restrict__ Gq,
                  const int* __restrict__ rowptr, int slice, int slice2, int nZ, size_t rp_stride,
-                 const cpx* __restrict__ tw)
+                 int cfg_stride, int cfg_off2, const cpx* __restrict__ tw)
 {
     pdl_prologue();
     using C = ColCfg<N>;
@@ -309,9 +315,10 @@ k_potential_cols(cpx* __restrict__ B, const cpx* __restrict__ A, const float* __
     for (int m = 0; m < E; m++) acc[m] = make_float2(0.f, 0.f);
     bool any = false;
     for (int z = 0; z < nZ; z++) {
-        const int* rp = rowptr + (size_t)b * rp_stride + (size_t)(slice * nZ + z) * N;
+        const int bA = b * cfg_stride, bB = bA + cfg_off2;     // configurations of the two parts (see k_density_rows)
+        const int* rp = rowptr + (size_t)bA * rp_stride + (size_t)(slice * nZ + z) * N;
         // second slice of the pair (imaginary part); the same slice again when there is none
-        const int* rp2 = slice2 >= 0 ? rowptr + (size_t)b * rp_stride + (size_t)(slice2 * nZ + z) * N : rp;
+        const int* rp2 = slice2 >= 0 ? rowptr + (size_t)bB * rp_stride + (size_t)(slice2 * nZ + z) * N : rp;
         if (rp[N] == rp[0] && rp2[N] == rp2[0]) continue;  // species absent from both slices (CTA-uniform)
         const cpx* Az = A + (size_t)(b * nZ + z) * N * N + kx0;
         cpx x[E];
@@ -337,7 +344,7 @@ template <int N>
 __global__ void __launch_bounds__(PipeCfg<N>::THREADS, 1)
 k_potential_cols_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                      const float* __restrict__ Gq, const int* __restrict__ rowptr, int slice, int slice2, int nZ,
-                     size_t rp_stride, int tiles_x, int ntiles, const cpx* __restrict__ tw)
+                     size_t rp_stride, int cfg_stride, int cfg_off2, int tiles_x, int ntiles, const cpx* __restrict__ tw)
 {
     pdl_prologue();
     using C = PipeCfg<N>;
@@ -348,8 +355,8 @@ k_potential_cols_tma(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     const int theta = pipe.theta;
     auto rows_of = [=](int b, int z, int sl) { return rowptr + (size_t)b * rp_stride + (size_t)(sl * nZ + z) * N; };
     auto present = [=](int b, int z) {
-        const int* rp = rows_of(b, z, slice);
-        const int* rp2 = slice2 >= 0 ? rows_of(b, z, slice2) : rp;
+        const int* rp = rows_of(b * cfg_stride, z, slice);
+        const int* rp2 = slice2 >= 0 ? rows_of(b * cfg_stride + cfg_off2, z, slice2) : rp;
         return rp[N] != rp[0] || rp2[N] != rp2[0];
     };
     // first present species at or after (t, z), walking this CTA's tiles; t >= ntiles: none left
@@ -377,8 +384,8 @@ k_potential_cols_tma(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         bool any = false;
         while (lt == t) {                      // the landed (or landing) tile belongs to this output tile
             const int z = lz;
-            const int* rp = rows_of(b, z, slice);
-            const int* rp2 = slice2 >= 0 ? rows_of(b, z, slice2) : rp;
+            const int* rp = rows_of(b * cfg_stride, z, slice);
+            const int* rp2 = slice2 >= 0 ? rows_of(b * cfg_stride + cfg_off2, z, slice2) : rp;
             lz++;
             seek(lt, lz);
             cpx x[E];
@@ -403,7 +410,7 @@ k_potential_cols_tma(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 template <int NN>
 void launch_potential_cols_n(const SweepGeom& g, cpx* B, const cpx* A, const float* Gq,
                            const int* rowptr, int slice, int slice2, int nZ, int batch, size_t rowptr_stride,
-                           cudaStream_t st)
+                           int cfg_stride, int cfg_off2, cudaStream_t st)
 {
     if constexpr (pipe_supported<NN>()) {
         if (pipe_enabled()) {
@@ -414,7 +421,7 @@ void launch_potential_cols_n(const SweepGeom& g, cpx* B, const cpx* A, const flo
             tile_map(&mapA, A, NN, batch * nZ, P::CW, P::BR);
             tile_map(&mapB, B, NN, batch, P::CW, P::BR);
             launch_pdl(k_potential_cols_tma<NN>, dim3(pipe_grid(ntiles)), dim3(P::THREADS), P::SMEM, st, mapA, mapB, Gq, rowptr, slice, slice2,
-                                                                                  nZ, rowptr_stride, tiles_x, ntiles, g.tw);
+                                                                                  nZ, rowptr_stride, cfg_stride, cfg_off2, tiles_x, ntiles, g.tw);
             FDES_LAUNCH_CHECK();
             return;
         }
@@ -423,7 +430,7 @@ void launch_potential_cols_n(const SweepGeom& g, cpx* B, const cpx* A, const flo
     FDES_ALLOW_SMEM((k_potential_cols<NN>), C::SMEM);
     dim3 grid(NN / C::CW, batch);
     launch_pdl(k_potential_cols<NN>, dim3(grid), dim3(C::THREADS), C::SMEM, st, B, A, Gq, rowptr, slice, slice2, nZ,
-                                                           rowptr_stride, g.tw);
+                                                           rowptr_stride, cfg_stride, cfg_off2, g.tw);
     FDES_LAUNCH_CHECK();
 }
 

@@ -36,14 +36,15 @@ int rows_per_block(int N) { return vt(N).rows_per_block; }
 int cols_per_block(int N) { return vt(N).cols_per_block; }
 
 void launch_density_rows(const SweepGeom& g, cpx* A, const int* rowptr, const int* rec_col, const float* rec_w,
-                         int slice, int slice2, int nZ, int batch, size_t rec_stride, size_t rowptr_stride, cudaStream_t st)
+                         int slice, int slice2, int nZ, int batch, size_t rec_stride, size_t rowptr_stride, cudaStream_t st,
+                         int cfg_stride, int cfg_off2)
 {
-    vt(g.N).density_rows(g, A, rowptr, rec_col, rec_w, slice, slice2, nZ, batch, rec_stride, rowptr_stride, st);
+    vt(g.N).density_rows(g, A, rowptr, rec_col, rec_w, slice, slice2, nZ, batch, rec_stride, rowptr_stride, cfg_stride, cfg_off2, st);
 }
 void launch_potential_cols(const SweepGeom& g, cpx* B, const cpx* A, const float* Gq, const int* rowptr, int slice,
-                           int slice2, int nZ, int batch, size_t rowptr_stride, cudaStream_t st)
+                           int slice2, int nZ, int batch, size_t rowptr_stride, cudaStream_t st, int cfg_stride, int cfg_off2)
 {
-    vt(g.N).potential_cols(g, B, A, Gq, rowptr, slice, slice2, nZ, batch, rowptr_stride, st);
+    vt(g.N).potential_cols(g, B, A, Gq, rowptr, slice, slice2, nZ, batch, rowptr_stride, cfg_stride, cfg_off2, st);
 }
 void launch_transmit_rows(const SweepGeom& g, const cpx* W, cpx* D, int npair, float imPot, int batch, cudaStream_t st)
 {

@@ -119,6 +119,30 @@ def test_batching_does_not_change_results(batch, fb):
     np.testing.assert_array_equal(ea, eb)
 
 
+@pytest.mark.parametrize("n", [128, 1024, 600])
+def test_odd_slice_count_pairs_last_slices_of_two_configurations(n, fb, orc, tmp_path):
+    """With an odd number of slices and an even batch the last slices of configurations 2j and 2j + 1 share one
+    complex transform through S1 / S2 / S3 (real and imaginary part), instead of running as half-empty pairs:
+    same result as batch 1 up to rounding, and parity with the oracle (3 species, absorptive, 5 slices,
+    4 frozen-phonon configurations; 1024: TMA-pipelined sweeps, 600: generic sweeps)."""
+    from fdes_b200 import specimens
+    d = 0.2e-10
+    atoms = specimens.random_slab(200, n * d, 5 * 2e-10, seed=n, species=(79, 14, 8))
+    cnf = specimens.write_cnf(tmp_path / "odd.cnf", image_size=n // 2, border_size=n // 4, slices=5, pixel_size=d,
+                              slice_thickness=2e-10, atoms=atoms, voltage=120e3, absorptive=0.03, frozen_phonons=4)
+    out = {}
+    for batch in (1, 2, 4):
+        with fb.Simulation(cnf, want_exitwave=True, batch=batch) as sim:
+            assert sim.m3 == 5
+            out[batch] = sim.simulate()
+    for batch in (2, 4):
+        assert rel_l2(out[batch][1], out[1][1]) < 1e-6 and rel_l2(out[batch][0], out[1][0]) < 1e-6
+    p, Z, xyz, dwf, occ = orc.read_cnf(str(cnf))
+    res = orc.build_measurements(p, Z, xyz, dwf, occ)
+    assert rel_l2(out[4][1], res.exitwave) < TOL_WAVE
+    assert rel_l2(out[4][0], res.image) < TOL_INTENSITY
+
+
 def test_rank_shards_sum_to_the_whole(fb, tmp_path):
     """rank/world sharding of the phonon configurations incl. the RNG positioning: for every
     measurement k the partial sums of (rank 0, rank 1) of 2 add up to the single-rank result (the
