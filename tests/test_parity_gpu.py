@@ -412,6 +412,31 @@ def test_stem_scan_against_oracle(frozen, fb, orc, tmp_path):
     np.testing.assert_allclose(tot, N * N, rtol=1e-5)
 
 
+@pytest.mark.parametrize("N", [320, 800, 1000, 600])
+def test_stem_detector_sums_at_non_power_of_two_grids(N, fb, orc, tmp_path):
+    """The detector reduction runs with 160 / 320 / 200 threads per CTA at 320 / 800 / 1000 (and on the generic
+    sweeps at 600): every thread's partial sum must reach the result.  Empty specimen: a detector that covers the
+    whole pattern collects n1 * n2 (probe normalisation, src/multisliceSimulation.cu:578-580); with atoms: parity
+    with the oracle's per-probe restatement for two positions and three rings."""
+    from fdes_b200 import specimens
+    d = 0.25e-10
+    atoms = specimens.random_slab(30, N * d * 0.5, 2 * 2e-10, seed=N, species=(79, 14))
+    cnf = specimens.write_cnf(tmp_path / "stem.cnf", image_size=N, border_size=0, slices=2, pixel_size=d,
+                              slice_thickness=2e-10, atoms=atoms, voltage=200e3, mode=2, objective_aperture=10e-3)
+    pos = np.array([[0, 0], [5, -3]], np.float32) * np.float32(d)
+    det = np.array([[0, 8], [8, 30], [30, 120]], np.float32)
+    with fb.Simulation(cnf, batch=2) as sim:
+        got, _ = sim.stem_scan(pos, det)
+    p, Z, xyz, dwf, occ = orc.read_cnf(str(cnf))
+    want = _oracle_stem(orc, p, Z, [xyz], occ, pos, det)
+    np.testing.assert_allclose(got, want, rtol=TOL_INTENSITY, atol=1e-4 * want.max())
+    a0 = np.ascontiguousarray(atoms, np.float32)
+    a0[:, 3] = 1e-6                                    # all atoms outside the slab
+    with fb.Simulation(cnf, atoms6=a0, batch=2) as sim:
+        tot, _ = sim.stem_scan(pos, np.array([[0, 1000]], np.float32))
+    np.testing.assert_allclose(tot, N * N, rtol=1e-5)
+
+
 def test_stem_scan_needs_probe_mode(fb):
     with fb.Simulation(DATA / "tem64.cnf") as sim:
         with pytest.raises(fb.FdesError, match="mode 2"):
