@@ -25,6 +25,10 @@
 #include <cuda.h>
 #include <cstdint>
 
+#ifndef FDES_SPLIT_2048
+#define FDES_SPLIT_2048 1
+#endif
+
 namespace fdes {
 
 // ---------------------------------------------------------------------------------------------
@@ -107,6 +111,8 @@ struct PipeCfg {
                          OFF_BAR = OFF_TW + TW_ELEMS * 8;
     static constexpr size_t SMEM = OFF_BAR + 64;
     static constexpr bool WARP_SYNC = (T <= 32);
+    // 2048-point columns as TWO 1024-point transforms, each inside one warp (see ColPipe::acquire_fft)
+    static constexpr bool SPLIT = (N == 2048) && (FDES_SPLIT_2048 != 0);
     static_assert(N >= 512 && (N & (N - 1)) == 0 && N <= 4096, "pipelined column tiles: N = 512 .. 4096, power of two");
     static_assert(T % 8 == 0, "swizzle phase of a thread must not depend on m");
 };
@@ -130,9 +136,10 @@ struct PipeSync {
 //                         starts the store
 // finish() before the kernel exits.
 // DBG (microbenchmarks only): bit 0 = no tile loads, bit 1 = no tile stores.
-template <int N, int DBG = 0>
+template <int N, int DBG = 0, bool ALLOW_SPLIT = true>
 struct ColPipe {
     using C = PipeCfg<N>;
+    static constexpr bool SPLIT = C::SPLIT && ALLOW_SPLIT;
     static constexpr int E = C::E, T = C::T;
     unsigned char* base;       // 1024-byte aligned shared memory
     uint64_t *full, *sfree;
@@ -236,6 +243,161 @@ struct ColPipe {
     __device__ __forceinline__ void finish() const
     {
         if (threadIdx.x == 0) tma_store_wait<0>();
+    }
+
+    // -----------------------------------------------------------------------------------------
+    // Forward transform of the landed tile / inverse transform into the outgoing tile.
+    //
+    // Default: acquire + fft_line (forward), fft_line + release (inverse); x[m] <-> ky = ky0() + m*T.
+    //
+    // SPLIT (N = 2048, two warps w = 0, 1 per column): a radix-2 decimation step is folded into the tile
+    // accesses, so that each warp runs a 1024-point transform of its own (32 x 32: ONE exchange, warp-level
+    // synchronisation) instead of the two warps sharing three passes with named barriers around two
+    // exchanges:
+    //   forward (decimation in frequency), on the way out of the landing buffer, j = lane + 32 m < 1024:
+    //       warp 0: a[j] = f[j] + f[j + 1024]                  -> X[2k]     = FFT_1024(a)[k]
+    //       warp 1: b[j] = (f[j] - f[j + 1024]) W^j            -> X[2k + 1] = FFT_1024(b)[k]
+    //     (each warp reads both halves of the column: 64 LDS.64 per thread, no exchange, no barrier)
+    //   the spectrum is held as x[m] = X[2 (lane + 32 m) + w] = X[ky0() + m*T] with ky0() = 2 lane + w
+    //   inverse (decimation in time): A = IFFT_1024(X even) in warp 0, B = IFFT_1024(X odd) in warp 1,
+    //       f[j] = A[j] + conj(W)^j B[j],  f[j + 1024] = A[j] - conj(W)^j B[j]
+    //     by a HALF exchange: warp 0 hands A[j], m >= 16, to warp 1 and takes conj(W)^j B[j], m < 16; each
+    //     thread then writes 32 points of the outgoing tile (16 STS + 16 LDS per thread, one named barrier).
+    // Per tile and thread 256 shared-memory accesses and 1 named barrier instead of 320 and 8.
+    // -----------------------------------------------------------------------------------------
+    static constexpr int split_tw_offset()                                   // W^j = exp(-2 pi i j / N), j < N/2
+    {
+        if constexpr (SPLIT) return twiddle_offset<N, E, N / 2>() + N / 2;
+        else return 0;
+    }
+    static constexpr int SPLIT_TW = split_tw_offset();
+    static constexpr int HALF_LS = line_smem_elems<E>(N / 2);               // exchange region of one warp
+    __device__ __forceinline__ int ky0() const
+    {
+        if constexpr (SPLIT) return 2 * (theta & 31) + (theta >> 5);
+        else return theta;
+    }
+    template <class Keep>
+    __device__ __forceinline__ void acquire_fft(cpx (&x)[E], bool have_next, const CUtensorMap* map, int x0_next, int z_next,
+                                                Keep keep)
+    {
+        if constexpr (!SPLIT) {
+            acquire(x, have_next, map, x0_next, z_next, keep);
+            fft_line_tw<N, E, -1>(x, sm(), theta, tw(), sync());
+        } else {
+            const int w = theta >> 5, lane = theta & 31;
+            if (!(DBG & 1)) mbar_wait(full, nload & 1);
+            nload++;
+            const uint32_t o = (uint32_t)lane * C::ROWB + (uint32_t)line * 8;
+            const unsigned char* p = base + C::OFF_L + (o ^ (((o >> 7) & C::SWZ_MASK) << 4));
+            const auto twd = tw();
+            if (w == 0) {
+#pragma unroll
+                for (int m = 0; m < E; m++) {
+                    const int j = lane + 32 * m;
+                    cpx v0 = *reinterpret_cast<const cpx*>(p + m * (32 * C::ROWB));
+                    cpx v1 = *reinterpret_cast<const cpx*>(p + m * (32 * C::ROWB) + (N / 2) * C::ROWB);
+                    if (!keep(j)) v0 = make_float2(0.f, 0.f);
+                    if (!keep(j + N / 2)) v1 = make_float2(0.f, 0.f);
+                    x[m] = padd(v0, v1);
+                }
+            } else {
+                split_first_odd<0>(x, p, lane, twd, keep);
+            }
+            __syncthreads();                       // every thread has its points: L may be overwritten
+            if (threadIdx.x == 0 && have_next) issue_load(map, x0_next, z_next);
+            cpx* smw = reinterpret_cast<cpx*>(base + C::OFF_X) + line * C::LSTRIDE + w * HALF_LS;
+            fft_line_tw<N / 2, E, -1>(x, smw, lane, twd, SyncWarp());
+        }
+    }
+    __device__ __forceinline__ void acquire_fft(cpx (&x)[E], bool have_next, const CUtensorMap* map, int x0_next, int z_next)
+    {
+        acquire_fft(x, have_next, map, x0_next, z_next, KeepEvery());
+    }
+    // x[M] = (f[j] - f[j + N/2]) W^j, j = lane + 32 M (compile-time table offsets)
+    template <int M, class TW, class Keep>
+    __device__ __forceinline__ void split_first_odd(cpx (&x)[E], const unsigned char* p, int lane, TW twd, Keep keep) const
+    {
+        if constexpr (M < E) {
+            const int j = lane + 32 * M;
+            cpx v0 = *reinterpret_cast<const cpx*>(p + M * (32 * C::ROWB));
+            cpx v1 = *reinterpret_cast<const cpx*>(p + M * (32 * C::ROWB) + (N / 2) * C::ROWB);
+            if (!keep(j)) v0 = make_float2(0.f, 0.f);
+            if (!keep(j + N / 2)) v1 = make_float2(0.f, 0.f);
+            x[M] = cmul(psub(v0, v1), twd.template at<SPLIT_TW + 32 * M>(lane));
+            split_first_odd<M + 1>(x, p, lane, twd, keep);
+        }
+    }
+    template <int M, class TW>
+    __device__ __forceinline__ void split_last_odd(cpx (&x)[E], int lane, TW twd) const
+    {
+        if constexpr (M < E) {
+            x[M] = cmul_conj(x[M], twd.template at<SPLIT_TW + 32 * M>(lane));
+            split_last_odd<M + 1>(x, lane, twd);
+        }
+    }
+    // inverse transform (skipped for an all-zero spectrum: do_fft = false), optional scale, and hand-over
+    // of the tile
+    template <bool SCALE = false>
+    __device__ __forceinline__ void ifft_release(cpx (&x)[E], bool do_fft, const CUtensorMap* map, int x0, int z, float scale = 1.f)
+    {
+        if constexpr (!SPLIT) {
+            if (do_fft) fft_line_tw<N, E, 1>(x, sm(), theta, tw(), sync());
+            if constexpr (SCALE) {
+#pragma unroll
+                for (int m = 0; m < E; m++) x[m] = make_float2(x[m].x * scale, x[m].y * scale);
+            }
+            release(x, map, x0, z);
+        } else {
+            const int w = theta >> 5, lane = theta & 31;
+            const auto twd = tw();
+            cpx* col = reinterpret_cast<cpx*>(base + C::OFF_X) + line * C::LSTRIDE;
+            cpx* mine = col + w * HALF_LS;
+            const cpx* other = col + (1 - w) * HALF_LS;
+            if (do_fft) fft_line_tw<N / 2, E, 1>(x, mine, lane, twd, SyncWarp());
+            if constexpr (SCALE) {
+#pragma unroll
+                for (int m = 0; m < E; m++) x[m] = make_float2(x[m].x * scale, x[m].y * scale);
+            }
+            // the warp's own exchange region is free after its transform; the partner reads it after the
+            // barrier and before the __syncthreads below, i.e. before this warp's next transform writes it
+            if (w == 0) {
+#pragma unroll
+                for (int m = 0; m < E / 2; m++) mine[m * 32 + lane] = x[m + E / 2];
+            } else {
+                split_last_odd<0>(x, lane, twd);
+#pragma unroll
+                for (int m = 0; m < E / 2; m++) mine[m * 32 + lane] = x[m];
+            }
+            sync()();                              // the two warps of this column
+            if (it > 0 && !(DBG & 2)) mbar_wait(sfree, (it - 1) & 1);
+            const uint32_t o = (uint32_t)lane * C::ROWB + (uint32_t)line * 8;
+            unsigned char* p = base + C::OFF_S + (o ^ (((o >> 7) & C::SWZ_MASK) << 4));
+            if (w == 0) {
+#pragma unroll
+                for (int m = 0; m < E / 2; m++) {
+                    const cpx b = other[m * 32 + lane];
+                    *reinterpret_cast<cpx*>(p + m * (32 * C::ROWB)) = padd(x[m], b);
+                    *reinterpret_cast<cpx*>(p + m * (32 * C::ROWB) + (N / 2) * C::ROWB) = psub(x[m], b);
+                }
+            } else {
+#pragma unroll
+                for (int m = E / 2; m < E; m++) {
+                    const cpx a = other[(m - E / 2) * 32 + lane];
+                    *reinterpret_cast<cpx*>(p + m * (32 * C::ROWB)) = padd(a, x[m]);
+                    *reinterpret_cast<cpx*>(p + m * (32 * C::ROWB) + (N / 2) * C::ROWB) = psub(a, x[m]);
+                }
+            }
+            fence_proxy_async();
+            __syncthreads();
+            if (threadIdx.x == 0 && !(DBG & 2)) {
+#pragma unroll
+                for (int k = 0; k < C::NBOX; k++)
+                    tma_store_3d(map, base + C::OFF_S + k * C::BR * C::ROWB, x0, k * C::BR, z);
+                tma_store_commit();
+            }
+            it++;
+        }
     }
 };
 

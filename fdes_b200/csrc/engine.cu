@@ -165,7 +165,7 @@ Engine::Engine(const Params& pin, const Atoms& atoms, const EngineOptions& opt) 
                                  "uses a transposed cuFFT plan for m1 != m2, src/crystalMaker.cu:575)");
     if (!fft_size_supported(p_.m1))
         throw std::runtime_error("grid size " + std::to_string(p_.m1) +
-                                 " unsupported: sample size (image + 2*border) must be even and between 8 and 8192");
+                                 " unsupported: sample size (image + 2*border) must be between 8 and 8192");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         throw std::runtime_error("no CUDA device: fdes_b200 has no CPU fallback");

@@ -445,6 +445,89 @@ __device__ __forceinline__ void fft_line(cpx (&x)[E], cpx* sm, int theta, const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// split lines: a line of N = 2 x 1024 points on the two warps w = 0, 1 of the line
+// ---------------------------------------------------------------------------------------------
+// With 32 points per thread a 2048-point line needs three Stockham passes (32 x 32 x 2) and two full
+// exchanges between two warps (named barriers).  Folding the radix-2 step into the accesses that happen
+// anyway leaves each warp a 1024-point transform of its own (32 x 32: one exchange, __syncwarp only):
+//   first step of a transform taken from memory (decimation in frequency), j = lane + 32 m < N/2:
+//       warp 0: a[j] = f[j] + f[j + N/2]            X[2k]     = FFT_{N/2}(a)[k]
+//       warp 1: b[j] = (f[j] - f[j + N/2]) W^j      X[2k + 1] = FFT_{N/2}(b)[k]
+//     (each warp reads both halves of the line; the result is held as x[m] = X[2 (lane + 32 m) + w])
+//   last step of a transform that goes to memory (decimation in time), from x[m] = g[2 (lane + 32 m) + w]:
+//       A = FFT_{N/2}(g even) in warp 0, B = FFT_{N/2}(g odd) in warp 1,
+//       X[k] = A[k] + W^k B[k],  X[k + N/2] = A[k] - W^k B[k]
+//     by a HALF exchange: warp 0 hands A[k], m >= 16, to warp 1 and takes W^k B[k], m < 16; every thread
+//     then owns 16 values of k and emits X[k] and X[k + N/2] (16 STS + 16 LDS per thread, one barrier of
+//     the two warps).
+// W^j = exp(DIR 2 pi i j / N) is the t = 1 row of the line's own radix-2 pass table.
+template <int N, int E>
+__host__ __device__ constexpr int split_tw_offset() { return twiddle_offset<N, E, N / 2>() + N / 2; }
+
+template <int N, int E, int DIR, int M, class TW, class Load>
+__device__ __forceinline__ void split_dif_odd(cpx (&x)[E], int lane, TW tw, Load load)
+{
+    if constexpr (M < E) {
+        const cpx d = psub(load(lane, M), load(lane, M + E));
+        const cpx wv = tw.template at<split_tw_offset<N, E>() + 32 * M>(lane);
+        x[M] = DIR < 0 ? cmul(d, wv) : cmul_conj(d, wv);
+        split_dif_odd<N, E, DIR, M + 1>(x, lane, tw, load);
+    }
+}
+// load(lane, blk) = f[lane + 32 blk], blk = 0 .. 2E-1 (blk is a compile-time constant after unrolling)
+template <int N, int E, int DIR, class TW, class Load>
+__device__ __forceinline__ void split_dif(cpx (&x)[E], int w, int lane, TW tw, Load load)
+{
+    static_assert(N == 64 * E, "two warps of 32 threads with E points each");
+    if (w == 0) {
+#pragma unroll
+        for (int m = 0; m < E; m++) x[m] = padd(load(lane, m), load(lane, m + E));
+    } else {
+        split_dif_odd<N, E, DIR, 0>(x, lane, tw, load);
+    }
+}
+template <int N, int E, int DIR, int M, class TW>
+__device__ __forceinline__ void split_twiddle_all(cpx (&x)[E], int lane, TW tw)
+{
+    if constexpr (M < E) {
+        const cpx wv = tw.template at<split_tw_offset<N, E>() + 32 * M>(lane);
+        x[M] = DIR < 0 ? cmul(x[M], wv) : cmul_conj(x[M], wv);
+        split_twiddle_all<N, E, DIR, M + 1>(x, lane, tw);
+    }
+}
+// mine / other: 16 x 32 exchange slots of this warp / of the partner warp; pair_sync: barrier of the two
+// warps; emit(lane, blk, lo, hi): X[lane + 32 blk] = lo, X[lane + 32 blk + N/2] = hi.
+// The caller must make sure that `mine` is not rewritten before the partner has read it.
+template <int N, int E, int DIR, class TW, class Sync, class Emit>
+__device__ __forceinline__ void split_dit_combine(cpx (&x)[E], int w, int lane, TW tw, cpx* mine, const cpx* other,
+                                                  Sync pair_sync, Emit emit)
+{
+    static_assert(N == 64 * E, "two warps of 32 threads with E points each");
+    if (w == 0) {
+#pragma unroll
+        for (int m = 0; m < E / 2; m++) mine[m * 32 + lane] = x[m + E / 2];
+    } else {
+        split_twiddle_all<N, E, DIR, 0>(x, lane, tw);
+#pragma unroll
+        for (int m = 0; m < E / 2; m++) mine[m * 32 + lane] = x[m];
+    }
+    pair_sync();
+    if (w == 0) {
+#pragma unroll
+        for (int m = 0; m < E / 2; m++) {
+            const cpx b = other[m * 32 + lane];
+            emit(lane, m, padd(x[m], b), psub(x[m], b));
+        }
+    } else {
+#pragma unroll
+        for (int m = E / 2; m < E; m++) {
+            const cpx a = other[(m - E / 2) * 32 + lane];
+            emit(lane, m, padd(a, x[m]), psub(a, x[m]));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // column tiles
 // ---------------------------------------------------------------------------------------------
 // Per-thread view of a column sweep: which column line it transforms, and how the CTA's tile

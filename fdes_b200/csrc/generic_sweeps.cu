@@ -1,4 +1,4 @@
-// fdes_b200 -- the multislice sweeps for ANY even grid size (run-time N): the fallback behind the
+// fdes_b200 -- the multislice sweeps for ANY grid size, even or odd (run-time N): the fallback behind the
 // register-resident kernels of sweep_kernels.cuh, which exist for a fixed list of sizes
 // (sweep_vtable.h).  The reference accepts every sample size m = n + 2 dn (src/paramStructure.cu:650-651,
 // cufftPlan2d at :676-679), e.g. image_size 600 or 675 + 2 * 100; those grids run here.
@@ -67,6 +67,10 @@ __device__ void g_fft(cpx*& a, cpx*& b, const GPlan& pl, int L, const cpx* __res
         const int M = N / r;                 // butterflies per line
         const int step = N / (Ns * r);       // twiddle exponent unit of this pass
         const int dstep = N / r;             // exponent unit of the radix-r DFT matrix
+        // Wd: the same table in double precision (appended to W, see gen_twiddles).  Long direct DFTs (prime
+        // factors beyond 16, e.g. N = 499) multiply and accumulate in double: a float32 sum of hundreds of
+        // terms loses a digit that the O(log N) stages of cuFFT keep.
+        const double* Wd = reinterpret_cast<const double*>(W + N);      // 8-byte aligned for any N
         for (int w = threadIdx.x; w < L * M * r; w += GT) {
             // one OUTPUT element per work item: (line l, butterfly j, output index s)
             const int s = w % r, j = (w / r) % M, l = w / (r * M);
@@ -74,17 +78,34 @@ __device__ void g_fft(cpx*& a, cpx*& b, const GPlan& pl, int L, const cpx* __res
             int q = k * step + s * dstep;    // exponent increment per input t
             q %= N;
             const cpx* in = a + l * N + j;
-            cpx acc = in[0];
-            int e = q;
-            for (int t = 1; t < r; t++) {
-                cpx tw = W[e];
-                if (dir > 0) tw.y = -tw.y;
-                acc = make_float2(acc.x + in[t * M].x * tw.x - in[t * M].y * tw.y,
-                                  acc.y + in[t * M].x * tw.y + in[t * M].y * tw.x);
-                e += q;
-                if (e >= N) e -= N;
+            cpx res;
+            if (r > 16) {
+                double ax = in[0].x, ay = in[0].y;
+                int e = q;
+                for (int t = 1; t < r; t++) {
+                    double2 tw = make_double2(Wd[2 * e], Wd[2 * e + 1]);
+                    if (dir > 0) tw.y = -tw.y;
+                    const double vx = in[t * M].x, vy = in[t * M].y;
+                    ax += vx * tw.x - vy * tw.y;
+                    ay += vx * tw.y + vy * tw.x;
+                    e += q;
+                    if (e >= N) e -= N;
+                }
+                res = make_float2((float)ax, (float)ay);
+            } else {
+                cpx acc = in[0];
+                int e = q;
+                for (int t = 1; t < r; t++) {
+                    cpx tw = W[e];
+                    if (dir > 0) tw.y = -tw.y;
+                    acc = make_float2(acc.x + in[t * M].x * tw.x - in[t * M].y * tw.y,
+                                      acc.y + in[t * M].x * tw.y + in[t * M].y * tw.x);
+                    e += q;
+                    if (e >= N) e -= N;
+                }
+                res = acc;
             }
-            b[l * N + (j - k) * r + k + s * Ns] = acc;
+            b[l * N + (j - k) * r + k + s * Ns] = res;
         }
         __syncthreads();
         cpx* t = a; a = b; b = t;
@@ -597,26 +618,33 @@ void gen_detector_cols(const SweepGeom& g, const cpx* Psi, float* partial, float
     g_detector_finish<<<(n + 127) / 128, 128, 0, st>>>(partial, out, tiles, rings.n, batch, weight);
     GEN_LAUNCHED();
 }
-// W[k] = exp(-2 pi i k / N), exact on the axes
+// W[k] = exp(-2 pi i k / N), exact on the axes: N float32 pairs, followed by the same N values as double
+// pairs (2 cpx slots each) for the long direct DFTs of g_fft
 std::vector<cpx> gen_twiddles(int N)
 {
-    std::vector<cpx> w((size_t)N);
+    std::vector<cpx> w((size_t)3 * N);
+    double* wd = reinterpret_cast<double*>(w.data() + N);
     for (int k = 0; k < N; k++) {
-        if (k == 0) w[k] = make_float2(1.f, 0.f);
-        else if (4 * k == N) w[k] = make_float2(0.f, -1.f);
-        else if (2 * k == N) w[k] = make_float2(-1.f, 0.f);
-        else if (4 * k == 3 * N) w[k] = make_float2(0.f, 1.f);
+        double c, s;
+        if (k == 0) { c = 1; s = 0; }
+        else if (4 * k == N) { c = 0; s = -1; }
+        else if (2 * k == N) { c = -1; s = 0; }
+        else if (4 * k == 3 * N) { c = 0; s = 1; }
         else {
             const double a = -2.0 * 3.14159265358979323846 * (double)k / (double)N;
-            w[k] = make_float2((float)cos(a), (float)sin(a));
+            c = cos(a); s = sin(a);
         }
+        w[k] = make_float2((float)c, (float)s);
+        wd[2 * k] = c; wd[2 * k + 1] = s;
     }
     return w;
 }
 
 }  // namespace
 
-bool generic_size_supported(int N) { return N >= 8 && N <= 8192 && N % 2 == 0; }
+// odd sizes too: the half-index convention i > N/2 -> i - N and the quarter tables (index min(k, N - k)
+// <= N/2) hold for either parity; a prime N is one direct O(N^2) DFT per line
+bool generic_size_supported(int N) { return N >= 8 && N <= 8192; }
 
 const SweepVTable* generic_sweep_vtable()
 {

@@ -337,7 +337,7 @@ void launch_area_mask_blend(cpx* psi, int N, int dn1, int dn2, cudaStream_t st)
 // NVLink peer mappings (cudaDeviceEnablePeerAccess) and adds them in the fixed order 0 .. n-1, so
 // the result does not depend on timing.  128-bit loads; no staging copies.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_peer_sum(float4* __restrict__ dst, PeerSources src, size_t n4)
+__global__ void k_peer_sum(float4* __restrict__ dst, PeerSources src, size_t n4, size_t n)
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         float4 a = dst[i];
@@ -347,12 +347,18 @@ __global__ void k_peer_sum(float4* __restrict__ dst, PeerSources src, size_t n4)
         }
         dst[i] = a;
     }
+    // the last n % 4 floats (odd grid sizes)
+    if (blockIdx.x == 0 && threadIdx.x < n - 4 * n4) {
+        const size_t i = 4 * n4 + threadIdx.x;
+        float a = reinterpret_cast<float*>(dst)[i];
+        for (int r = 0; r < src.n; r++) a += src.p[r][i];
+        reinterpret_cast<float*>(dst)[i] = a;
+    }
 }
 void launch_peer_sum(float* dst, const PeerSources& src, size_t n, cudaStream_t st)
 {
-    // n is a multiple of 4 for every grid of the engine (m1 * m2 floats, m1 even)
     const size_t n4 = n / 4;
-    k_peer_sum<<<(unsigned)std::min<size_t>((n4 + 255) / 256, 148 * 8), 256, 0, st>>>(reinterpret_cast<float4*>(dst), src, n4);
+    k_peer_sum<<<(unsigned)std::max<size_t>(1, std::min<size_t>((n4 + 255) / 256, 148 * 8)), 256, 0, st>>>(reinterpret_cast<float4*>(dst), src, n4, n);
 }
 
 }  // namespace fdes

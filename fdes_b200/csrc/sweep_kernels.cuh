@@ -351,8 +351,10 @@ k_potential_cols_tma(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     extern __shared__ __align__(1024) unsigned char pipe_smem[];
     constexpr int Q = N / 2 + 1;
     constexpr int E = C::E;
-    ColPipe<N> pipe(pipe_smem, tw);
-    const int theta = pipe.theta;
+    // no split lines here: each warp of a split column would evaluate the row predicates of BOTH halves
+    // (measured at 2048^2: 142 us against 135 us)
+    ColPipe<N, 0, false> pipe(pipe_smem, tw);
+    const int ky0 = pipe.ky0();                 // x[m] <-> ky = ky0 + m*T
     auto rows_of = [=](int b, int z, int sl) { return rowptr + (size_t)b * rp_stride + (size_t)(sl * nZ + z) * N; };
     auto present = [=](int b, int z) {
         const int* rp = rows_of(b * cfg_stride, z, slice);
@@ -390,19 +392,17 @@ k_potential_cols_tma(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             seek(lt, lz);
             cpx x[E];
             // rows without deposits were not written by S1: read them as zero
-            pipe.acquire(x, lt < ntiles, &mapA, (lt % tiles_x) * C::CW, (lt / tiles_x) * nZ + lz,
-                         [rp, rp2](int y) { return (rp[y + 1] > rp[y]) | (rp2[y + 1] > rp2[y]); });
+            pipe.acquire_fft(x, lt < ntiles, &mapA, (lt % tiles_x) * C::CW, (lt / tiles_x) * nZ + lz,
+                             [rp, rp2](int y) { return (rp[y + 1] > rp[y]) | (rp2[y + 1] > rp2[y]); });
             any = true;
-            fft_line_tw<N, E, -1>(x, pipe.sm(), theta, pipe.tw(), pipe.sync());
             const float* G = Gq + (size_t)z * Q * Q + (size_t)ax * Q;
-            quarter_table_apply<N, E, 0>(x, G + theta, G - theta,
+            quarter_table_apply<N, E, 0>(x, G + ky0, G - ky0,
                                          [](cpx v, float gz) { return pmul(v, make_float2(gz, gz)); });
 #pragma unroll
             for (int m = 0; m < E; m++) acc[m] = padd(acc[m], x[m]);
         }
         pipe.publish_store_drained();
-        if (any) fft_line_tw<N, E, 1>(acc, pipe.sm(), theta, pipe.tw(), pipe.sync());
-        pipe.release(acc, &mapB, kx0, b);
+        pipe.ifft_release(acc, any, &mapB, kx0, b);
     }
     pipe.finish();
 }
@@ -596,11 +596,112 @@ k_transmit_rows(const cpx* __restrict__ W, cpx* __restrict__ D, int npair, float
     }
 }
 
+// ---- 2048-point rows as two 1024-point transforms, one per warp (split_dif / split_dit_combine, fft_core.cuh) ----
+#ifndef FDES_SPLIT_ROWS_MIN_CTAS
+#define FDES_SPLIT_ROWS_MIN_CTAS 3
+#endif
+template <int N>
+constexpr bool row_split_supported() { return N == 2048 && FDES_SPLIT_2048 != 0; }
+// FDES_B200_NO_SPLIT=1 selects the three-pass row kernels (A/B comparisons)
+static bool row_split_enabled()
+{
+    static const bool on = [] { const char* e = getenv("FDES_B200_NO_SPLIT"); return !(e && e[0] == '1'); }();
+    return on;
+}
+template <int N>
+struct SplitRowCfg {
+    static constexpr int E = 32, H = N / 2, RPB = 2, THREADS = RPB * 64;
+    static constexpr int HLS = line_smem_elems<E>(H);                 // exchange region of one warp
+    static constexpr size_t SMEM_FFT = (size_t)RPB * 2 * HLS * sizeof(cpx);
+};
+struct PairSync {      // the two warps of row `line` of the CTA
+    int id;
+    __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+};
+
+// S3 for split rows: the inverse transform of W starts with the radix-2 step on the loads (no exchange), the
+// forward transforms of the two transmission functions end with the half exchange.  V and t0 are held at the
+// positions x = 2 (lane + 32 m) + w -- the pointwise exp(iV) does not care.
+template <int N>
+__global__ void __launch_bounds__(SplitRowCfg<N>::THREADS, FDES_SPLIT_ROWS_MIN_CTAS)
+k_transmit_rows_split(const cpx* __restrict__ W, cpx* __restrict__ D, int npair, float imPot, const cpx* __restrict__ tw)
+{
+    pdl_prologue();
+    using C = SplitRowCfg<N>;
+    extern __shared__ cpx smem[];
+    constexpr int E = C::E;
+    constexpr int lo_end = Band<N>::lo_end, hi_start = Band<N>::hi_start;
+    const int line = threadIdx.x / 64, theta = threadIdx.x % 64, w = theta >> 5, lane = theta & 31;
+    const size_t row = (size_t)blockIdx.x * C::RPB + line;
+    const cpx* src = W + ((size_t)blockIdx.y * N + row) * N;
+    cpx* mine = smem + (line * 2 + w) * C::HLS;
+    const cpx* other = smem + (line * 2 + (1 - w)) * C::HLS;
+    float* park = reinterpret_cast<float*>(smem + C::RPB * 2 * C::HLS) + line * (2 * N);   // V_a | V_b
+    const TwGlobal twg{tw};
+    const PairSync pair_sync{line + 1};
+    cpx x[E];
+#pragma unroll 1
+    for (int ph = 0; ph <= npair; ph++) {
+        if (ph == 0) {
+            // inverse transform as swap(FFT(swap(.)))
+            split_dif<N, E, -1>(x, w, lane, twg, [src](int ln, int blk) {
+                const cpx v = src[ln + 32 * blk];
+                return make_float2(v.y, v.x);
+            });
+        } else {
+            const float* V = park + (ph - 1) * N;
+            float amax = 0.f;
+#pragma unroll
+            for (int m = 0; m < E; m++) amax = fmaxf(amax, fabsf(V[theta + m * 64]));
+            if (amax < 1.0e5f) {
+#pragma unroll
+                for (int m = 0; m < E; m++) {
+                    const float v = V[theta + m * 64];
+                    x[m] = expi_packed(v);
+                    if (imPot != 0.f) {
+                        const float e = __expf(-(v * imPot));
+                        x[m] = make_float2(e * x[m].x, e * x[m].y);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < E; m++) x[m] = transmission(V[theta + m * 64], imPot);
+            }
+        }
+        fft_line_tw<N / 2, E, -1>(x, mine, lane, twg, SyncWarp());
+        if (ph == 0) {
+#pragma unroll
+            for (int m = 0; m < E; m++) {
+                park[theta + m * 64] = x[m].y;
+                park[N + theta + m * 64] = x[m].x;
+            }
+        } else {
+            cpx* out = D + ((size_t)(blockIdx.y * 2 + (ph - 1)) * N + row) * N;
+            split_dit_combine<N, E, -1>(x, w, lane, twg, mine, other, pair_sync, [out](int ln, int blk, cpx lo, cpx hi) {
+                if (in_band(32 * blk, lo_end, hi_start)) out[ln + 32 * blk] = lo;
+                if (in_band(32 * blk + N / 2, lo_end, hi_start)) out[ln + 32 * blk + N / 2] = hi;
+            });
+            if (ph < npair) pair_sync();      // the partner has read this warp's slots before the next transform reuses them
+        }
+    }
+}
+
 template <int NN>
 void launch_transmit_rows_n(const SweepGeom& g, const cpx* W, cpx* D, int npair, float imPot, int batch,
                           cudaStream_t st)
 {
     using C = RowCfg<NN>;
+    if constexpr (row_split_supported<NN>()) {
+        if (row_split_enabled()) {
+            using S = SplitRowCfg<NN>;
+            const size_t smem = S::SMEM_FFT + (size_t)S::RPB * NN * 2 * sizeof(float);
+            FDES_ALLOW_SMEM((k_transmit_rows_split<NN>), smem);
+            Band<NN>::check(g);
+            launch_pdl(k_transmit_rows_split<NN>, dim3(NN / S::RPB, batch), dim3(S::THREADS), smem, st, W, D, npair, imPot, g.tw);
+            FDES_LAUNCH_CHECK();
+            return;
+        }
+    }
     const size_t smem = C::SMEM + (size_t)C::RPB * NN * 2 * sizeof(float);
     FDES_ALLOW_SMEM((k_transmit_rows<NN>), smem);
     dim3 grid(NN / C::RPB, batch);
@@ -654,7 +755,7 @@ k_bandlimit_cols_tma(const __grid_constant__ CUtensorMap map, int npair, int lo_
     extern __shared__ __align__(1024) unsigned char pipe_smem[];
     constexpr int E = C::E;
     ColPipe<N> pipe(pipe_smem, tw);
-    const int theta = pipe.theta;
+    const int ky0 = pipe.ky0();                 // x[m] <-> ky = ky0 + m*T
     // image y of the tile list -> entry (b, p) of a [batch][2] stack (npair = 0: plain [batch])
     auto entry = [npair](int y) { return npair == 0 ? y : (y / npair) * 2 + y % npair; };
     int t = blockIdx.x;
@@ -669,19 +770,17 @@ k_bandlimit_cols_tma(const __grid_constant__ CUtensorMap map, int npair, int lo_
         const int kx0 = band_col0((t % tiles_x) * C::CW, lo_end, hi_start), kx = kx0 + pipe.line;
         const int tn = t + gridDim.x;
         cpx x[E];
-        pipe.acquire(x, tn < ntiles, &map, band_col0((tn % tiles_x) * C::CW, lo_end, hi_start), entry(tn / tiles_x));
-        fft_line_tw<N, E, -1>(x, pipe.sm(), theta, pipe.tw(), pipe.sync());
+        pipe.acquire_fft(x, tn < ntiles, &map, band_col0((tn % tiles_x) * C::CW, lo_end, hi_start), entry(tn / tiles_x));
         pipe.publish_store_drained();
         const int i1 = kx > N / 2 ? kx - N : kx;
 #pragma unroll
         for (int m = 0; m < E; m++) {
-            const int ky = theta + m * C::T;
+            const int ky = ky0 + m * C::T;
             const int i2 = ky > N / 2 ? ky - N : ky;
             const bool cut = ((float)(i1 * i1 + i2 * i2) * 9.f / (mind * mind)) > 1.f;
             x[m] = cut ? make_float2(0.f, 0.f) : make_float2(x[m].x * alpha, x[m].y * alpha);
         }
-        fft_line_tw<N, E, 1>(x, pipe.sm(), theta, pipe.tw(), pipe.sync());
-        pipe.release(x, &map, kx0, entry(t / tiles_x));
+        pipe.ifft_release(x, true, &map, kx0, entry(t / tiles_x));
     }
     pipe.finish();
 }
@@ -789,11 +888,90 @@ k_multiply_rows(cpx* __restrict__ Psi, const cpx* __restrict__ Tk, size_t e_batc
     }
 }
 
+// S5 for split rows: t = IFFT(E row) and psi = IFFT(Psi row) both start with the radix-2 step on the loads, so
+// the two factors meet at the same positions x = 2 (lane + 32 m) + w; only the forward transform of the product
+// needs the half exchange: one barrier of two warps per row instead of twelve.
+template <int N>
+__global__ void __launch_bounds__(SplitRowCfg<N>::THREADS, FDES_SPLIT_ROWS_MIN_CTAS)
+k_multiply_rows_split(cpx* __restrict__ Psi, const cpx* __restrict__ Tk, size_t e_batch_stride, int psi_full,
+                      const cpx* __restrict__ tw)
+{
+    pdl_prologue();
+    using C = SplitRowCfg<N>;
+    extern __shared__ cpx smem[];
+    constexpr int E = C::E;
+    constexpr int lo_end = Band<N>::lo_end, hi_start = Band<N>::hi_start;
+    const int line = threadIdx.x / 64, theta = threadIdx.x % 64, w = theta >> 5, lane = theta & 31;
+    const size_t row = (size_t)blockIdx.x * C::RPB + line;
+    const cpx* e = Tk + (size_t)blockIdx.y * e_batch_stride + row * N;
+    cpx* p = Psi + ((size_t)blockIdx.y * N + row) * N;
+    cpx* mine = smem + (line * 2 + w) * C::HLS;
+    const cpx* other = smem + (line * 2 + (1 - w)) * C::HLS;
+    cpx* park = smem + C::RPB * 2 * C::HLS + line * N;
+    const TwGlobal twg{tw};
+    cpx x[E];
+#pragma unroll 1
+    for (int ph = 0; ph < 3; ph++) {
+        if (ph == 0) {
+            split_dif<N, E, -1>(x, w, lane, twg, [e](int ln, int blk) {
+                const cpx v = in_band(32 * blk, lo_end, hi_start) ? e[ln + 32 * blk] : make_float2(0.f, 0.f);
+                return make_float2(v.y, v.x);
+            });
+            // pull the band columns of the psi row into L2 for the next phase (see k_multiply_rows)
+            constexpr int LINES = N * 8 / 128;
+            for (int l = theta; l < LINES; l += 64) {
+                const int kx = l * 16;
+                if (psi_full || in_band(kx, lo_end, hi_start)) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + kx));
+            }
+        } else if (ph == 1) {
+            if (psi_full) {
+                split_dif<N, E, -1>(x, w, lane, twg, [p](int ln, int blk) {
+                    const cpx v = ld_g(p + ln + 32 * blk);
+                    return make_float2(v.y, v.x);
+                });
+            } else {
+                split_dif<N, E, -1>(x, w, lane, twg, [p](int ln, int blk) {
+                    const cpx v = in_band(32 * blk, lo_end, hi_start) ? ld_g(p + ln + 32 * blk) : make_float2(0.f, 0.f);
+                    return make_float2(v.y, v.x);
+                });
+            }
+        }
+        fft_line_tw<N / 2, E, -1>(x, mine, lane, twg, SyncWarp());
+        if (ph == 0) {
+#pragma unroll
+            for (int m = 0; m < E; m++) park[theta + m * 64] = x[m];
+        } else if (ph == 1) {
+#pragma unroll
+            for (int m = 0; m < E; m++) {
+                const cpx a = park[theta + m * 64], b = x[m];
+                x[m] = cmul(make_float2(a.y, a.x), make_float2(b.y, b.x));
+            }
+        } else {
+            split_dit_combine<N, E, -1>(x, w, lane, twg, mine, other, PairSync{line + 1}, [p](int ln, int blk, cpx lo, cpx hi) {
+                if (in_band(32 * blk, lo_end, hi_start)) p[ln + 32 * blk] = lo;
+                if (in_band(32 * blk + N / 2, lo_end, hi_start)) p[ln + 32 * blk + N / 2] = hi;
+            });
+        }
+    }
+}
+
 template <int NN>
 void launch_multiply_rows_n(const SweepGeom& g, cpx* Psi, const cpx* E, size_t e_batch_stride,
                           int batch, bool psi_full, cudaStream_t st)
 {
     using C = typename MultiplyRowsCfg<NN>::type;
+    if constexpr (row_split_supported<NN>()) {
+        if (row_split_enabled()) {
+            using S = SplitRowCfg<NN>;
+            const size_t smem = S::SMEM_FFT + (size_t)S::RPB * NN * sizeof(cpx);
+            FDES_ALLOW_SMEM((k_multiply_rows_split<NN>), smem);
+            Band<NN>::check(g);
+            launch_pdl(k_multiply_rows_split<NN>, dim3(NN / S::RPB, batch), dim3(S::THREADS), smem, st, Psi, E, e_batch_stride,
+                       psi_full ? 1 : 0, g.tw);
+            FDES_LAUNCH_CHECK();
+            return;
+        }
+    }
     const size_t smem = C::SMEM + (size_t)C::RPB * NN * sizeof(cpx);
     FDES_ALLOW_SMEM((k_multiply_rows<NN>), smem);
     dim3 grid(NN / C::RPB, batch);
@@ -841,7 +1019,7 @@ k_propagate_cols_tma(const __grid_constant__ CUtensorMap map, const cpx* __restr
     constexpr int Q = N / 2 + 1;
     constexpr int E = C::E;
     ColPipe<N> pipe(pipe_smem, tw);
-    const int theta = pipe.theta;
+    const int ky0 = pipe.ky0();                 // x[m] <-> ky = ky0 + m*T
     int t = blockIdx.x;
     if (t >= ntiles) return;
     if (threadIdx.x == 0) {
@@ -852,13 +1030,11 @@ k_propagate_cols_tma(const __grid_constant__ CUtensorMap map, const cpx* __restr
         const int kx0 = band_col0((t % tiles_x) * C::CW, lo_end, hi_start), kx = kx0 + pipe.line;
         const int tn = t + gridDim.x;
         cpx x[E];
-        pipe.acquire(x, tn < ntiles, &map, band_col0((tn % tiles_x) * C::CW, lo_end, hi_start), tn / tiles_x);
-        fft_line_tw<N, E, -1>(x, pipe.sm(), theta, pipe.tw(), pipe.sync());
+        pipe.acquire_fft(x, tn < ntiles, &map, band_col0((tn % tiles_x) * C::CW, lo_end, hi_start), tn / tiles_x);
         pipe.publish_store_drained();
         const cpx* P = Pq + (size_t)min(kx, N - kx) * Q;
-        quarter_table_apply<N, E, 0>(x, P + theta, P - theta, [](cpx v, cpx p) { return cmul(v, p); });
-        fft_line_tw<N, E, 1>(x, pipe.sm(), theta, pipe.tw(), pipe.sync());
-        pipe.release(x, &map, kx0, t / tiles_x);
+        quarter_table_apply<N, E, 0>(x, P + ky0, P - ky0, [](cpx v, cpx p) { return cmul(v, p); });
+        pipe.ifft_release(x, true, &map, kx0, t / tiles_x);
     }
     pipe.finish();
 }
@@ -1118,7 +1294,7 @@ k_ctf_cols_tma(const __grid_constant__ CUtensorMap map_in, const __grid_constant
     extern __shared__ __align__(1024) unsigned char pipe_smem[];
     constexpr int E = C::E;
     ColPipe<N> pipe(pipe_smem, tw);
-    const int theta = pipe.theta;
+    const int ky0 = pipe.ky0();                 // x[m] <-> ky = ky0 + m*T
     int t = blockIdx.x;
     if (t >= ntiles) return;
     if (threadIdx.x == 0) {
@@ -1129,19 +1305,15 @@ k_ctf_cols_tma(const __grid_constant__ CUtensorMap map_in, const __grid_constant
         const int kx0 = band_col0((t % tiles_x) * C::CW, lo_end, hi_start), kx = kx0 + pipe.line;
         const int tn = t + gridDim.x;
         cpx x[E];
-        pipe.acquire(x, tn < ntiles, &map_in, band_col0((tn % tiles_x) * C::CW, lo_end, hi_start), tn / tiles_x);
-        fft_line_tw<N, E, -1>(x, pipe.sm(), theta, pipe.tw(), pipe.sync());
+        pipe.acquire_fft(x, tn < ntiles, &map_in, band_col0((tn % tiles_x) * C::CW, lo_end, hi_start), tn / tiles_x);
         pipe.publish_store_drained();
-        const cpx* tab = table + (size_t)kx * N + theta;
+        const cpx* tab = table + (size_t)kx * N + ky0;
 #pragma unroll
         for (int m = 0; m < E; m++) {
             const cpx w = ld_nc(tab + m * C::T);
             x[m] = make_float2(w.x * x[m].x - w.y * x[m].y, w.x * x[m].y + w.y * x[m].x);
         }
-        fft_line_tw<N, E, 1>(x, pipe.sm(), theta, pipe.tw(), pipe.sync());
-#pragma unroll
-        for (int m = 0; m < E; m++) x[m] = make_float2(x[m].x * scale, x[m].y * scale);
-        pipe.release(x, &map_out, kx0, t / tiles_x);
+        pipe.template ifft_release<true>(x, true, &map_out, kx0, t / tiles_x, scale);
     }
     pipe.finish();
 }

@@ -25,7 +25,7 @@ static const SweepVTable* find_vtable(int N)
 static const SweepVTable& vt(int N)
 {
     const SweepVTable* t = find_vtable(N);
-    if (!t) throw std::runtime_error("grid size " + std::to_string(N) + " unsupported: sample size (image + 2*border) must be even, 8 .. 8192");
+    if (!t) throw std::runtime_error("grid size " + std::to_string(N) + " unsupported: sample size (image + 2*border) must be 8 .. 8192");
     return *t;
 }
 

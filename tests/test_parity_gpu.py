@@ -225,10 +225,16 @@ def test_cli_binary(orc, tmp_path, oracle_runs):
 
 def test_unsupported_inputs_fail_loudly(fb, tmp_path):
     from fdes_b200 import specimens
-    specimens.write_cnf(tmp_path / "odd.cnf", image_size=41, border_size=20, slices=2, pixel_size=0.25e-10,
+    cnf = specimens.write_cnf(tmp_path / "rect.cnf", image_size=40, border_size=12, slices=2, pixel_size=0.25e-10,
+                              slice_thickness=2e-10, atoms=specimens.au_cuboctahedron(1))
+    text = open(cnf).read().replace("image_size_y: 40", "image_size_y: 48")
+    open(cnf, "w").write(text)
+    with pytest.raises(fb.FdesError, match="non-square"):
+        fb.Simulation(cnf)
+    specimens.write_cnf(tmp_path / "tiny.cnf", image_size=3, border_size=1, slices=2, pixel_size=0.25e-10,
                         slice_thickness=2e-10, atoms=specimens.au_cuboctahedron(1))
-    with pytest.raises(fb.FdesError, match="must be even"):
-        fb.Simulation(tmp_path / "odd.cnf")
+    with pytest.raises(fb.FdesError, match="between 8 and 8192"):
+        fb.Simulation(tmp_path / "tiny.cnf")
     with pytest.raises(fb.FdesError, match="cannot read"):
         fb.Simulation(tmp_path / "missing.cnf")
 
@@ -299,6 +305,22 @@ def _oracle_vs_library(cnf, fb, orc, atoms6=None):
     assert rel_l2(ew, res.exitwave) < TOL_WAVE
     assert rel_l2(img, res.image) < TOL_INTENSITY
     return img, ew
+
+
+@pytest.mark.parametrize("n,dn,mode", [(41, 20, 0), (75, 0, 2), (101, 13, 1)])
+def test_odd_grid_sizes_against_oracle(fb, orc, tmp_path, n, dn, mode):
+    """Odd sample sizes (81, 75, 127 = prime): the run-time-N sweeps against the numpy oracle (the live
+    reference covers odd sizes in test_random_grid_sizes_against_live_reference)."""
+    from fdes_b200 import specimens
+    m = n + 2 * dn
+    d = 0.25e-10
+    atoms = specimens.random_slab(60, m * d, 4 * 2e-10, seed=n, species=(79, 14))
+    cnf = specimens.write_cnf(tmp_path / f"odd{m}.cnf", image_size=n, border_size=dn, slices=4, pixel_size=d,
+                              slice_thickness=2e-10, atoms=atoms, voltage=200e3, mode=mode, absorptive=0.03,
+                              objective_aperture=0.015, frozen_phonons=2 if mode == 0 else 0,
+                              aberrations={"C1": (-1e-8, 0.0), "C3": (2e-4, 0.0)})
+    img, ew = _oracle_vs_library(cnf, fb, orc)
+    assert ew.shape[-1] == m
 
 
 def test_au_2048_against_oracle(fb, orc, tmp_path):

@@ -20,7 +20,7 @@ k_dbg(const __grid_constant__ CUtensorMap map, const cpx* __restrict__ Pq, int l
     constexpr int Q = N / 2 + 1;
     constexpr int E = C::E;
     ColPipe<N, DBG> pipe(pipe_smem, tw);
-    const int theta = pipe.theta;
+    const int theta = pipe.ky0();
     int t = blockIdx.x;
     if (t >= ntiles) return;
     long long c_full = 0, c_drain = 0, c_rel = 0;
@@ -33,16 +33,14 @@ k_dbg(const __grid_constant__ CUtensorMap map, const cpx* __restrict__ Pq, int l
         long long c0 = clock64();
         if (!(DBG & 1)) mbar_wait(pipe.full, pipe.nload & 1);
         c_full += clock64() - c0;
-        pipe.acquire(x, tn < ntiles, &map, band_col0((tn % tiles_x) * C::CW, lo_end, hi_start), tn / tiles_x);
-        fft_line_tw<N, E, -1>(x, pipe.sm(), theta, pipe.tw(), pipe.sync());
+        pipe.acquire_fft(x, tn < ntiles, &map, band_col0((tn % tiles_x) * C::CW, lo_end, hi_start), tn / tiles_x);
         c0 = clock64();
         pipe.publish_store_drained();
         c_drain += clock64() - c0;
         const cpx* P = Pq + (size_t)min(kx, N - kx) * Q;
         quarter_table_apply<N, E, 0>(x, P + theta, P - theta, [](cpx v, cpx p) { return cmul(v, p); });
-        fft_line_tw<N, E, 1>(x, pipe.sm(), theta, pipe.tw(), pipe.sync());
         c0 = clock64();
-        pipe.release(x, &map, kx0, t / tiles_x);
+        pipe.ifft_release(x, true, &map, kx0, t / tiles_x);      // inverse transform + hand-over
         c_rel += clock64() - c0;
     }
     pipe.finish();
@@ -128,7 +126,12 @@ void run(int batch, int reps)
     CK(cudaMemcpy(a.data(), d0, total * sizeof(cpx), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(b.data(), d1, total * sizeof(cpx), cudaMemcpyDeviceToHost));
     size_t diff = 0, changed = 0;
-    for (size_t i = 0; i < total; i++) { diff += memcmp(&a[i], &b[i], sizeof(cpx)) != 0; changed += memcmp(&a[i], &h[i], sizeof(cpx)) != 0; }
+    double num = 0, den = 0;
+    for (size_t i = 0; i < total; i++) {
+        diff += memcmp(&a[i], &b[i], sizeof(cpx)) != 0; changed += memcmp(&a[i], &h[i], sizeof(cpx)) != 0;
+        num += (double)(a[i].x - b[i].x) * (a[i].x - b[i].x) + (double)(a[i].y - b[i].y) * (a[i].y - b[i].y);
+        den += (double)a[i].x * a[i].x + (double)a[i].y * a[i].y;
+    }
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float ms0 = 0, ms1 = 0;
     for (int w = 0; w < 2; w++) {
@@ -143,9 +146,9 @@ void run(int batch, int reps)
     cudaFuncAttributes f0, f1;
     cudaFuncGetAttributes(&f0, k_propagate_cols<N>); cudaFuncGetAttributes(&f1, k_propagate_cols_tma<N>);
     const double gb = 16.0 * total / 1e9;
-    printf("N=%4d batch=%2d band=%4d | staged CW=%2d regs=%3d: %8.2f us %6.0f GB/s | tma CW=%2d regs=%3d grid=%d tiles=%d: %8.2f us %6.0f GB/s | differing=%zu changed=%zu of %zu\n",
+    printf("N=%4d batch=%2d band=%4d | staged CW=%2d regs=%3d: %8.2f us %6.0f GB/s | tma CW=%2d regs=%3d grid=%d tiles=%d: %8.2f us %6.0f GB/s | differing=%zu changed=%zu of %zu rel-L2 %.2e\n",
            N, batch, bc, C::CW, f0.numRegs, ms0 / reps * 1e3, gb / (ms0 / reps * 1e-3), Pc::CW, f1.numRegs, grid1, ntiles,
-           ms1 / reps * 1e3, gb / (ms1 / reps * 1e-3), diff, changed, total);
+           ms1 / reps * 1e3, gb / (ms1 / reps * 1e-3), diff, changed, total, sqrt(num / (den > 0 ? den : 1)));
     cudaFree(d0); cudaFree(d1); cudaFree(P); cudaFree(tw);
 }
 
