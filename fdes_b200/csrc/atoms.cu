@@ -263,12 +263,12 @@ void launch_radix_sort(const SortBuffers& sb, int n, int key_bits, int nconf, cu
 }
 
 // rowptr[k] = lower_bound(keys_sorted, k)
-__global__ void k_row_pointers(const uint32_t* __restrict__ keys, int n, int* __restrict__ rowptr, int nkeys)
+__global__ void k_row_pointers(const uint32_t* __restrict__ keys, int n, int* __restrict__ rowptr, int nkeys, size_t rp_stride)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > nkeys) return;
     keys += (size_t)blockIdx.y * n;
-    rowptr += (size_t)blockIdx.y * ((size_t)nkeys + 1);
+    rowptr += (size_t)blockIdx.y * rp_stride;
     int lo = 0, hi = n;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
@@ -276,9 +276,32 @@ __global__ void k_row_pointers(const uint32_t* __restrict__ keys, int n, int* __
     }
     rowptr[k] = lo;
 }
-void launch_row_pointers(const uint32_t* keys_sorted, int n, int* rowptr, int nkeys, int nconf, cudaStream_t st)
+void launch_row_pointers(const uint32_t* keys_sorted, int n, int* rowptr, int nkeys, int nconf, cudaStream_t st, size_t rp_stride)
 {
-    k_row_pointers<<<dim3((nkeys + 1 + 255) / 256, nconf), 256, 0, st>>>(keys_sorted, n, rowptr, nkeys);
+    if (rp_stride == 0) rp_stride = (size_t)nkeys + 1;
+    k_row_pointers<<<dim3((nkeys + 1 + 255) / 256, nconf), 256, 0, st>>>(keys_sorted, n, rowptr, nkeys, rp_stride);
+}
+
+// one thread per mask word (kernels.cuh: launch_row_masks)
+__global__ void k_row_masks(int* __restrict__ rowptr, size_t rp_stride, int nkeys, int N, int E)
+{
+    const int T = N / E, nwords = (nkeys / N) * T;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nwords) return;
+    const int* rp = rowptr + (size_t)blockIdx.y * rp_stride;
+    uint32_t* mask = reinterpret_cast<uint32_t*>(rowptr + (size_t)blockIdx.y * rp_stride + nkeys + 1);
+    const int kg = i / T, theta = i % T;
+    uint32_t w = 0;
+    for (int m = 0; m < E; m++) {
+        const int k = kg * N + theta + m * T;
+        w |= (rp[k + 1] > rp[k] ? 1u : 0u) << m;
+    }
+    mask[i] = w;
+}
+void launch_row_masks(int* rowptr, size_t rp_stride, int nkeys, int N, int E, int nconf, cudaStream_t st)
+{
+    const int nwords = (nkeys / N) * (N / E);
+    k_row_masks<<<dim3((nwords + 255) / 256, nconf), 256, 0, st>>>(rowptr, rp_stride, nkeys, N, E);
 }
 
 }  // namespace fdes

@@ -194,7 +194,11 @@ struct ColPipe {
     }
     // x[m] <- landed tile (rows with keep(row) == false read as zero); then (have_next) thread 0
     // starts the load of the next tile
-    struct KeepEvery { __device__ __forceinline__ bool operator()(int) const { return true; } };
+    // Keep: operator()(m): row theta + m*T is read (else zero); split(r): row lane + 32 r of a split line
+    struct KeepEvery {
+        __device__ __forceinline__ bool operator()(int) const { return true; }
+        __device__ __forceinline__ bool split(int) const { return true; }
+    };
     __device__ __forceinline__ void acquire(cpx (&x)[E], bool have_next, const CUtensorMap* map, int x0_next, int z_next)
     {
         acquire(x, have_next, map, x0_next, z_next, KeepEvery());
@@ -209,7 +213,7 @@ struct ColPipe {
 #pragma unroll
         for (int m = 0; m < E; m++) {
             const cpx v = *reinterpret_cast<const cpx*>(p + m * (T * C::ROWB));
-            x[m] = keep(theta + m * T) ? v : make_float2(0.f, 0.f);
+            x[m] = keep(m) ? v : make_float2(0.f, 0.f);
         }
         __syncthreads();                       // every thread has its points: L may be overwritten
         if (threadIdx.x == 0 && have_next) issue_load(map, x0_next, z_next);
@@ -294,11 +298,10 @@ struct ColPipe {
             if (w == 0) {
 #pragma unroll
                 for (int m = 0; m < E; m++) {
-                    const int j = lane + 32 * m;
                     cpx v0 = *reinterpret_cast<const cpx*>(p + m * (32 * C::ROWB));
                     cpx v1 = *reinterpret_cast<const cpx*>(p + m * (32 * C::ROWB) + (N / 2) * C::ROWB);
-                    if (!keep(j)) v0 = make_float2(0.f, 0.f);
-                    if (!keep(j + N / 2)) v1 = make_float2(0.f, 0.f);
+                    if (!keep.split(m)) v0 = make_float2(0.f, 0.f);
+                    if (!keep.split(m + E)) v1 = make_float2(0.f, 0.f);
                     x[m] = padd(v0, v1);
                 }
             } else {
@@ -319,11 +322,10 @@ struct ColPipe {
     __device__ __forceinline__ void split_first_odd(cpx (&x)[E], const unsigned char* p, int lane, TW twd, Keep keep) const
     {
         if constexpr (M < E) {
-            const int j = lane + 32 * M;
             cpx v0 = *reinterpret_cast<const cpx*>(p + M * (32 * C::ROWB));
             cpx v1 = *reinterpret_cast<const cpx*>(p + M * (32 * C::ROWB) + (N / 2) * C::ROWB);
-            if (!keep(j)) v0 = make_float2(0.f, 0.f);
-            if (!keep(j + N / 2)) v1 = make_float2(0.f, 0.f);
+            if (!keep.split(M)) v0 = make_float2(0.f, 0.f);
+            if (!keep.split(M + E)) v1 = make_float2(0.f, 0.f);
             x[M] = cmul(psub(v0, v1), twd.template at<SPLIT_TW + 32 * M>(lane));
             split_first_odd<M + 1>(x, p, lane, twd, keep);
         }

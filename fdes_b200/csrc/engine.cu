@@ -214,7 +214,9 @@ void Engine::init(const Atoms& atoms)
     while ((1LL << key_bits_) <= nk) key_bits_++;
     nrec_ = 4 * nAt_;
     rec_stride_ = (size_t)nrec_;
-    rp_stride_ = (size_t)nkeys_ + 1;
+    // row pointers of a configuration, followed by its row masks (launch_row_masks)
+    mask_E_ = line_points(N_);
+    rp_stride_ = (size_t)nkeys_ + 1 + (mask_E_ > 0 ? (size_t)(nkeys_ / N_) * (N_ / mask_E_) : 0);
 
     pt.mark("ctor: host prep");
     CK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
@@ -322,6 +324,7 @@ void Engine::setup_tables()
     while (kb + 1 <= N_ / 2 && !(((float)((kb + 1) * (kb + 1)) * 9.f / (mind * mind)) > 1.f)) kb++;
     g_.N = N_;
     g_.tw = tw_;
+    g_.mask_off = mask_E_ > 0 ? nkeys_ + 1 : 0;
     g_.lo_end = ((kb + 1 + 31) / 32) * 32;
     g_.hi_start = ((N_ - kb) / 32) * 32;
     if (g_.lo_end >= g_.hi_start) { g_.lo_end = N_; g_.hi_start = N_; }
@@ -432,9 +435,10 @@ void Engine::bin_and_sort(int b0, int nconf, const float* xyz_dev, int set, cuda
     launch_bin_atoms(xyz_dev, zidx_, occ_, nAt_, bg, keys, cols, w, nullptr, nconf, st);
     SortBuffers sb{keys, keys_tmp_, cols, cols_tmp_, w, w_tmp_, hist_};
     launch_radix_sort(sb, nrec_, key_bits_, nconf, st);
-    launch_row_pointers(keys, nrec_, r.rowptr + (size_t)b0 * rp_stride_, nkeys_, nconf, st);
+    launch_row_pointers(keys, nrec_, r.rowptr + (size_t)b0 * rp_stride_, nkeys_, nconf, st, rp_stride_);
+    if (mask_E_ > 0) launch_row_masks(r.rowptr + (size_t)b0 * rp_stride_, rp_stride_, nkeys_, N_, mask_E_, nconf, st);
     int passes = (key_bits_ + 7) / 8; if (passes & 1) passes++; if (!passes) passes = 2;
-    tm_.kernel_launches += 2 + 3 * passes;
+    tm_.kernel_launches += 2 + 3 * passes + (mask_E_ > 0 ? 1 : 0);
 }
 
 // jitter + bin + sort + row pointers for the configurations of one batch (slots 0 .. nb-1)

@@ -561,8 +561,11 @@ struct ColTile {
         else __syncthreads();
     }
     // x[m] <- tile(theta + m*T, line); tile = &array[0][first column of the tile].
-    // keep(row) == false reads as zero without touching memory.  `again`: the tile buffer was
-    // used by a previous load/transform of this CTA.
+    // keep(i) == false: row mask_pos() + i*T reads as zero without touching memory (a row-mask word
+    // of position mask_pos(), kernels.cuh).  `again`: the tile buffer was used by a previous
+    // load/transform of this CTA.
+    // position (within a line) of the rows this thread moves in load(): rows mask_pos() + i*T
+    __device__ __forceinline__ int mask_pos() const { return C::STAGED ? lr : theta; }
     template <class Keep>
     __device__ __forceinline__ void load(cpx (&x)[E], const cpx* __restrict__ tile, Keep keep, bool again = false) const
     {
@@ -572,7 +575,7 @@ struct ColTile {
 #pragma unroll
             for (int i = 0; i < E; i++) {
                 const int row = lr + i * C::RPI;
-                v[i] = keep(row) ? tile[(size_t)row * N + lc] : make_float2(0.f, 0.f);
+                v[i] = keep(i) ? tile[(size_t)row * N + lc] : make_float2(0.f, 0.f);
             }
 #pragma unroll
             for (int i = 0; i < E; i++) smem[lc * C::LSTRIDE + smpad<E>(lr + i * C::RPI)] = v[i];
@@ -584,7 +587,7 @@ struct ColTile {
 #pragma unroll
             for (int m = 0; m < E; m++) {
                 const int row = theta + m * T;
-                x[m] = keep(row) ? tile[(size_t)row * N + line] : make_float2(0.f, 0.f);
+                x[m] = keep(m) ? tile[(size_t)row * N + line] : make_float2(0.f, 0.f);
             }
         }
     }

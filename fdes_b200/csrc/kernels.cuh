@@ -16,6 +16,9 @@ struct SweepGeom {
     int lo_end;         // columns kx in [0, lo_end) or [hi_start, N) can be non-zero after the
     int hi_start;       //   2/3 band limit (bounds rounded outwards to multiples of 32)
     const cpx* tw;      // pass twiddle tables of make_twiddles(N) (layout: fft_core.cuh)
+    // Row masks of the deposit records (launch_row_masks): the masks of a configuration start mask_off
+    // 32-bit words after its row pointers (0: none, the generic sweeps read the row pointers instead)
+    int mask_off = 0;
 };
 // host copy of the twiddle tables a SweepGeom of size N must point to (on the device)
 std::vector<cpx> make_twiddles(int N);
@@ -24,6 +27,7 @@ bool fft_size_supported(int N);
 bool fft_size_is_fast(int N);   // register-resident kernels (else the generic run-time-N sweeps)
 int rows_per_block(int N);
 int cols_per_block(int N);
+int line_points(int N);         // points per thread E of a line transform (0: generic sweeps, no row masks)
 
 // ---- per-slice sweeps (S1..S6) -------------------------------------------
 // The potential sweeps S1..S3 work on slice PAIRS: the densities of slice and slice2 travel as the
@@ -188,7 +192,12 @@ int sort_num_blocks(int n);
 void launch_radix_sort(const SortBuffers& sb, int n, int key_bits, int nconf, cudaStream_t st);
 // rowptr[k] = first sorted record with key >= k, k in [0, nkeys]; records with key >= nkeys
 // (rejected atoms) stay beyond rowptr[nkeys]
+// Row masks: for every configuration and every key group kg = slice * nZ + z (N consecutive keys) T = N / E
+// words; bit m of word theta <-> row theta + m * T has deposit records.  These are the rows S1 writes and
+// the only rows S2 may read; a thread of a column sweep holds exactly the rows of one word.
+// rowptr: [nconf][rp_stride] ints, the masks of a configuration follow its nkeys + 1 row pointers.
+void launch_row_masks(int* rowptr, size_t rp_stride, int nkeys, int N, int E, int nconf, cudaStream_t st);
 void launch_row_pointers(const uint32_t* keys_sorted, int n, int* rowptr, int nkeys, int nconf,
-                         cudaStream_t st);
+                         cudaStream_t st, size_t rp_stride = 0);   // rp_stride 0: nkeys + 1
 
 }  // namespace fdes

@@ -173,6 +173,19 @@ __device__ __forceinline__ void quarter_table_apply(cpx (&x)[E], const TabT* lo,
     }
 }
 struct KeepAll { __device__ __forceinline__ bool operator()(int) const { return true; } };
+// Rows with deposit records, from the row-mask words of the thread's position (launch_row_masks): w0 = word of
+// position theta (bit m <-> row theta + m*T); for the split lines of col_pipe.cuh w0 / w1 = words of positions
+// lane / lane + 32, so that row lane + 32 r is bit r/2 of word r%2.
+struct KeepMask {
+    uint32_t w0, w1;
+    __device__ __forceinline__ bool operator()(int m) const { return (w0 >> m) & 1u; }
+    __device__ __forceinline__ bool split(int r) const { return (((r & 1) ? w1 : w0) >> (r >> 1)) & 1u; }
+};
+// mask words of configuration b, key group kg = slice * nZ + z (T words each)
+__device__ __forceinline__ const uint32_t* row_mask_words(const int* rowptr, size_t rp_stride, int mask_off, int b, int kg, int T)
+{
+    return reinterpret_cast<const uint32_t*>(rowptr + (size_t)b * rp_stride + mask_off) + (size_t)kg * T;
+}
 
 __device__ __forceinline__ bool in_band(int kx, int lo_end, int hi_start)
 {
@@ -298,7 +311,7 @@ void launch_density_rows_n(const SweepGeom& g, cpx* A, const int* rowptr, const 
 template <int N>
 __global__ void __launch_bounds__(ColCfg<N>::THREADS, ColCfg<N>::MIN_CTAS)
 k_potential_cols(cpx* __restrict__ B, const cpx* __restrict__ A, const float* __restrict__ Gq,
-                 const int* __restrict__ rowptr, int slice, int slice2, int nZ, size_t rp_stride,
+                 const int* __restrict__ rowptr, int slice, int slice2, int nZ, size_t rp_stride, int mask_off,
                  int cfg_stride, int cfg_off2, const cpx* __restrict__ tw)
 {
     pdl_prologue();
@@ -322,9 +335,10 @@ k_potential_cols(cpx* __restrict__ B, const cpx* __restrict__ A, const float* __
         if (rp[N] == rp[0] && rp2[N] == rp2[0]) continue;  // species absent from both slices (CTA-uniform)
         const cpx* Az = A + (size_t)(b * nZ + z) * N * N + kx0;
         cpx x[E];
-        // rows without deposits were not written by S1: read them as zero (branch-free test so the
-        // tile loads stay batched)
-        ctx.load(x, Az, [rp, rp2](int y) { return (rp[y + 1] > rp[y]) | (rp2[y + 1] > rp2[y]); }, any);
+        // rows without deposits were not written by S1: read them as zero
+        uint32_t kw = row_mask_words(rowptr, rp_stride, mask_off, bA, slice * nZ + z, C::T)[ctx.mask_pos()];
+        if (slice2 >= 0) kw |= row_mask_words(rowptr, rp_stride, mask_off, bB, slice2 * nZ + z, C::T)[ctx.mask_pos()];
+        ctx.load(x, Az, KeepMask{kw, 0u}, any);
         any = true;
         fft_line<N, E, -1>(x, ctx.sm, theta, tw, ctx);
         const float* G = Gq + (size_t)z * Q * Q + (size_t)ax * Q;
@@ -344,17 +358,19 @@ template <int N>
 __global__ void __launch_bounds__(PipeCfg<N>::THREADS, 1)
 k_potential_cols_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                      const float* __restrict__ Gq, const int* __restrict__ rowptr, int slice, int slice2, int nZ,
-                     size_t rp_stride, int cfg_stride, int cfg_off2, int tiles_x, int ntiles, const cpx* __restrict__ tw)
+                     size_t rp_stride, int mask_off, int cfg_stride, int cfg_off2, int tiles_x, int ntiles,
+                     const cpx* __restrict__ tw)
 {
     pdl_prologue();
     using C = PipeCfg<N>;
     extern __shared__ __align__(1024) unsigned char pipe_smem[];
     constexpr int Q = N / 2 + 1;
     constexpr int E = C::E;
-    // no split lines here: each warp of a split column would evaluate the row predicates of BOTH halves
-    // (measured at 2048^2: 142 us against 135 us)
-    ColPipe<N, 0, false> pipe(pipe_smem, tw);
+    ColPipe<N> pipe(pipe_smem, tw);
+    using Pipe = ColPipe<N>;
     const int ky0 = pipe.ky0();                 // x[m] <-> ky = ky0 + m*T
+    // positions of this thread's row-mask words
+    const int mp0 = Pipe::SPLIT ? (pipe.theta & 31) : pipe.theta, mp1 = Pipe::SPLIT ? mp0 + 32 : mp0;
     auto rows_of = [=](int b, int z, int sl) { return rowptr + (size_t)b * rp_stride + (size_t)(sl * nZ + z) * N; };
     auto present = [=](int b, int z) {
         const int* rp = rows_of(b * cfg_stride, z, slice);
@@ -386,14 +402,17 @@ k_potential_cols_tma(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         bool any = false;
         while (lt == t) {                      // the landed (or landing) tile belongs to this output tile
             const int z = lz;
-            const int* rp = rows_of(b * cfg_stride, z, slice);
-            const int* rp2 = slice2 >= 0 ? rows_of(b * cfg_stride + cfg_off2, z, slice2) : rp;
+            // rows without deposits were not written by S1: read them as zero
+            const uint32_t* mA = row_mask_words(rowptr, rp_stride, mask_off, b * cfg_stride, slice * nZ + z, C::T);
+            KeepMask keep{mA[mp0], mA[mp1]};
+            if (slice2 >= 0) {
+                const uint32_t* mB = row_mask_words(rowptr, rp_stride, mask_off, b * cfg_stride + cfg_off2, slice2 * nZ + z, C::T);
+                keep.w0 |= mB[mp0]; keep.w1 |= mB[mp1];
+            }
             lz++;
             seek(lt, lz);
             cpx x[E];
-            // rows without deposits were not written by S1: read them as zero
-            pipe.acquire_fft(x, lt < ntiles, &mapA, (lt % tiles_x) * C::CW, (lt / tiles_x) * nZ + lz,
-                             [rp, rp2](int y) { return (rp[y + 1] > rp[y]) | (rp2[y + 1] > rp2[y]); });
+            pipe.acquire_fft(x, lt < ntiles, &mapA, (lt % tiles_x) * C::CW, (lt / tiles_x) * nZ + lz, keep);
             any = true;
             const float* G = Gq + (size_t)z * Q * Q + (size_t)ax * Q;
             quarter_table_apply<N, E, 0>(x, G + ky0, G - ky0,
@@ -412,6 +431,7 @@ void launch_potential_cols_n(const SweepGeom& g, cpx* B, const cpx* A, const flo
                            const int* rowptr, int slice, int slice2, int nZ, int batch, size_t rowptr_stride,
                            int cfg_stride, int cfg_off2, cudaStream_t st)
 {
+    if (g.mask_off <= 0) throw std::runtime_error("S2 needs the row masks of the deposit records (SweepGeom::mask_off)");
     if constexpr (pipe_supported<NN>()) {
         if (pipe_enabled()) {
             using P = PipeCfg<NN>;
@@ -421,7 +441,7 @@ void launch_potential_cols_n(const SweepGeom& g, cpx* B, const cpx* A, const flo
             tile_map(&mapA, A, NN, batch * nZ, P::CW, P::BR);
             tile_map(&mapB, B, NN, batch, P::CW, P::BR);
             launch_pdl(k_potential_cols_tma<NN>, dim3(pipe_grid(ntiles)), dim3(P::THREADS), P::SMEM, st, mapA, mapB, Gq, rowptr, slice, slice2,
-                                                                                  nZ, rowptr_stride, cfg_stride, cfg_off2, tiles_x, ntiles, g.tw);
+                                                                                  nZ, rowptr_stride, g.mask_off, cfg_stride, cfg_off2, tiles_x, ntiles, g.tw);
             FDES_LAUNCH_CHECK();
             return;
         }
@@ -430,7 +450,7 @@ void launch_potential_cols_n(const SweepGeom& g, cpx* B, const cpx* A, const flo
     FDES_ALLOW_SMEM((k_potential_cols<NN>), C::SMEM);
     dim3 grid(NN / C::CW, batch);
     launch_pdl(k_potential_cols<NN>, dim3(grid), dim3(C::THREADS), C::SMEM, st, B, A, Gq, rowptr, slice, slice2, nZ,
-                                                           rowptr_stride, cfg_stride, cfg_off2, g.tw);
+                                                           rowptr_stride, g.mask_off, cfg_stride, cfg_off2, g.tw);
     FDES_LAUNCH_CHECK();
 }
 
@@ -1529,7 +1549,7 @@ template <int N>
 const SweepVTable* make_sweep_vtable()
 {
     static const SweepVTable vt = {
-        N, RowCfg<N>::RPB, ColCfg<N>::CW,
+        N, RowCfg<N>::RPB, ColCfg<N>::CW, LineCfg<N>::E,
         &launch_density_rows_n<N>, &launch_potential_cols_n<N>, &launch_transmit_rows_n<N>,
         &launch_bandlimit_cols_n<N>, &launch_multiply_rows_n<N>, &launch_propagate_cols_n<N>,
         &launch_rows_fft_n<N>, &launch_rows_fft_sum_n<N>, &launch_cols_fft_n<N>,

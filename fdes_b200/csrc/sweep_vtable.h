@@ -18,7 +18,7 @@ namespace fdes {
 void tile_map(CUtensorMap_st* out, const void* base, int N, int nimg, int CW, int BR);
 
 struct SweepVTable {
-    int N, rows_per_block, cols_per_block;
+    int N, rows_per_block, cols_per_block, line_points;
     void (*density_rows)(const SweepGeom&, cpx*, const int*, const int*, const float*, int, int, int, int, size_t, size_t, int, int, cudaStream_t);
     void (*potential_cols)(const SweepGeom&, cpx*, const cpx*, const float*, const int*, int, int, int, int, size_t, int, int, cudaStream_t);
     void (*transmit_rows)(const SweepGeom&, const cpx*, cpx*, int, float, int, cudaStream_t);

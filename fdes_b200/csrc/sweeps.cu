@@ -34,6 +34,7 @@ bool fft_size_is_fast(int N) { return find_fast_vtable(N) != nullptr; }
 std::vector<cpx> make_twiddles(int N) { return vt(N).make_twiddles(N); }
 int rows_per_block(int N) { return vt(N).rows_per_block; }
 int cols_per_block(int N) { return vt(N).cols_per_block; }
+int line_points(int N) { return vt(N).line_points; }
 
 void launch_density_rows(const SweepGeom& g, cpx* A, const int* rowptr, const int* rec_col, const float* rec_w,
                          int slice, int slice2, int nZ, int batch, size_t rec_stride, size_t rowptr_stride, cudaStream_t st,
