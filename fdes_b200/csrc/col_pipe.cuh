@@ -63,15 +63,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     while (!mbar_try_wait(bar, parity)) {}
 }
 // box at coordinates (x = column, y = row, z = image) of a rank-3 tensor map -> shared memory
+// FDES_TMA_STREAM=1: the tiles carry an evict_first L2 policy (they stream through once per sweep; the tables
+// should stay)
+#ifndef FDES_TMA_STREAM
+#define FDES_TMA_STREAM 0
+#endif
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z)
 {
+#if FDES_TMA_STREAM
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)), "l"(l2_stream_policy()) : "memory");
+#else
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int x, int y, int z)
 {
+#if FDES_TMA_STREAM
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(x), "r"(y), "r"(z), "l"(l2_stream_policy()) : "memory");
+#else
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                  ::"l"(map), "r"(smem_u32(src)), "r"(x), "r"(y), "r"(z) : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all but the N most recent bulk groups have finished READING their shared-memory source
@@ -305,7 +320,7 @@ struct ColPipe {
                     x[m] = padd(v0, v1);
                 }
             } else {
-                split_first_odd<0>(x, p, lane, twd, keep);
+                split_first_odd<0>(x, p, lane, twd, keep, twd.template at<SPLIT_TW>(lane));
             }
             __syncthreads();                       // every thread has its points: L may be overwritten
             if (threadIdx.x == 0 && have_next) issue_load(map, x0_next, z_next);
@@ -319,23 +334,31 @@ struct ColPipe {
     }
     // x[M] = (f[j] - f[j + N/2]) W^j, j = lane + 32 M (compile-time table offsets)
     template <int M, class TW, class Keep>
-    __device__ __forceinline__ void split_first_odd(cpx (&x)[E], const unsigned char* p, int lane, TW twd, Keep keep) const
+    __device__ __forceinline__ void split_first_odd(cpx (&x)[E], const unsigned char* p, int lane, TW twd, Keep keep, cpx wlane) const
     {
         if constexpr (M < E) {
             cpx v0 = *reinterpret_cast<const cpx*>(p + M * (32 * C::ROWB));
             cpx v1 = *reinterpret_cast<const cpx*>(p + M * (32 * C::ROWB) + (N / 2) * C::ROWB);
             if (!keep.split(M)) v0 = make_float2(0.f, 0.f);
             if (!keep.split(M + E)) v1 = make_float2(0.f, 0.f);
+#if FDES_SPLIT_TW_CONST_COLS
+            x[M] = split_twiddle<N, E, -1, M>(psub(v0, v1), wlane);
+#else
             x[M] = cmul(psub(v0, v1), twd.template at<SPLIT_TW + 32 * M>(lane));
-            split_first_odd<M + 1>(x, p, lane, twd, keep);
+#endif
+            split_first_odd<M + 1>(x, p, lane, twd, keep, wlane);
         }
     }
     template <int M, class TW>
-    __device__ __forceinline__ void split_last_odd(cpx (&x)[E], int lane, TW twd) const
+    __device__ __forceinline__ void split_last_odd(cpx (&x)[E], int lane, TW twd, cpx wlane) const
     {
         if constexpr (M < E) {
+#if FDES_SPLIT_TW_CONST_COLS
+            x[M] = split_twiddle<N, E, 1, M>(x[M], wlane);
+#else
             x[M] = cmul_conj(x[M], twd.template at<SPLIT_TW + 32 * M>(lane));
-            split_last_odd<M + 1>(x, lane, twd);
+#endif
+            split_last_odd<M + 1>(x, lane, twd, wlane);
         }
     }
     // inverse transform (skipped for an all-zero spectrum: do_fft = false), optional scale, and hand-over
@@ -367,7 +390,7 @@ struct ColPipe {
 #pragma unroll
                 for (int m = 0; m < E / 2; m++) mine[m * 32 + lane] = x[m + E / 2];
             } else {
-                split_last_odd<0>(x, lane, twd);
+                split_last_odd<0>(x, lane, twd, twd.template at<SPLIT_TW>(lane));
 #pragma unroll
                 for (int m = 0; m < E / 2; m++) mine[m * 32 + lane] = x[m];
             }

@@ -81,11 +81,57 @@ __device__ __forceinline__ cpx ld_nc_at(const cpx* p)
     asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "l"(p), "n"(OFF * 8));
     return v;
 }
+// The quarter tables (propagator, scattering factors) are re-read by every tile of every image while the
+// wave functions stream through L2 once per sweep: an evict_last policy keeps the tables resident.
+#ifndef FDES_TABLE_KEEP
+#define FDES_TABLE_KEEP 1
+#endif
+__device__ __forceinline__ uint64_t l2_keep_policy()
+{
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_stream_policy()
+{
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// KEEP: only for tables that are small next to the 126 MB of L2 (the launchers pass N <= 2048: 8 MB; the
+// 34 MB propagator table of a 4096^2 grid, kept resident, costs the other sweeps more than it gains S6)
+template <int OFF, bool KEEP = true>
+__device__ __forceinline__ cpx ld_tab_at(const cpx* p)
+{
+#if FDES_TABLE_KEEP
+    if constexpr (!KEEP) return ld_nc_at<OFF>(p);
+    cpx v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0,%1}, [%2+%3], %4;" : "=f"(v.x), "=f"(v.y) : "l"(p), "n"(OFF * 8), "l"(l2_keep_policy()));
+    return v;
+#else
+    return ld_nc_at<OFF>(p);
+#endif
+}
+// (the real scattering-factor tables of S2 are nZ x (N/2+1)^2 floats -- 50 MB for three species at 4096^2: kept
+// resident they crowd the tiles out of L2, S2 1643 -> 1943 us; they take the default policy)
+template <int OFF, bool KEEP = false>
+__device__ __forceinline__ float ld_tab_at(const float* p)
+{
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1+%2];" : "=f"(v) : "l"(p), "n"(OFF * 4));
+    return v;
+}
 template <int OFF>
 __device__ __forceinline__ float ld_nc_at(const float* p)
 {
     float v;
     asm volatile("ld.global.nc.f32 %0, [%1+%2];" : "=f"(v) : "l"(p), "n"(OFF * 4));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_nc_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
 __device__ __forceinline__ float ld_nc(const float* p)
@@ -464,14 +510,33 @@ __device__ __forceinline__ void fft_line(cpx (&x)[E], cpx* sm, int theta, const 
 template <int N, int E>
 __host__ __device__ constexpr int split_tw_offset() { return twiddle_offset<N, E, N / 2>() + N / 2; }
 
+// FDES_SPLIT_TW_CONST=1: W^j, j = lane + 32 m, as (compile-time W^{32 m}) x (per-thread W^lane) -- two
+// register multiplications instead of a table load and one multiplication
+#ifndef FDES_SPLIT_TW_CONST
+#define FDES_SPLIT_TW_CONST 1      // rows: S5 at 2048^2 232 -> 211 us (the table loads go through the same L1 as the row loads)
+#endif
+#ifndef FDES_SPLIT_TW_CONST_COLS
+#define FDES_SPLIT_TW_CONST_COLS 0 // pipelined columns (table in shared memory): no gain measured
+#endif
+template <int N, int E, int DIR, int M>
+__device__ __forceinline__ cpx split_twiddle(cpx v, cpx wlane)
+{
+    static_assert(N == 2048, "W^{32 m} = exp(2 pi i m / 64)");
+    const cpx u = mul_w64<DIR, M>(v);
+    return DIR < 0 ? cmul(u, wlane) : cmul_conj(u, wlane);
+}
 template <int N, int E, int DIR, int M, class TW, class Load>
-__device__ __forceinline__ void split_dif_odd(cpx (&x)[E], int lane, TW tw, Load load)
+__device__ __forceinline__ void split_dif_odd(cpx (&x)[E], int lane, TW tw, Load load, cpx wlane)
 {
     if constexpr (M < E) {
         const cpx d = psub(load(lane, M), load(lane, M + E));
+#if FDES_SPLIT_TW_CONST
+        x[M] = split_twiddle<N, E, DIR, M>(d, wlane);
+#else
         const cpx wv = tw.template at<split_tw_offset<N, E>() + 32 * M>(lane);
         x[M] = DIR < 0 ? cmul(d, wv) : cmul_conj(d, wv);
-        split_dif_odd<N, E, DIR, M + 1>(x, lane, tw, load);
+#endif
+        split_dif_odd<N, E, DIR, M + 1>(x, lane, tw, load, wlane);
     }
 }
 // load(lane, blk) = f[lane + 32 blk], blk = 0 .. 2E-1 (blk is a compile-time constant after unrolling)
@@ -483,16 +548,21 @@ __device__ __forceinline__ void split_dif(cpx (&x)[E], int w, int lane, TW tw, L
 #pragma unroll
         for (int m = 0; m < E; m++) x[m] = padd(load(lane, m), load(lane, m + E));
     } else {
-        split_dif_odd<N, E, DIR, 0>(x, lane, tw, load);
+        const cpx wlane = tw.template at<split_tw_offset<N, E>()>(lane);
+        split_dif_odd<N, E, DIR, 0>(x, lane, tw, load, wlane);
     }
 }
 template <int N, int E, int DIR, int M, class TW>
-__device__ __forceinline__ void split_twiddle_all(cpx (&x)[E], int lane, TW tw)
+__device__ __forceinline__ void split_twiddle_all(cpx (&x)[E], int lane, TW tw, cpx wlane)
 {
     if constexpr (M < E) {
+#if FDES_SPLIT_TW_CONST
+        x[M] = split_twiddle<N, E, DIR, M>(x[M], wlane);
+#else
         const cpx wv = tw.template at<split_tw_offset<N, E>() + 32 * M>(lane);
         x[M] = DIR < 0 ? cmul(x[M], wv) : cmul_conj(x[M], wv);
-        split_twiddle_all<N, E, DIR, M + 1>(x, lane, tw);
+#endif
+        split_twiddle_all<N, E, DIR, M + 1>(x, lane, tw, wlane);
     }
 }
 // mine / other: 16 x 32 exchange slots of this warp / of the partner warp; pair_sync: barrier of the two
@@ -507,7 +577,7 @@ __device__ __forceinline__ void split_dit_combine(cpx (&x)[E], int w, int lane, 
 #pragma unroll
         for (int m = 0; m < E / 2; m++) mine[m * 32 + lane] = x[m + E / 2];
     } else {
-        split_twiddle_all<N, E, DIR, 0>(x, lane, tw);
+        split_twiddle_all<N, E, DIR, 0>(x, lane, tw, tw.template at<split_tw_offset<N, E>()>(lane));
 #pragma unroll
         for (int m = 0; m < E / 2; m++) mine[m * 32 + lane] = x[m];
     }

@@ -167,9 +167,22 @@ __device__ __forceinline__ void quarter_table_apply(cpx (&x)[E], const TabT* lo,
 {
     constexpr int T = N / E;
     if constexpr (M < E) {
-        if constexpr (M < E / 2) x[M] = f(x[M], ld_nc_at<M * T>(lo));
-        else x[M] = f(x[M], ld_nc_at<N - M * T>(hi));
+        if constexpr (M < E / 2) x[M] = f(x[M], ld_tab_at<M * T, (N <= 2048)>(lo));
+        else x[M] = f(x[M], ld_tab_at<N - M * T, (N <= 2048)>(hi));
         quarter_table_apply<N, E, M + 1>(x, lo, hi, f);
+    }
+}
+#ifndef FDES_S6_PRELOAD
+#define FDES_S6_PRELOAD 0
+#endif
+// pre[m] = lo[m * T], m = M .. CNT-1 (the first half of a quarter-table column, see quarter_table_apply)
+template <int N, int E, int M, int CNT>
+__device__ __forceinline__ void table_preload(cpx (&pre)[CNT], const cpx* lo)
+{
+    static_assert(CNT <= E / 2, "only the first half of the points reads through lo");
+    if constexpr (M < CNT) {
+        pre[M] = ld_tab_at<M * (N / E), (N <= 2048)>(lo);
+        table_preload<N, E, M + 1, CNT>(pre, lo);
     }
 }
 struct KeepAll { __device__ __forceinline__ bool operator()(int) const { return true; } };
@@ -202,7 +215,27 @@ static int band_cols(const SweepGeom& g)
 }
 
 // The pipelined form (col_pipe.cuh): persistent CTAs, tiles fed by TMA.  Tile t covers the band
-// columns [CW * (t % tiles_x), +CW) of image t / tiles_x; consecutive CTAs work on adjacent tiles.
+// columns [CW * ord.xt(t), +CW) of image ord.img(t) (TileOrder below).
+// Order in which the persistent CTAs visit the tiles of a launch.  Tile number t -> (column tile, image):
+// groups of 8 adjacent column tiles (the tiles that share 128-byte lines at 16- and 32-byte tile rows), then
+// the images of the batch, then the next group.  The 148 CTAs then work on the SAME columns of all images at the
+// same time, so the quarter-table rows of those columns (propagator, scattering factors: 34 + 50 MB at 4096^2)
+// would be read from HBM once per launch instead of once per image.  FDES_TILE_ORDER=0: all tiles of an image first.
+// Measured: no gain at any size (4096^2 S2 -3 %, S6 +2 %), so the default stays 0.
+#ifndef FDES_TILE_ORDER
+#define FDES_TILE_ORDER 0
+#endif
+struct TileOrder {
+    int tiles_x, per, gx;
+    __device__ __forceinline__ TileOrder(int tiles_x_, int ntiles) : tiles_x(tiles_x_)
+    {
+        gx = (FDES_TILE_ORDER && tiles_x_ % 8 == 0) ? 8 : tiles_x_;
+        per = gx * (ntiles / tiles_x_);
+    }
+    __device__ __forceinline__ int xt(int t) const { return (t / per) * gx + t % gx; }     // column tile
+    __device__ __forceinline__ int img(int t) const { return (t % per) / gx; }            // image
+};
+
 template <int N>
 constexpr bool pipe_supported() { return N == 512 || N == 1024 || N == 2048 || N == 4096; }
 // (N = 2048 / 4096: tile rows of 32 / 16 bytes.  With generic LD/ST, 255 registers and four-instruction
@@ -367,6 +400,7 @@ k_potential_cols_tma(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     constexpr int Q = N / 2 + 1;
     constexpr int E = C::E;
     ColPipe<N> pipe(pipe_smem, tw);
+    const TileOrder ord(tiles_x, ntiles);
     using Pipe = ColPipe<N>;
     const int ky0 = pipe.ky0();                 // x[m] <-> ky = ky0 + m*T
     // positions of this thread's row-mask words
@@ -381,9 +415,36 @@ k_potential_cols_tma(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     auto seek = [=](int& t, int& z) {
         while (t < ntiles) {
             for (; z < nZ; z++)
-                if (present(t / tiles_x, z)) return;
+                if (present(ord.img(t), z)) return;
             t += gridDim.x; z = 0;
         }
+    };
+    // row masks of item (tile, z): rows without deposits were not written by S1 and read as zero.  The words
+    // of the NEXT item are requested before the transforms of the current one (volatile loads stay in place),
+    // so their latency is not in front of the tile.
+    auto load_keep = [=](int tile, int z) {
+        const int bb = (ord.img(tile)) * cfg_stride;
+#ifdef FDES_S2_ROWPTR_KEEP      // experiment: the masks rebuilt from the row pointers per item
+        {
+            const int* rp = rows_of(bb, z, slice);
+            const int* rp2 = slice2 >= 0 ? rows_of(bb + cfg_off2, z, slice2) : rp;
+            KeepMask k{0u, 0u};
+#pragma unroll
+            for (int m = 0; m < E; m++) {
+                const int y = mp0 + m * C::T;
+                k.w0 |= (uint32_t)((rp[y + 1] > rp[y]) | (rp2[y + 1] > rp2[y])) << m;
+            }
+            return k;
+        }
+#endif
+        const uint32_t* mA = row_mask_words(rowptr, rp_stride, mask_off, bb, slice * nZ + z, C::T);
+        KeepMask k{ld_nc_u32(mA + mp0), Pipe::SPLIT ? ld_nc_u32(mA + mp1) : 0u};
+        if (slice2 >= 0) {
+            const uint32_t* mB = row_mask_words(rowptr, rp_stride, mask_off, bb + cfg_off2, slice2 * nZ + z, C::T);
+            k.w0 |= ld_nc_u32(mB + mp0);
+            if (Pipe::SPLIT) k.w1 |= ld_nc_u32(mB + mp1);
+        }
+        return k;
     };
     int t = blockIdx.x;
     if (t >= ntiles) return;
@@ -391,10 +452,12 @@ k_potential_cols_tma(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     seek(lt, lz);
     if (threadIdx.x == 0) {
         prefetch_tensormap(&mapA); prefetch_tensormap(&mapB);
-        if (lt < ntiles) pipe.issue_load(&mapA, (lt % tiles_x) * C::CW, (lt / tiles_x) * nZ + lz);
+        if (lt < ntiles) pipe.issue_load(&mapA, ord.xt(lt) * C::CW, (ord.img(lt)) * nZ + lz);
     }
+    KeepMask keep_next{0u, 0u};
+    if (lt < ntiles) keep_next = load_keep(lt, lz);
     for (; t < ntiles; t += gridDim.x) {
-        const int kx0 = (t % tiles_x) * C::CW, kx = kx0 + pipe.line, b = t / tiles_x;
+        const int kx0 = ord.xt(t) * C::CW, kx = kx0 + pipe.line, b = ord.img(t);
         const int ax = min(kx, N - kx);
         cpx acc[E];
 #pragma unroll
@@ -402,17 +465,12 @@ k_potential_cols_tma(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         bool any = false;
         while (lt == t) {                      // the landed (or landing) tile belongs to this output tile
             const int z = lz;
-            // rows without deposits were not written by S1: read them as zero
-            const uint32_t* mA = row_mask_words(rowptr, rp_stride, mask_off, b * cfg_stride, slice * nZ + z, C::T);
-            KeepMask keep{mA[mp0], mA[mp1]};
-            if (slice2 >= 0) {
-                const uint32_t* mB = row_mask_words(rowptr, rp_stride, mask_off, b * cfg_stride + cfg_off2, slice2 * nZ + z, C::T);
-                keep.w0 |= mB[mp0]; keep.w1 |= mB[mp1];
-            }
+            const KeepMask keep = keep_next;
             lz++;
             seek(lt, lz);
+            if (lt < ntiles) keep_next = load_keep(lt, lz);
             cpx x[E];
-            pipe.acquire_fft(x, lt < ntiles, &mapA, (lt % tiles_x) * C::CW, (lt / tiles_x) * nZ + lz, keep);
+            pipe.acquire_fft(x, lt < ntiles, &mapA, ord.xt(lt) * C::CW, (ord.img(lt)) * nZ + lz, keep);
             any = true;
             const float* G = Gq + (size_t)z * Q * Q + (size_t)ax * Q;
             quarter_table_apply<N, E, 0>(x, G + ky0, G - ky0,
@@ -775,6 +833,7 @@ k_bandlimit_cols_tma(const __grid_constant__ CUtensorMap map, int npair, int lo_
     extern __shared__ __align__(1024) unsigned char pipe_smem[];
     constexpr int E = C::E;
     ColPipe<N> pipe(pipe_smem, tw);
+    const TileOrder ord(tiles_x, ntiles);
     const int ky0 = pipe.ky0();                 // x[m] <-> ky = ky0 + m*T
     // image y of the tile list -> entry (b, p) of a [batch][2] stack (npair = 0: plain [batch])
     auto entry = [npair](int y) { return npair == 0 ? y : (y / npair) * 2 + y % npair; };
@@ -782,15 +841,15 @@ k_bandlimit_cols_tma(const __grid_constant__ CUtensorMap map, int npair, int lo_
     if (t >= ntiles) return;
     if (threadIdx.x == 0) {
         prefetch_tensormap(&map);
-        pipe.issue_load(&map, band_col0((t % tiles_x) * C::CW, lo_end, hi_start), entry(t / tiles_x));
+        pipe.issue_load(&map, band_col0(ord.xt(t) * C::CW, lo_end, hi_start), entry(ord.img(t)));
     }
     const float mind = (float)N;
     const float alpha = 1.f / ((float)(N * N));
     for (; t < ntiles; t += gridDim.x) {
-        const int kx0 = band_col0((t % tiles_x) * C::CW, lo_end, hi_start), kx = kx0 + pipe.line;
+        const int kx0 = band_col0(ord.xt(t) * C::CW, lo_end, hi_start), kx = kx0 + pipe.line;
         const int tn = t + gridDim.x;
         cpx x[E];
-        pipe.acquire_fft(x, tn < ntiles, &map, band_col0((tn % tiles_x) * C::CW, lo_end, hi_start), entry(tn / tiles_x));
+        pipe.acquire_fft(x, tn < ntiles, &map, band_col0(ord.xt(tn) * C::CW, lo_end, hi_start), entry(ord.img(tn)));
         pipe.publish_store_drained();
         const int i1 = kx > N / 2 ? kx - N : kx;
 #pragma unroll
@@ -800,7 +859,7 @@ k_bandlimit_cols_tma(const __grid_constant__ CUtensorMap map, int npair, int lo_
             const bool cut = ((float)(i1 * i1 + i2 * i2) * 9.f / (mind * mind)) > 1.f;
             x[m] = cut ? make_float2(0.f, 0.f) : make_float2(x[m].x * alpha, x[m].y * alpha);
         }
-        pipe.ifft_release(x, true, &map, kx0, entry(t / tiles_x));
+        pipe.ifft_release(x, true, &map, kx0, entry(ord.img(t)));
     }
     pipe.finish();
 }
@@ -1039,22 +1098,35 @@ k_propagate_cols_tma(const __grid_constant__ CUtensorMap map, const cpx* __restr
     constexpr int Q = N / 2 + 1;
     constexpr int E = C::E;
     ColPipe<N> pipe(pipe_smem, tw);
+    const TileOrder ord(tiles_x, ntiles);
     const int ky0 = pipe.ky0();                 // x[m] <-> ky = ky0 + m*T
     int t = blockIdx.x;
     if (t >= ntiles) return;
     if (threadIdx.x == 0) {
         prefetch_tensormap(&map);
-        pipe.issue_load(&map, band_col0((t % tiles_x) * C::CW, lo_end, hi_start), t / tiles_x);
+        pipe.issue_load(&map, band_col0(ord.xt(t) * C::CW, lo_end, hi_start), ord.img(t));
     }
     for (; t < ntiles; t += gridDim.x) {
-        const int kx0 = band_col0((t % tiles_x) * C::CW, lo_end, hi_start), kx = kx0 + pipe.line;
+        const int kx0 = band_col0(ord.xt(t) * C::CW, lo_end, hi_start), kx = kx0 + pipe.line;
         const int tn = t + gridDim.x;
         cpx x[E];
-        pipe.acquire_fft(x, tn < ntiles, &map, band_col0((tn % tiles_x) * C::CW, lo_end, hi_start), tn / tiles_x);
-        pipe.publish_store_drained();
         const cpx* P = Pq + (size_t)min(kx, N - kx) * Q;
+#if FDES_S6_PRELOAD > 0
+        // the first table entries are requested before the forward transform, so that their L2 latency passes
+        // behind it instead of in front of the multiplications
+        cpx pre[FDES_S6_PRELOAD];
+        table_preload<N, E, 0, FDES_S6_PRELOAD>(pre, P + ky0);
+#endif
+        pipe.acquire_fft(x, tn < ntiles, &map, band_col0(ord.xt(tn) * C::CW, lo_end, hi_start), ord.img(tn));
+        pipe.publish_store_drained();
+#if FDES_S6_PRELOAD > 0
+#pragma unroll
+        for (int m = 0; m < FDES_S6_PRELOAD; m++) x[m] = cmul(x[m], pre[m]);
+        quarter_table_apply<N, E, FDES_S6_PRELOAD>(x, P + ky0, P - ky0, [](cpx v, cpx p) { return cmul(v, p); });
+#else
         quarter_table_apply<N, E, 0>(x, P + ky0, P - ky0, [](cpx v, cpx p) { return cmul(v, p); });
-        pipe.ifft_release(x, true, &map, kx0, t / tiles_x);
+#endif
+        pipe.ifft_release(x, true, &map, kx0, ord.img(t));
     }
     pipe.finish();
 }
@@ -1314,18 +1386,19 @@ k_ctf_cols_tma(const __grid_constant__ CUtensorMap map_in, const __grid_constant
     extern __shared__ __align__(1024) unsigned char pipe_smem[];
     constexpr int E = C::E;
     ColPipe<N> pipe(pipe_smem, tw);
+    const TileOrder ord(tiles_x, ntiles);
     const int ky0 = pipe.ky0();                 // x[m] <-> ky = ky0 + m*T
     int t = blockIdx.x;
     if (t >= ntiles) return;
     if (threadIdx.x == 0) {
         prefetch_tensormap(&map_in); prefetch_tensormap(&map_out);
-        pipe.issue_load(&map_in, band_col0((t % tiles_x) * C::CW, lo_end, hi_start), t / tiles_x);
+        pipe.issue_load(&map_in, band_col0(ord.xt(t) * C::CW, lo_end, hi_start), ord.img(t));
     }
     for (; t < ntiles; t += gridDim.x) {
-        const int kx0 = band_col0((t % tiles_x) * C::CW, lo_end, hi_start), kx = kx0 + pipe.line;
+        const int kx0 = band_col0(ord.xt(t) * C::CW, lo_end, hi_start), kx = kx0 + pipe.line;
         const int tn = t + gridDim.x;
         cpx x[E];
-        pipe.acquire_fft(x, tn < ntiles, &map_in, band_col0((tn % tiles_x) * C::CW, lo_end, hi_start), tn / tiles_x);
+        pipe.acquire_fft(x, tn < ntiles, &map_in, band_col0(ord.xt(tn) * C::CW, lo_end, hi_start), ord.img(tn));
         pipe.publish_store_drained();
         const cpx* tab = table + (size_t)kx * N + ky0;
 #pragma unroll
@@ -1333,7 +1406,7 @@ k_ctf_cols_tma(const __grid_constant__ CUtensorMap map_in, const __grid_constant
             const cpx w = ld_nc(tab + m * C::T);
             x[m] = make_float2(w.x * x[m].x - w.y * x[m].y, w.x * x[m].y + w.y * x[m].x);
         }
-        pipe.template ifft_release<true>(x, true, &map_out, kx0, t / tiles_x, scale);
+        pipe.template ifft_release<true>(x, true, &map_out, kx0, ord.img(t), scale);
     }
     pipe.finish();
 }
