@@ -57,6 +57,8 @@ UNIT = "Mpx*slices/s"
 
 WORKLOADS = {
     # name: (builder, description, species count)
+    "srtio3_800": ("config_srtio3_800", "SrTiO3 9x9x20 cells 8100 atoms / 3 species, 800^2 grid, 40 x 1.9525 A slices in 400 "
+                                        "sub-slices, 200 kV (BASELINE configs[0] geometry in .cnf form)"),
     "si001_1024": ("config_si001_1024", "Si[001] 11552 atoms, 1024^2 grid, 11 x 2 A slices, 100 kV (BASELINE configs[1])"),
     "au_2048": ("config_au_2048", "Au cuboctahedron 309 atoms, 2048^2 grid, 12 x 2.1 A slices, 50 kV (BASELINE configs[2])"),
     "slab_4096": ("config_random_4096_short", "random slab 4000 atoms / 3 species, 4096^2 grid, 20 x 2 A slices, 200 kV "
@@ -64,8 +66,8 @@ WORKLOADS = {
     "slab_4096_full": ("config_random_4096", "random slab 100000 atoms / 3 species, 4096^2 grid, 500 x 2 A slices, 200 kV "
                                             "(BASELINE configs[4] at its named size)"),
 }
-DEFAULT_CONFIGS_PER_STEP = {"si001_1024": 400, "au_2048": 80, "slab_4096": 20, "slab_4096_full": 2}
-REF_SAMPLE_CONFIGS = {"si001_1024": 16, "au_2048": 4, "slab_4096": 1, "slab_4096_full": 1}
+DEFAULT_CONFIGS_PER_STEP = {"srtio3_800": 20, "si001_1024": 400, "au_2048": 80, "slab_4096": 20, "slab_4096_full": 2}
+REF_SAMPLE_CONFIGS = {"srtio3_800": 1, "si001_1024": 16, "au_2048": 4, "slab_4096": 1, "slab_4096_full": 1}
 
 
 def peaks():

@@ -153,6 +153,18 @@ def config_random_4096_short(path, frozen_phonons: int = 2, with_atoms: bool = T
     return config_random_4096(path, n_atoms=4000, slices=20, frozen_phonons=frozen_phonons, with_atoms=with_atoms)
 
 
+def config_srtio3_800(path, frozen_phonons: int = 0, with_atoms: bool = True):
+    """Config 1 in .cnf form: SrTiO3 9 x 9 x 20 cells (8100 atoms, 3 species), 200 kV, 800^2 grid (400 + 2*200) at
+    0.087862 A, 40 slices of 1.9525 A run as 400 sub-slices of 0.19525 A, absorptive factor 0.1 -- the geometry
+    of config_srtio3_qsc_800 (the .qsc form, which the parity tests run against the reference)."""
+    atoms = srtio3_slab(9, 9, 20)
+    write_cnf(path, image_size=400, border_size=200, slices=40, pixel_size=0.087862e-10, slice_thickness=1.9525e-10,
+              sub_slice_thickness=0.19525e-10, atoms=atoms if with_atoms else None, voltage=200e3, absorptive=0.1,
+              objective_aperture=20e-3, frozen_phonons=frozen_phonons,
+              comment="SrTiO3 9x9x20 cells, 800^2, 400 sub-slices")
+    return atoms
+
+
 def config_srtio3_stem_512(path, frozen_phonons: int = 0, with_atoms: bool = True):
     """Config 4: SrTiO3 4 x 4 x 20 cells centred in a 5-cell-wide 512^2 box (d = 19.525 A / 512),
     40 x 1.9525 A slices, 200 kV, 20 mrad probe (mode 2), no aberrations."""

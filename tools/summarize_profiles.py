@@ -21,6 +21,13 @@ SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 
 
 def main(tag, sub="", batch=10):
     out, prof = ROOT / "gpurun_out" / sub, ROOT / "profiles"
+    launch_shares(tag, out, prof)
+    summarize_rep(out / "prof_sweeps.ncu-rep", prof, f"{tag}_ncu_full_raw.csv", f"{tag}_ncu_sweeps_summary.json", batch, True, tag)
+    if (out / "prof_sweeps_2048.ncu-rep").exists():      # the same capture on the Au 2048^2 workload
+        summarize_rep(out / "prof_sweeps_2048.ncu-rep", prof, None, f"{tag}_ncu_sweeps_2048_summary.json", batch, False, tag)
+
+
+def launch_shares(tag, out, prof):
     shutil.copy(out / "launches.csv", prof / f"{tag}_launches.csv")
     rows = list(csv.reader(l for l in open(prof / f"{tag}_launches.csv") if l.startswith('"')))
     hdr = rows[0]
@@ -36,10 +43,13 @@ def main(tag, sub="", batch=10):
                 "cold-cache serialised times: compare shares)\n\n")
         for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
             f.write(f"{k[:52]:52s} n={a[0]:4d} avg={a[1] / a[0]:8.2f}us share={100 * a[1] / tot:5.1f}%\n")
-    raw = prof / f"{tag}_ncu_full_raw.csv"
-    raw.write_text(subprocess.run(["ncu", "-i", str(out / "prof_sweeps.ncu-rep"), "--page", "raw", "--csv"],
-                                  capture_output=True, text=True, check=True).stdout)
-    rows = list(csv.reader(open(raw)))
+
+
+def summarize_rep(rep, prof, raw_name, summary_name, batch, write_traffic, tag):
+    text = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if raw_name:
+        (prof / raw_name).write_text(text)
+    rows = list(csv.reader(text.splitlines()))
     hdr, units = rows[0], rows[1]
     val = lambda r, n: float(r[hdr.index(n)].replace(",", "")) * SCALE.get(units[hdr.index(n)], 1)
     summary, traffic = [], {}
@@ -70,7 +80,10 @@ def main(tag, sub="", batch=10):
         summary[-1]["global_load_sectors_per_request"] = round(sec / req, 2) if req and sec else None
         summary[-1]["l2_hit_pct"] = opt(r, "lts__t_sector_hit_rate.pct")
         traffic.setdefault(key.split(" ")[0], int(rd + wr))
-    json.dump(summary, open(prof / f"{tag}_ncu_sweeps_summary.json", "w"), indent=1)
+    json.dump(summary, open(prof / summary_name, "w"), indent=1)
+    if not write_traffic:
+        print("wrote", summary_name)
+        return
     json.dump({"source": f"profiles/{tag}_ncu_full_raw.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch; "
                          "S1..S4 launches cover a slice pair)", "batch": batch, "per_launch_bytes": traffic},
               open(prof / "dram_traffic.json", "w"), indent=1)
