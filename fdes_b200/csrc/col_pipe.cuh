@@ -63,30 +63,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     while (!mbar_try_wait(bar, parity)) {}
 }
 // box at coordinates (x = column, y = row, z = image) of a rank-3 tensor map -> shared memory
-// FDES_TMA_STREAM=1: the tiles carry an evict_first L2 policy (they stream through once per sweep; the tables
-// should stay)
-#ifndef FDES_TMA_STREAM
-#define FDES_TMA_STREAM 0
-#endif
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z)
 {
-#if FDES_TMA_STREAM
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)), "l"(l2_stream_policy()) : "memory");
-#else
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
-#endif
 }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int x, int y, int z)
 {
-#if FDES_TMA_STREAM
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;"
-                 ::"l"(map), "r"(smem_u32(src)), "r"(x), "r"(y), "r"(z), "l"(l2_stream_policy()) : "memory");
-#else
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                  ::"l"(map), "r"(smem_u32(src)), "r"(x), "r"(y), "r"(z) : "memory");
-#endif
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all but the N most recent bulk groups have finished READING their shared-memory source

@@ -172,19 +172,6 @@ __device__ __forceinline__ void quarter_table_apply(cpx (&x)[E], const TabT* lo,
         quarter_table_apply<N, E, M + 1>(x, lo, hi, f);
     }
 }
-#ifndef FDES_S6_PRELOAD
-#define FDES_S6_PRELOAD 0
-#endif
-// pre[m] = lo[m * T], m = M .. CNT-1 (the first half of a quarter-table column, see quarter_table_apply)
-template <int N, int E, int M, int CNT>
-__device__ __forceinline__ void table_preload(cpx (&pre)[CNT], const cpx* lo)
-{
-    static_assert(CNT <= E / 2, "only the first half of the points reads through lo");
-    if constexpr (M < CNT) {
-        pre[M] = ld_tab_at<M * (N / E), (N <= 2048)>(lo);
-        table_preload<N, E, M + 1, CNT>(pre, lo);
-    }
-}
 struct KeepAll { __device__ __forceinline__ bool operator()(int) const { return true; } };
 // Rows with deposit records, from the row-mask words of the thread's position (launch_row_masks): w0 = word of
 // position theta (bit m <-> row theta + m*T); for the split lines of col_pipe.cuh w0 / w1 = words of positions
@@ -216,24 +203,14 @@ static int band_cols(const SweepGeom& g)
 
 // The pipelined form (col_pipe.cuh): persistent CTAs, tiles fed by TMA.  Tile t covers the band
 // columns [CW * ord.xt(t), +CW) of image ord.img(t) (TileOrder below).
-// Order in which the persistent CTAs visit the tiles of a launch.  Tile number t -> (column tile, image):
-// groups of 8 adjacent column tiles (the tiles that share 128-byte lines at 16- and 32-byte tile rows), then
-// the images of the batch, then the next group.  The 148 CTAs then work on the SAME columns of all images at the
-// same time, so the quarter-table rows of those columns (propagator, scattering factors: 34 + 50 MB at 4096^2)
-// would be read from HBM once per launch instead of once per image.  FDES_TILE_ORDER=0: all tiles of an image first.
-// Measured: no gain at any size (4096^2 S2 -3 %, S6 +2 %), so the default stays 0.
-#ifndef FDES_TILE_ORDER
-#define FDES_TILE_ORDER 0
-#endif
+// Tile number t of a launch -> (column tile, image): all tiles of an image first, consecutive CTAs on adjacent
+// tiles (they share 128-byte lines at 16- and 32-byte tile rows).  (Visiting the same columns of all images
+// together, so that a quarter-table row is fetched once per launch, was measured and gained nothing.)
 struct TileOrder {
-    int tiles_x, per, gx;
-    __device__ __forceinline__ TileOrder(int tiles_x_, int ntiles) : tiles_x(tiles_x_)
-    {
-        gx = (FDES_TILE_ORDER && tiles_x_ % 8 == 0) ? 8 : tiles_x_;
-        per = gx * (ntiles / tiles_x_);
-    }
-    __device__ __forceinline__ int xt(int t) const { return (t / per) * gx + t % gx; }     // column tile
-    __device__ __forceinline__ int img(int t) const { return (t % per) / gx; }            // image
+    int tiles_x;
+    __device__ __forceinline__ TileOrder(int tiles_x_, int) : tiles_x(tiles_x_) {}
+    __device__ __forceinline__ int xt(int t) const { return t % tiles_x; }      // column tile
+    __device__ __forceinline__ int img(int t) const { return t / tiles_x; }     // image
 };
 
 template <int N>
@@ -424,19 +401,6 @@ k_potential_cols_tma(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     // so their latency is not in front of the tile.
     auto load_keep = [=](int tile, int z) {
         const int bb = (ord.img(tile)) * cfg_stride;
-#ifdef FDES_S2_ROWPTR_KEEP      // experiment: the masks rebuilt from the row pointers per item
-        {
-            const int* rp = rows_of(bb, z, slice);
-            const int* rp2 = slice2 >= 0 ? rows_of(bb + cfg_off2, z, slice2) : rp;
-            KeepMask k{0u, 0u};
-#pragma unroll
-            for (int m = 0; m < E; m++) {
-                const int y = mp0 + m * C::T;
-                k.w0 |= (uint32_t)((rp[y + 1] > rp[y]) | (rp2[y + 1] > rp2[y])) << m;
-            }
-            return k;
-        }
-#endif
         const uint32_t* mA = row_mask_words(rowptr, rp_stride, mask_off, bb, slice * nZ + z, C::T);
         KeepMask k{ld_nc_u32(mA + mp0), Pipe::SPLIT ? ld_nc_u32(mA + mp1) : 0u};
         if (slice2 >= 0) {
@@ -1111,21 +1075,9 @@ k_propagate_cols_tma(const __grid_constant__ CUtensorMap map, const cpx* __restr
         const int tn = t + gridDim.x;
         cpx x[E];
         const cpx* P = Pq + (size_t)min(kx, N - kx) * Q;
-#if FDES_S6_PRELOAD > 0
-        // the first table entries are requested before the forward transform, so that their L2 latency passes
-        // behind it instead of in front of the multiplications
-        cpx pre[FDES_S6_PRELOAD];
-        table_preload<N, E, 0, FDES_S6_PRELOAD>(pre, P + ky0);
-#endif
         pipe.acquire_fft(x, tn < ntiles, &map, band_col0(ord.xt(tn) * C::CW, lo_end, hi_start), ord.img(tn));
         pipe.publish_store_drained();
-#if FDES_S6_PRELOAD > 0
-#pragma unroll
-        for (int m = 0; m < FDES_S6_PRELOAD; m++) x[m] = cmul(x[m], pre[m]);
-        quarter_table_apply<N, E, FDES_S6_PRELOAD>(x, P + ky0, P - ky0, [](cpx v, cpx p) { return cmul(v, p); });
-#else
         quarter_table_apply<N, E, 0>(x, P + ky0, P - ky0, [](cpx v, cpx p) { return cmul(v, p); });
-#endif
         pipe.ifft_release(x, true, &map, kx0, ord.img(t));
     }
     pipe.finish();
