@@ -325,6 +325,10 @@ void Engine::setup_tables()
     g_.N = N_;
     g_.tw = tw_;
     g_.mask_off = mask_E_ > 0 ? nkeys_ + 1 : 0;
+    {
+        const char* e = getenv("FDES_B200_NO_FIRST_SLICE_SHORTCUT");     // A/B switch
+        plane_first_slice_ = p_.mode != 2 && !p_.doBeamTilt && sweeps_pipelined(N_) && !(e && e[0] == '1');
+    }
     g_.lo_end = ((kb + 1 + 31) / 32) * 32;
     g_.hi_start = ((N_ - kb) / 32) * 32;
     if (g_.lo_end >= g_.hi_start) { g_.lo_end = N_; g_.hi_start = N_; }
@@ -501,7 +505,9 @@ void Engine::run_batches(int k, int jb, int je, bool reference_order)
         CK(cudaStreamWaitEvent(st_, ev_prep_[set], 0));
         act_ = set;
         if (p_.mode != 2 && !p_.doBeamTilt) {
-            launch_plane_wave_rowspace(Psi_, N_, nb, st_);     // psi_in_ is the plane wave: write it directly
+            // psi_in_ is the plane wave: write it directly -- unless the first slice does not read it at all
+            // (run_slices_plain: psi = 1, so S6 takes FFT_row(t) straight from D)
+            if (!plane_first_slice_) launch_plane_wave_rowspace(Psi_, N_, nb, st_);
         } else {
             for (int b = 0; b < nb; b++)
                 CK(cudaMemcpyAsync(Psi_ + (size_t)b * NN, psi_in_, NN * sizeof(cpx), cudaMemcpyDeviceToDevice, st_));
@@ -528,8 +534,10 @@ void Engine::run_slices_plain(int nb)
             launch_potential_cols(g_, W_, A_, Gq_, rs_[act_].rowptr, s, s, nZ_, nb / 2, rp_stride_, st_, 2, 1);
             launch_transmit_rows(g_, W_, D_, 2, p_.imPot, nb / 2, st_);
             launch_bandlimit_cols(g_, D_, nb, 0, st_);
-            launch_multiply_rows(g_, Psi_, D_, NN, nb, first_full && s == 0, st_);
-            launch_propagate_cols(g_, Psi_, Pq_, nb, st_);
+            if (!(plane_first_slice_ && s == 0 && launch_propagate_cols_from(g_, Psi_, D_, 1, nb, Pq_, nb, st_))) {
+                launch_multiply_rows(g_, Psi_, D_, NN, nb, first_full && s == 0, st_);
+                launch_propagate_cols(g_, Psi_, Pq_, nb, st_);
+            }
             break;
         }
         const int s2 = npair > 1 ? s + 1 : -1;
@@ -538,6 +546,8 @@ void Engine::run_slices_plain(int nb)
         launch_transmit_rows(g_, W_, D_, npair, p_.imPot, nb, st_);
         launch_bandlimit_cols(g_, D_, nb, npair, st_);
         for (int p = 0; p < npair; p++) {
+            // first slice of a plane wave: psi = 1, FFT_row(t psi) is what S4 left in D -- no S5
+            if (plane_first_slice_ && s + p == 0 && launch_propagate_cols_from(g_, Psi_, D_, 2, 2 * nb, Pq_, nb, st_)) continue;
             launch_multiply_rows(g_, Psi_, D_ + (size_t)p * NN, 2 * NN, nb, first_full && s + p == 0, st_);
             launch_propagate_cols(g_, Psi_, Pq_, nb, st_);
         }

@@ -137,6 +137,7 @@ private:
     unsigned int* hist_ = nullptr;
     double *norm_partial_ = nullptr, *norm_result_ = nullptr;
     size_t rec_stride_ = 0, rp_stride_ = 0;
+    bool plane_first_slice_ = false;  // plane-wave illumination on pipelined column kernels: slice 0 runs S6 from D, no S5
     int mask_E_ = 0;                  // points per thread of a line (row-mask layout); 0: no masks
     int nkeys_ = 0, key_bits_ = 0, nrec_ = 0;
     int lens_k_ = -1, incident_k_ = -1;

@@ -27,6 +27,7 @@ bool fft_size_supported(int N);
 bool fft_size_is_fast(int N);   // register-resident kernels (else the generic run-time-N sweeps)
 int rows_per_block(int N);
 int cols_per_block(int N);
+bool sweeps_pipelined(int N);   // column sweeps on the TMA pipeline (col_pipe.cuh): launch_propagate_cols_from works
 int line_points(int N);         // points per thread E of a line transform (0: generic sweeps, no row masks)
 
 // ---- per-slice sweeps (S1..S6) -------------------------------------------
@@ -56,6 +57,12 @@ void launch_multiply_rows(const SweepGeom& g, cpx* Psi, const cpx* E, size_t e_b
                           int batch, bool psi_full, cudaStream_t st);
 // S6: column FFT -> x Fresnel propagator (quarter table, mask and 1/N folded in) -> inverse
 void launch_propagate_cols(const SweepGeom& g, cpx* Psi, const cpx* Pq, int batch, cudaStream_t st);
+// S6 out of place: Psi[b] = IFFT_col(FFT_col(N * src[b * src_img_stride]) * P), band columns, src an image stack with
+// images of N*N elements.  The first slice of a plane wave needs no S5: psi = 1, so FFT_row(t * psi) is the
+// band-limited FFT_row(t) that S4 left in D.  Returns false when the size has no such kernel (generic sweeps,
+// register-staged column kernels): the caller then runs S5 + S6.
+bool launch_propagate_cols_from(const SweepGeom& g, cpx* Psi, const cpx* src, int src_img_stride, int src_images,
+                                const cpx* Pq, int batch, cudaStream_t st);
 
 // ---- STEM probe scan ----------------------------------------------------------------------
 constexpr int MAX_DETECTORS = 8;

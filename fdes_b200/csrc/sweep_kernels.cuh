@@ -1053,7 +1053,8 @@ k_propagate_cols(cpx* __restrict__ Psi, const cpx* __restrict__ Pq, int lo_end, 
 
 template <int N>
 __global__ void __launch_bounds__(PipeCfg<N>::THREADS, 1)
-k_propagate_cols_tma(const __grid_constant__ CUtensorMap map, const cpx* __restrict__ Pq, int lo_end, int hi_start,
+k_propagate_cols_tma(const __grid_constant__ CUtensorMap map, const __grid_constant__ CUtensorMap map_out,
+                     int src_img_stride, float in_scale, const cpx* __restrict__ Pq, int lo_end, int hi_start,
                      int tiles_x, int ntiles, const cpx* __restrict__ tw)
 {
     pdl_prologue();
@@ -1066,19 +1067,24 @@ k_propagate_cols_tma(const __grid_constant__ CUtensorMap map, const cpx* __restr
     const int ky0 = pipe.ky0();                 // x[m] <-> ky = ky0 + m*T
     int t = blockIdx.x;
     if (t >= ntiles) return;
+    // image b is read from image b * src_img_stride of the source stack (in place: the same stack, stride 1)
     if (threadIdx.x == 0) {
-        prefetch_tensormap(&map);
-        pipe.issue_load(&map, band_col0(ord.xt(t) * C::CW, lo_end, hi_start), ord.img(t));
+        prefetch_tensormap(&map); prefetch_tensormap(&map_out);
+        pipe.issue_load(&map, band_col0(ord.xt(t) * C::CW, lo_end, hi_start), ord.img(t) * src_img_stride);
     }
     for (; t < ntiles; t += gridDim.x) {
         const int kx0 = band_col0(ord.xt(t) * C::CW, lo_end, hi_start), kx = kx0 + pipe.line;
         const int tn = t + gridDim.x;
         cpx x[E];
         const cpx* P = Pq + (size_t)min(kx, N - kx) * Q;
-        pipe.acquire_fft(x, tn < ntiles, &map, band_col0(ord.xt(tn) * C::CW, lo_end, hi_start), ord.img(tn));
+        pipe.acquire_fft(x, tn < ntiles, &map, band_col0(ord.xt(tn) * C::CW, lo_end, hi_start), ord.img(tn) * src_img_stride);
         pipe.publish_store_drained();
+        if (in_scale != 1.f) {
+#pragma unroll
+            for (int m = 0; m < E; m++) x[m] = make_float2(x[m].x * in_scale, x[m].y * in_scale);
+        }
         quarter_table_apply<N, E, 0>(x, P + ky0, P - ky0, [](cpx v, cpx p) { return cmul(v, p); });
-        pipe.ifft_release(x, true, &map, kx0, ord.img(t));
+        pipe.ifft_release(x, true, &map_out, kx0, ord.img(t));
     }
     pipe.finish();
 }
@@ -1093,8 +1099,8 @@ void launch_propagate_cols_n(const SweepGeom& g, cpx* Psi, const cpx* Pq, int ba
             const int tiles_x = band_cols(g) / P::CW, ntiles = tiles_x * batch;
             CUtensorMap map;
             tile_map(&map, Psi, NN, batch, P::CW, P::BR);
-            launch_pdl(k_propagate_cols_tma<NN>, dim3(pipe_grid(ntiles)), dim3(P::THREADS), P::SMEM, st, map, Pq, g.lo_end, g.hi_start,
-                                                                                  tiles_x, ntiles, g.tw);
+            launch_pdl(k_propagate_cols_tma<NN>, dim3(pipe_grid(ntiles)), dim3(P::THREADS), P::SMEM, st, map, map, 1, 1.f, Pq, g.lo_end,
+                                                                                  g.hi_start, tiles_x, ntiles, g.tw);
             FDES_LAUNCH_CHECK();
             return;
         }
@@ -1104,6 +1110,29 @@ void launch_propagate_cols_n(const SweepGeom& g, cpx* Psi, const cpx* Pq, int ba
     dim3 grid(band_cols(g) / C::CW, batch);
     launch_pdl(k_propagate_cols<NN>, dim3(grid), dim3(C::THREADS), C::SMEM, st, Psi, Pq, g.lo_end, g.hi_start, g.tw);
     FDES_LAUNCH_CHECK();
+}
+
+// S6 reading the band columns of another image stack (launch_propagate_cols_from, kernels.cuh): pipelined kernels only
+template <int NN>
+bool launch_propagate_cols_from_n(const SweepGeom& g, cpx* Psi, const cpx* src, int src_img_stride, int src_images, const cpx* Pq,
+                                  int batch, cudaStream_t st)
+{
+    if constexpr (pipe_supported<NN>()) {
+        if (pipe_enabled()) {
+            using P = PipeCfg<NN>;
+            FDES_ALLOW_SMEM((k_propagate_cols_tma<NN>), P::SMEM);
+            const int tiles_x = band_cols(g) / P::CW, ntiles = tiles_x * batch;
+            CUtensorMap map_in, map_out;
+            tile_map(&map_in, src, NN, src_images, P::CW, P::BR);
+            tile_map(&map_out, Psi, NN, batch, P::CW, P::BR);
+            // S5 with psi = 1 returns FFT_row(IFFT_row(D)) = N * D (unnormalised transforms): the same factor here
+            launch_pdl(k_propagate_cols_tma<NN>, dim3(pipe_grid(ntiles)), dim3(P::THREADS), P::SMEM, st, map_in, map_out, src_img_stride,
+                       (float)NN, Pq, g.lo_end, g.hi_start, tiles_x, ntiles, g.tw);
+            FDES_LAUNCH_CHECK();
+            return true;
+        }
+    }
+    return false;
 }
 
 // =============================================================================================
@@ -1569,6 +1598,9 @@ std::vector<cpx> make_twiddles_n(int = 0)
     return tw;
 }
 
+template <int N>
+bool sweeps_pipelined_n() { return pipe_supported<N>() && pipe_enabled(); }
+
 // the launchers of one grid size, collected for the run-time dispatch in sweeps.cu
 template <int N>
 const SweepVTable* make_sweep_vtable()
@@ -1579,7 +1611,7 @@ const SweepVTable* make_sweep_vtable()
         &launch_bandlimit_cols_n<N>, &launch_multiply_rows_n<N>, &launch_propagate_cols_n<N>,
         &launch_rows_fft_n<N>, &launch_rows_fft_sum_n<N>, &launch_cols_fft_n<N>,
         &launch_probe_cols_n<N>, &detector_tiles_n<N>, &launch_detector_cols_n<N>,
-        &make_twiddles_n<N>,
+        &make_twiddles_n<N>, &launch_propagate_cols_from_n<N>, &sweeps_pipelined_n<N>,
     };
     return &vt;
 }
