@@ -328,6 +328,7 @@ void Engine::setup_tables()
     {
         const char* e = getenv("FDES_B200_NO_FIRST_SLICE_SHORTCUT");     // A/B switch
         plane_first_slice_ = p_.mode != 2 && !p_.doBeamTilt && sweeps_pipelined(N_) && !(e && e[0] == '1');
+        fuse_ctf_ = p_.mode == 0 && sweeps_pipelined(N_) && !(e && e[0] == '1');
     }
     g_.lo_end = ((kb + 1 + 31) / 32) * 32;
     g_.hi_start = ((N_ - kb) / 32) * 32;
@@ -512,6 +513,7 @@ void Engine::run_batches(int k, int jb, int je, bool reference_order)
             for (int b = 0; b < nb; b++)
                 CK(cudaMemcpyAsync(Psi_ + (size_t)b * NN, psi_in_, NN * sizeof(cpx), cudaMemcpyDeviceToDevice, st_));
         }
+        if (fuse_ctf_ && !ew_) ensure_lens(k);     // read by the last slice's S6
         slice_loop(nb);
         CK(cudaEventRecord(ev_used_[set], st_));
         accumulate_outputs(k, nb);
@@ -523,6 +525,20 @@ void Engine::run_slices_plain(int nb)
 {
     const size_t NN = (size_t)N_ * N_;
     const bool first_full = p_.doBeamTilt && p_.mode == 2;
+    const bool fuse = fuse_ctf_ && !ew_;
+    // S5 + S6 of one slice; Dp = transmission of configuration 0, d_stride elements between configurations.
+    //   first slice of a plane wave: psi = 1, so FFT_row(t psi) is N times what S4 left in D -- no S5, S6 reads D;
+    //   last slice with `fuse`: S6 also applies the CTF and writes the filtered waves to W_ (accumulate_outputs).
+    auto wave_step = [&](const cpx* Dp, size_t d_stride, int slice) {
+        const bool skip_s5 = plane_first_slice_ && slice == 0;
+        const bool with_ctf = fuse && slice == p_.m3 - 1;
+        if (!skip_s5) launch_multiply_rows(g_, Psi_, Dp, d_stride, nb, first_full && slice == 0, st_);
+        if (!skip_s5 && !with_ctf) { launch_propagate_cols(g_, Psi_, Pq_, nb, st_); return; }
+        const int img_stride = skip_s5 ? (int)(d_stride / NN) : 1;
+        if (!launch_propagate_cols_from(g_, with_ctf ? W_ : Psi_, skip_s5 ? Dp : Psi_, img_stride, img_stride * nb, Pq_, nb,
+                                        skip_s5, with_ctf ? lens_ : nullptr, st_))
+            throw std::runtime_error("propagate_cols_from missing although the column sweeps are pipelined");
+    };
     // The potential / transmission sweeps S1..S4 run once per PAIR of slices (the two densities
     // share one complex transform); S5/S6 then advance the wave through the two slices in turn.
     for (int s = 0; s < p_.m3; s += 2) {
@@ -534,10 +550,7 @@ void Engine::run_slices_plain(int nb)
             launch_potential_cols(g_, W_, A_, Gq_, rs_[act_].rowptr, s, s, nZ_, nb / 2, rp_stride_, st_, 2, 1);
             launch_transmit_rows(g_, W_, D_, 2, p_.imPot, nb / 2, st_);
             launch_bandlimit_cols(g_, D_, nb, 0, st_);
-            if (!(plane_first_slice_ && s == 0 && launch_propagate_cols_from(g_, Psi_, D_, 1, nb, Pq_, nb, st_))) {
-                launch_multiply_rows(g_, Psi_, D_, NN, nb, first_full && s == 0, st_);
-                launch_propagate_cols(g_, Psi_, Pq_, nb, st_);
-            }
+            wave_step(D_, NN, s);
             break;
         }
         const int s2 = npair > 1 ? s + 1 : -1;
@@ -545,12 +558,7 @@ void Engine::run_slices_plain(int nb)
         launch_potential_cols(g_, W_, A_, Gq_, rs_[act_].rowptr, s, s2, nZ_, nb, rp_stride_, st_);
         launch_transmit_rows(g_, W_, D_, npair, p_.imPot, nb, st_);
         launch_bandlimit_cols(g_, D_, nb, npair, st_);
-        for (int p = 0; p < npair; p++) {
-            // first slice of a plane wave: psi = 1, FFT_row(t psi) is what S4 left in D -- no S5
-            if (plane_first_slice_ && s + p == 0 && launch_propagate_cols_from(g_, Psi_, D_, 2, 2 * nb, Pq_, nb, st_)) continue;
-            launch_multiply_rows(g_, Psi_, D_ + (size_t)p * NN, 2 * NN, nb, first_full && s + p == 0, st_);
-            launch_propagate_cols(g_, Psi_, Pq_, nb, st_);
-        }
+        for (int p = 0; p < npair; p++) wave_step(D_ + (size_t)p * NN, 2 * NN, s + p);
     }
     if (first_full) launch_zero_outband(Psi_, N_, g_.lo_end, g_.hi_start, nb, st_);
 }
@@ -564,7 +572,8 @@ void Engine::slice_loop(int nb)
     if (!opt_.use_graph || (size_t)nb * N_ * N_ > ((size_t)1 << 21)) { run_slices_plain(nb); return; }
     cudaGraphExec_t& graph_ = this->graph_[act_];     // the captured launches carry the record pointers of a set
     int& graph_nb_ = this->graph_nb_[act_];
-    if (!graph_ || graph_nb_ != nb) {
+    const int key = 2 * nb + (fuse_ctf_ && !ew_ ? 1 : 0);     // what the captured launches depend on
+    if (!graph_ || graph_nb_ != key) {
         if (graph_) { cudaGraphExecDestroy(graph_); graph_ = nullptr; }
         // first use of each kernel must happen outside capture (function attributes are set there)
         if (!warmed_) { run_slices_plain(nb); warmed_ = true; graph_nb_ = -1; return; }
@@ -574,21 +583,26 @@ void Engine::slice_loop(int nb)
         CK(cudaStreamEndCapture(st_, &g));
         CK(cudaGraphInstantiate(&graph_, g, 0));
         CK(cudaGraphDestroy(g));
-        graph_nb_ = nb;
+        graph_nb_ = key;
     }
     CK(cudaGraphLaunch(graph_, st_));
+}
+
+// CTF table of measurement k (applyLensFunction, src/multisliceSimulation.cu:614-622), stored [kx][ky]
+void Engine::ensure_lens(int k)
+{
+    if (p_.mode == 0 && lens_k_ != k) {
+        launch_lens_table(lens_, N_, lens_params(p_, k, 0), 1.f, st_, /*transposed=*/true);
+        lens_k_ = k;
+        tm_.kernel_launches += 1;
+    }
 }
 
 void Engine::accumulate_outputs(int k, int nb)
 {
     const size_t NN = (size_t)N_ * N_;
     const float alpha = 1.f / ((float)count_);
-    if (p_.mode == 0 && lens_k_ != k) {
-        // CTF with the 1/N of applyLensFunction folded in (src/multisliceSimulation.cu:614-622)
-        launch_lens_table(lens_, N_, lens_params(p_, k, 0), 1.f, st_, /*transposed=*/true);
-        lens_k_ = k;
-        tm_.kernel_launches += 1;
-    }
+    ensure_lens(k);
     // exit wave and imaging-mode intensity: the batch is summed inside one launch, in the fixed
     // order b = 0 .. nb-1 (deterministic phonon average)
     if (ew_) {
@@ -599,8 +613,9 @@ void Engine::accumulate_outputs(int k, int nb)
     if (p_.mode == 0) {
         // W_ is free after the slice loop: CTF-filtered waves of the whole batch
         // (band columns only where the sweep is pipelined: the wave has no others, and the row sweep below
-        // reads none)
-        launch_cols_fft(g_, Psi_, W_, -1, COL_MUL_CPX_INV, lens_, 1.f / ((float)N_), nb, st_);
+        // reads none).  With fuse_ctf_ and no exit wave to keep, the last slice's S6 has written them already:
+        // IFFT_col(FFT_col(Psi) P lens) = (1/N) IFFT_col(FFT_col(Psi') lens) for Psi' = IFFT_col(FFT_col(Psi) P).
+        if (!(fuse_ctf_ && !ew_)) launch_cols_fft(g_, Psi_, W_, -1, COL_MUL_CPX_INV, lens_, 1.f / ((float)N_), nb, st_);
         RowOpts ro; ro.scale = alpha; ro.band_only_in = true;
         launch_rows_fft_sum(g_, W_, I_, +1, ROW_INTENS_ACCUM, ro, nb, st_);
         tm_.kernel_launches += 2;

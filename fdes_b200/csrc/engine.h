@@ -137,6 +137,8 @@ private:
     unsigned int* hist_ = nullptr;
     double *norm_partial_ = nullptr, *norm_result_ = nullptr;
     size_t rec_stride_ = 0, rp_stride_ = 0;
+    bool fuse_ctf_ = false;           // imaging mode on pipelined column kernels: the CTF rides on the last slice's S6 (when no exit wave is kept)
+    void ensure_lens(int k);
     bool plane_first_slice_ = false;  // plane-wave illumination on pipelined column kernels: slice 0 runs S6 from D, no S5
     int mask_E_ = 0;                  // points per thread of a line (row-mask layout); 0: no masks
     int nkeys_ = 0, key_bits_ = 0, nrec_ = 0;

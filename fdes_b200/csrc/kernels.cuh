@@ -57,12 +57,16 @@ void launch_multiply_rows(const SweepGeom& g, cpx* Psi, const cpx* E, size_t e_b
                           int batch, bool psi_full, cudaStream_t st);
 // S6: column FFT -> x Fresnel propagator (quarter table, mask and 1/N folded in) -> inverse
 void launch_propagate_cols(const SweepGeom& g, cpx* Psi, const cpx* Pq, int batch, cudaStream_t st);
-// S6 out of place: Psi[b] = IFFT_col(FFT_col(N * src[b * src_img_stride]) * P), band columns, src an image stack with
-// images of N*N elements.  The first slice of a plane wave needs no S5: psi = 1, so FFT_row(t * psi) is the
-// band-limited FFT_row(t) that S4 left in D.  Returns false when the size has no such kernel (generic sweeps,
-// register-staged column kernels): the caller then runs S5 + S6.
-bool launch_propagate_cols_from(const SweepGeom& g, cpx* Psi, const cpx* src, int src_img_stride, int src_images,
-                                const cpx* Pq, int batch, cudaStream_t st);
+// S6 out of place: out[b] = IFFT_col(FFT_col(c * src[b * src_img_stride]) * P [* lens]), band columns; src is an
+// image stack of src_images images of N*N elements.
+//   times_n (c = N): the first slice of a plane wave needs no S5 -- psi = 1, so FFT_row(t * psi) is N times the
+//     band-limited FFT_row(t) that S4 left in D;
+//   lens (table [kx][ky]): the CTF of the image formation (applyLensFunction, src/multisliceSimulation.cu:614-622)
+//     applied in the last slice's column transform pair, out = the CTF-filtered wave.
+// Returns false when the size has no such kernel (generic sweeps, register-staged column kernels; see
+// sweeps_pipelined): the caller then runs the separate sweeps.
+bool launch_propagate_cols_from(const SweepGeom& g, cpx* out, const cpx* src, int src_img_stride, int src_images,
+                                const cpx* Pq, int batch, bool times_n, const cpx* lens, cudaStream_t st);
 
 // ---- STEM probe scan ----------------------------------------------------------------------
 constexpr int MAX_DETECTORS = 8;

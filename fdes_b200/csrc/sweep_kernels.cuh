@@ -1054,8 +1054,8 @@ k_propagate_cols(cpx* __restrict__ Psi, const cpx* __restrict__ Pq, int lo_end, 
 template <int N>
 __global__ void __launch_bounds__(PipeCfg<N>::THREADS, 1)
 k_propagate_cols_tma(const __grid_constant__ CUtensorMap map, const __grid_constant__ CUtensorMap map_out,
-                     int src_img_stride, float in_scale, const cpx* __restrict__ Pq, int lo_end, int hi_start,
-                     int tiles_x, int ntiles, const cpx* __restrict__ tw)
+                     int src_img_stride, float in_scale, const cpx* __restrict__ Pq, const cpx* __restrict__ lens,
+                     int lo_end, int hi_start, int tiles_x, int ntiles, const cpx* __restrict__ tw)
 {
     pdl_prologue();
     using C = PipeCfg<N>;
@@ -1084,6 +1084,16 @@ k_propagate_cols_tma(const __grid_constant__ CUtensorMap map, const __grid_const
             for (int m = 0; m < E; m++) x[m] = make_float2(x[m].x * in_scale, x[m].y * in_scale);
         }
         quarter_table_apply<N, E, 0>(x, P + ky0, P - ky0, [](cpx v, cpx p) { return cmul(v, p); });
+        if (lens) {
+            // last slice of an imaging-mode batch: the CTF (table stored [kx][ky], as in k_ctf_cols_tma) rides on
+            // the same column transform pair instead of a sweep of its own
+            const cpx* tab = lens + (size_t)kx * N + ky0;
+#pragma unroll
+            for (int m = 0; m < E; m++) {
+                const cpx w = ld_nc(tab + m * C::T);
+                x[m] = make_float2(w.x * x[m].x - w.y * x[m].y, w.x * x[m].y + w.y * x[m].x);
+            }
+        }
         pipe.ifft_release(x, true, &map_out, kx0, ord.img(t));
     }
     pipe.finish();
@@ -1099,8 +1109,8 @@ void launch_propagate_cols_n(const SweepGeom& g, cpx* Psi, const cpx* Pq, int ba
             const int tiles_x = band_cols(g) / P::CW, ntiles = tiles_x * batch;
             CUtensorMap map;
             tile_map(&map, Psi, NN, batch, P::CW, P::BR);
-            launch_pdl(k_propagate_cols_tma<NN>, dim3(pipe_grid(ntiles)), dim3(P::THREADS), P::SMEM, st, map, map, 1, 1.f, Pq, g.lo_end,
-                                                                                  g.hi_start, tiles_x, ntiles, g.tw);
+            launch_pdl(k_propagate_cols_tma<NN>, dim3(pipe_grid(ntiles)), dim3(P::THREADS), P::SMEM, st, map, map, 1, 1.f, Pq,
+                                                                                  (const cpx*)nullptr, g.lo_end, g.hi_start, tiles_x, ntiles, g.tw);
             FDES_LAUNCH_CHECK();
             return;
         }
@@ -1115,7 +1125,7 @@ void launch_propagate_cols_n(const SweepGeom& g, cpx* Psi, const cpx* Pq, int ba
 // S6 reading the band columns of another image stack (launch_propagate_cols_from, kernels.cuh): pipelined kernels only
 template <int NN>
 bool launch_propagate_cols_from_n(const SweepGeom& g, cpx* Psi, const cpx* src, int src_img_stride, int src_images, const cpx* Pq,
-                                  int batch, cudaStream_t st)
+                                  int batch, bool times_n, const cpx* lens, cudaStream_t st)
 {
     if constexpr (pipe_supported<NN>()) {
         if (pipe_enabled()) {
@@ -1125,9 +1135,9 @@ bool launch_propagate_cols_from_n(const SweepGeom& g, cpx* Psi, const cpx* src, 
             CUtensorMap map_in, map_out;
             tile_map(&map_in, src, NN, src_images, P::CW, P::BR);
             tile_map(&map_out, Psi, NN, batch, P::CW, P::BR);
-            // S5 with psi = 1 returns FFT_row(IFFT_row(D)) = N * D (unnormalised transforms): the same factor here
+            // times_n: S5 with psi = 1 returns FFT_row(IFFT_row(D)) = N * D (unnormalised transforms): the same factor here
             launch_pdl(k_propagate_cols_tma<NN>, dim3(pipe_grid(ntiles)), dim3(P::THREADS), P::SMEM, st, map_in, map_out, src_img_stride,
-                       (float)NN, Pq, g.lo_end, g.hi_start, tiles_x, ntiles, g.tw);
+                       times_n ? (float)NN : 1.f, Pq, lens, g.lo_end, g.hi_start, tiles_x, ntiles, g.tw);
             FDES_LAUNCH_CHECK();
             return true;
         }

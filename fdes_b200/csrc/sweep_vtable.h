@@ -33,7 +33,7 @@ struct SweepVTable {
     void (*detector_cols)(const SweepGeom&, const cpx*, float*, float*, const DetectorRings&, float, float, float, int, cudaStream_t);
     std::vector<cpx> (*make_twiddles)(int N);
     // optional (may be null): S6 reading another image stack, see launch_propagate_cols_from
-    bool (*propagate_cols_from)(const SweepGeom&, cpx*, const cpx*, int, int, const cpx*, int, cudaStream_t);
+    bool (*propagate_cols_from)(const SweepGeom&, cpx*, const cpx*, int, int, const cpx*, int, bool, const cpx*, cudaStream_t);
     bool (*pipelined)();      // optional: the column sweeps of this size run on the TMA pipeline
 };
 

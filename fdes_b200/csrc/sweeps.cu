@@ -65,11 +65,11 @@ void launch_propagate_cols(const SweepGeom& g, cpx* Psi, const cpx* Pq, int batc
 {
     vt(g.N).propagate_cols(g, Psi, Pq, batch, st);
 }
-bool launch_propagate_cols_from(const SweepGeom& g, cpx* Psi, const cpx* src, int src_img_stride, int src_images, const cpx* Pq,
-                                int batch, cudaStream_t st)
+bool launch_propagate_cols_from(const SweepGeom& g, cpx* out, const cpx* src, int src_img_stride, int src_images, const cpx* Pq,
+                                int batch, bool times_n, const cpx* lens, cudaStream_t st)
 {
     const SweepVTable& t = vt(g.N);
-    return t.propagate_cols_from && t.propagate_cols_from(g, Psi, src, src_img_stride, src_images, Pq, batch, st);
+    return t.propagate_cols_from && t.propagate_cols_from(g, out, src, src_img_stride, src_images, Pq, batch, times_n, lens, st);
 }
 void launch_rows_fft(const SweepGeom& g, const void* in, void* out, int dir, RowEpilogue epi, const RowOpts& o, int batch,
                      cudaStream_t st)

@@ -119,7 +119,7 @@ void run(int batch, int reps)
     const int grid1 = ntiles < nsm ? ntiles : nsm;
     k_propagate_cols<N><<<grid0, C::THREADS, C::SMEM>>>(d0, P, g.lo_end, g.hi_start, tw);
     CK(cudaGetLastError());
-    k_propagate_cols_tma<N><<<grid1, Pc::THREADS, Pc::SMEM>>>(*map, *map, 1, 1.f, P, g.lo_end, g.hi_start, tiles_x, ntiles, tw);
+    k_propagate_cols_tma<N><<<grid1, Pc::THREADS, Pc::SMEM>>>(*map, *map, 1, 1.f, P, (const cpx*)nullptr, g.lo_end, g.hi_start, tiles_x, ntiles, tw);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     std::vector<cpx> a(total), b(total);
@@ -139,7 +139,7 @@ void run(int batch, int reps)
         for (int r = 0; r < reps; r++) k_propagate_cols<N><<<grid0, C::THREADS, C::SMEM>>>(d0, P, g.lo_end, g.hi_start, tw);
         cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms0, e0, e1);
         cudaEventRecord(e0);
-        for (int r = 0; r < reps; r++) k_propagate_cols_tma<N><<<grid1, Pc::THREADS, Pc::SMEM>>>(*map, *map, 1, 1.f, P, g.lo_end, g.hi_start, tiles_x, ntiles, tw);
+        for (int r = 0; r < reps; r++) k_propagate_cols_tma<N><<<grid1, Pc::THREADS, Pc::SMEM>>>(*map, *map, 1, 1.f, P, (const cpx*)nullptr, g.lo_end, g.hi_start, tiles_x, ntiles, tw);
         cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms1, e0, e1);
     }
     CK(cudaDeviceSynchronize());
