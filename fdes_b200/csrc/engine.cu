@@ -566,7 +566,7 @@ void Engine::run_slices_plain(int nb)
 void Engine::slice_loop(int nb)
 {
     tm_.slices_executed += (long long)p_.m3 * nb;
-    tm_.kernel_launches += 4LL * ((p_.m3 + 1) / 2) + 2LL * p_.m3;
+    tm_.kernel_launches += 4LL * ((p_.m3 + 1) / 2) + 2LL * p_.m3 - (plane_first_slice_ ? 1 : 0);   // no S5 in the first slice of a plane wave
     // a CUDA graph pays off when the sweeps are launch-bound (small grids, small batches); its
     // capture + instantiation costs about a millisecond, more than it saves on large launches
     if (!opt_.use_graph || (size_t)nb * N_ * N_ > ((size_t)1 << 21)) { run_slices_plain(nb); return; }
@@ -618,7 +618,7 @@ void Engine::accumulate_outputs(int k, int nb)
         if (!(fuse_ctf_ && !ew_)) launch_cols_fft(g_, Psi_, W_, -1, COL_MUL_CPX_INV, lens_, 1.f / ((float)N_), nb, st_);
         RowOpts ro; ro.scale = alpha; ro.band_only_in = true;
         launch_rows_fft_sum(g_, W_, I_, +1, ROW_INTENS_ACCUM, ro, nb, st_);
-        tm_.kernel_launches += 2;
+        tm_.kernel_launches += (fuse_ctf_ && !ew_) ? 1 : 2;
         return;
     }
     for (int b = 0; b < nb; b++) {   // fixed order: deterministic phonon average
