@@ -181,6 +181,20 @@ struct KeepMask {
     __device__ __forceinline__ bool operator()(int m) const { return (w0 >> m) & 1u; }
     __device__ __forceinline__ bool split(int r) const { return (((r & 1) ? w1 : w0) >> (r >> 1)) & 1u; }
 };
+// The same rows straight from the row pointers (position pos of the line, rows pos + m*T), evaluated inside the tile
+// access: 4 loads per row.  Used at 4096^2, where S2 with the mask words runs 7-25 % slower than with these
+// (measured on the three-species slab, same box: 1340 us against 1440-1670 us per slice of 10 images; the L2
+// hit rate of the scattering-factor tables drops from 54 % to 43 %) -- not understood, kept as measured.
+struct KeepRowPtr {
+    const int *rp, *rp2;
+    int pos, T;
+    __device__ __forceinline__ bool operator()(int m) const
+    {
+        const int y = pos + m * T;
+        return (rp[y + 1] > rp[y]) | (rp2[y + 1] > rp2[y]);
+    }
+    __device__ __forceinline__ bool split(int) const { return true; }      // split lines always use the masks
+};
 // mask words of configuration b, key group kg = slice * nZ + z (T words each)
 __device__ __forceinline__ const uint32_t* row_mask_words(const int* rowptr, size_t rp_stride, int mask_off, int b, int kg, int T)
 {
@@ -419,7 +433,7 @@ k_potential_cols_tma(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         if (lt < ntiles) pipe.issue_load(&mapA, ord.xt(lt) * C::CW, (ord.img(lt)) * nZ + lz);
     }
     KeepMask keep_next{0u, 0u};
-    if (lt < ntiles) keep_next = load_keep(lt, lz);
+    if (N < 4096 && lt < ntiles) keep_next = load_keep(lt, lz);
     for (; t < ntiles; t += gridDim.x) {
         const int kx0 = ord.xt(t) * C::CW, kx = kx0 + pipe.line, b = ord.img(t);
         const int ax = min(kx, N - kx);
@@ -430,11 +444,18 @@ k_potential_cols_tma(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         while (lt == t) {                      // the landed (or landing) tile belongs to this output tile
             const int z = lz;
             const KeepMask keep = keep_next;
+            const int* rp = rows_of(b * cfg_stride, z, slice);
+            const int* rp2 = slice2 >= 0 ? rows_of(b * cfg_stride + cfg_off2, z, slice2) : rp;
             lz++;
             seek(lt, lz);
-            if (lt < ntiles) keep_next = load_keep(lt, lz);
             cpx x[E];
-            pipe.acquire_fft(x, lt < ntiles, &mapA, ord.xt(lt) * C::CW, (ord.img(lt)) * nZ + lz, keep);
+            if constexpr (N >= 4096) {
+                pipe.acquire_fft(x, lt < ntiles, &mapA, ord.xt(lt) * C::CW, (ord.img(lt)) * nZ + lz,
+                                 KeepRowPtr{rp, rp2, pipe.theta, C::T});
+            } else {
+                if (lt < ntiles) keep_next = load_keep(lt, lz);
+                pipe.acquire_fft(x, lt < ntiles, &mapA, ord.xt(lt) * C::CW, (ord.img(lt)) * nZ + lz, keep);
+            }
             any = true;
             const float* G = Gq + (size_t)z * Q * Q + (size_t)ax * Q;
             quarter_table_apply<N, E, 0>(x, G + ky0, G - ky0,
