@@ -92,8 +92,7 @@ __device__ __forceinline__ uint64_t l2_keep_policy()
     asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
-// KEEP: only for tables that are small next to the 126 MB of L2 (the launchers pass N <= 2048: 8 MB; the
-// 34 MB propagator table of a 4096^2 grid, kept resident, costs the other sweeps more than it gains S6)
+// KEEP: the callers' switch (quarter_table_apply: FDES_TABLE_KEEP_MAXN)
 template <int OFF, bool KEEP = true>
 __device__ __forceinline__ cpx ld_tab_at(const cpx* p)
 {

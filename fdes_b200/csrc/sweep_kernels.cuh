@@ -162,13 +162,18 @@ using ColCtx = ColTile<N, LineCfg<N>::E, ColCfg<N>::CW, ColCfg<N>::STAGED>;
 // |ky| fastest: the T threads of a column read consecutive entries): the first half of the points
 // sits at lo + m*T, the second at hi + (N - m*T) with lo = tab + ax*Q + theta and
 // hi = tab + ax*Q - theta -- compile-time offsets.
+// largest grid size whose complex quarter table (the propagator) is read with the evict_last L2 policy
+// (fft_core.cuh: ld_tab_at).  4096^2, 34 MB table: S6 929 -> 861 us per slice of 10 images, S2 unchanged.
+#ifndef FDES_TABLE_KEEP_MAXN
+#define FDES_TABLE_KEEP_MAXN 4096
+#endif
 template <int N, int E, int M, class TabT, class F>
 __device__ __forceinline__ void quarter_table_apply(cpx (&x)[E], const TabT* lo, const TabT* hi, F f)
 {
     constexpr int T = N / E;
     if constexpr (M < E) {
-        if constexpr (M < E / 2) x[M] = f(x[M], ld_tab_at<M * T, (N <= 2048)>(lo));
-        else x[M] = f(x[M], ld_tab_at<N - M * T, (N <= 2048)>(hi));
+        if constexpr (M < E / 2) x[M] = f(x[M], ld_tab_at<M * T, (N <= FDES_TABLE_KEEP_MAXN)>(lo));
+        else x[M] = f(x[M], ld_tab_at<N - M * T, (N <= FDES_TABLE_KEEP_MAXN)>(hi));
         quarter_table_apply<N, E, M + 1>(x, lo, hi, f);
     }
 }
