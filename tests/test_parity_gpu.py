@@ -307,6 +307,33 @@ def _oracle_vs_library(cnf, fb, orc, atoms6=None):
     return img, ew
 
 
+@pytest.mark.parametrize("slices,mode", [(1, 0), (2, 0), (5, 0), (4, 1)])
+def test_first_and_last_slice_shortcuts_match_the_plain_sweeps(fb, tmp_path, monkeypatch, slices, mode):
+    """Plane wave: the first slice runs without S5 (S6 reads N * FFT_row(t) from the transmission stack); imaging
+    mode without an exit wave to keep: the CTF rides on the last slice's S6.  Same images as the six plain sweeps
+    per slice + the separate CTF sweep (FDES_B200_NO_FIRST_SLICE_SHORTCUT=1), 1024^2 = pipelined column sweeps;
+    one slice = first and last at once."""
+    from fdes_b200 import specimens
+    d = 0.2e-10
+    atoms = specimens.random_slab(300, 1024 * d, slices * 2e-10, seed=7 + slices, species=(79, 14))
+    cnf = specimens.write_cnf(tmp_path / "fl.cnf", image_size=512, border_size=256, slices=slices, pixel_size=d,
+                              slice_thickness=2e-10, atoms=atoms, voltage=120e3, absorptive=0.03, frozen_phonons=4, mode=mode,
+                              objective_aperture=0.015, aberrations={"C1": (-2e-8, 0.0), "C3": (3e-4, 0.0)})
+    out = {}
+    for off in ("0", "1"):
+        monkeypatch.setenv("FDES_B200_NO_FIRST_SLICE_SHORTCUT", off)
+        with fb.Simulation(cnf, want_exitwave=False) as sim:       # no exit wave kept: the fused CTF path
+            out[off, False] = sim.simulate()[0]
+        with fb.Simulation(cnf, want_exitwave=True) as sim:        # exit wave kept: separate CTF sweep
+            out[off, True] = sim.simulate()
+    ref_img, ref_ew = out["1", True]
+    assert np.isfinite(ref_img).all() and ref_img.mean() > 0.1
+    assert rel_l2(out["0", True][1], ref_ew) < 2e-6
+    for key in (("0", False), ("1", False)):
+        assert rel_l2(out[key], ref_img) < 2e-6
+    assert rel_l2(out["0", True][0], ref_img) < 2e-6
+
+
 @pytest.mark.parametrize("n,dn,mode", [(41, 20, 0), (75, 0, 2), (101, 13, 1)])
 def test_odd_grid_sizes_against_oracle(fb, orc, tmp_path, n, dn, mode):
     """Odd sample sizes (81, 75, 127 = prime): the run-time-N sweeps against the numpy oracle (the live
