@@ -80,6 +80,22 @@ def test_specimen_generators():
     assert specimens.srtio3_slab(2, 2, 3).shape == (60, 6)
 
 
+def test_bench_workloads_are_the_baseline_shapes(fb, tmp_path):
+    """The grids / slice counts of the bench workloads (bench.py WORKLOADS) as the library's reader sees them."""
+    import importlib.util
+    from fdes_b200 import specimens
+    spec = importlib.util.spec_from_file_location("bench", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    want = {"srtio3_800": (800, 400, 3), "si001_1024": (1024, 11, 1), "au_2048": (2048, 12, 1), "slab_4096": (4096, 20, 3)}
+    for name, (m, slices, nz) in want.items():
+        assert name in bench.WORKLOADS and name in bench.DEFAULT_CONFIGS_PER_STEP and name in bench.REF_SAMPLE_CONFIGS
+        cnf = tmp_path / f"{name}.cnf"
+        getattr(specimens, bench.WORKLOADS[name][0])(cnf, frozen_phonons=2)
+        r = fb.parse_cnf(cnf)
+        assert (r["m1"], r["m2"], r["m3"], r["nZ"], r["frPh"]) == (m, m, slices, nz, 2)
+
+
 def test_no_gpu_fails_loudly(fb):
     """There is no CPU fallback: without a CUDA device every computing entry point refuses."""
     import torch
