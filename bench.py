@@ -269,7 +269,8 @@ def run_ours(a):
                      "whole_step": {"achieved": round(step_gbs, 1), "frac": round(step_gbs / peak, 4),
                                     "frac_of_8TBps": round(step_gbs / 8000.0, 4),
                                     "note": "value x algorithmic bytes per pixel and slice, per GPU: atom preparation, wave "
-                                            "copies and image formation included"}},
+                                            "copies and image formation included; the first slice of a plane wave runs "
+                                            "without S5 (psi = 1) and moves 24 B/px less than this model counts"}},
         "sweeps": {n: {"ms": round(float(m), 5), "alg_GBps": round(ab[n] * px * batch / (float(m) * 1e-3) / 1e9, 1),
                        "frac": round(ab[n] * px * batch / (float(m) * 1e-3) / 1e9 / peak, 4)}
                    for n, m in zip(names, sweep_ms)},
