@@ -200,11 +200,14 @@ void Engine::init(const Atoms& atoms)
     j0_ = (int)(((long long)count_ * rank) / world);
     j1_ = (int)(((long long)count_ * (rank + 1)) / world);
     const int mine = std::max(1, j1_ - j0_);
-    // configurations advanced together.  10 fills the 148 SMs of a B200 evenly at every supported
-    // grid size -- the column sweeps have (2N/3 rounded to 32)/CW tiles per configuration, e.g. 88 at
-    // 1024^2: 880 tiles = 5.95 waves of 148 persistent CTAs against 4.76 for a batch of 8 -- and keeps
-    // the batch buffers ((4 + nZ) complex grids per configuration) far below the 180 GB of HBM
-    B_ = opt_.batch > 0 ? opt_.batch : 10;
+    // configurations advanced together: about 80 Mpixel per launch, at least 10 and at most 40 configurations
+    // (40 at 1024^2 and below, 20 at 2048^2, 10 at 4096^2).  Every sweep is one launch over the batch; the
+    // longer the launch, the less its ramp-up and tail weigh (measured, same box: 1024^2 55.5 / 59.0 / 60.6 /
+    // 61.7 Gpx*slices/s at 10 / 20 / 30 / 40; 2048^2 53.3 / 54.3 / 54.7 / 54.7 at 10 / 16 / 20 / 26; 4096^2
+    // 29.9 / 28.4 at 10 / 16), and the batch buffers ((4 + nZ) complex grids per configuration) stay far below
+    // the 180 GB of HBM
+    const long long fit = (80LL << 20) / ((long long)N_ * N_);
+    B_ = opt_.batch > 0 ? opt_.batch : (int)std::min(40LL, std::max(10LL, fit));
     while (B_ > 1 && (size_t)B_ * (4 + nZ_) * (size_t)N_ * N_ * sizeof(cpx) > ((size_t)48 << 30)) B_ /= 2;
     if (opt_.batch <= 0) B_ = std::min(B_, mine);   // an explicit batch is honoured (STEM probes batch independently of the phonon count)
     const long long nk = (long long)p_.m3 * nZ_ * N_;
