@@ -24,20 +24,21 @@ __global__ void k_scattering_table(float* __restrict__ Gq, int N, KirklandRow kr
     const int m1 = N, m2 = N;
     const float d1 = 1e10f * d1m;
     const float d2 = 1e10f * d2m;
-    float qsq = ((float)i1) / (d1 * ((float)m1));
-    float Vz = ((float)i2) / (d2 * ((float)m2));
-    qsq = qsq * qsq + Vz * Vz;
+    // |q|^2 in 1/A^2, Kirkland's parametrisation f(q) = sum_k a_k / (q^2 + b_k) + c_k exp(-d_k q^2)
+    const float q1 = ((float)i1) / (d1 * ((float)m1));
+    const float q2 = ((float)i2) / (d2 * ((float)m2));
+    const float qsq = q1 * q1 + q2 * q2;
     const float* a = kr.v;  // a_k = v[2k], b_k = v[2k+1], c_k = v[6+2k], d_k = v[7+2k]
-    Vz = a[0] / (qsq + a[1]) + a[6] * expf(-a[7] * qsq);
-    Vz += a[2] / (qsq + a[3]) + a[8] * expf(-a[9] * qsq);
-    Vz += a[4] / (qsq + a[5]) + a[10] * expf(-a[11] * qsq);
-    const float V = Vz * (4.78776452e-9f * sigma) / (d1 * d2 * ((float)(m1 * m2)));
-    float y = pi;
-    float x = ((float)i1) / ((float)m1) * y;
-    x = (x + FLT_EPSILON) / (sinf(x) + FLT_EPSILON);
-    y *= ((float)i2) / ((float)m2);
-    x *= (y + FLT_EPSILON) / (sinf(y) + FLT_EPSILON);
-    Gq[i] = V * x;
+    float f = a[0] / (qsq + a[1]) + a[6] * expf(-a[7] * qsq);
+    f += a[2] / (qsq + a[3]) + a[8] * expf(-a[9] * qsq);
+    f += a[4] / (qsq + a[5]) + a[10] * expf(-a[11] * qsq);
+    const float V = f * (4.78776452e-9f * sigma) / (d1 * d2 * ((float)(m1 * m2)));
+    // 1 / (sinc sinc) of the bilinear deposit, both arguments guarded by FLT_EPSILON as in divideBySinc
+    const float u1 = ((float)i1) / ((float)m1) * pi;
+    const float inv_sinc1 = (u1 + FLT_EPSILON) / (sinf(u1) + FLT_EPSILON);
+    const float u2 = pi * (((float)i2) / ((float)m2));
+    const float inv_sinc = inv_sinc1 * ((u2 + FLT_EPSILON) / (sinf(u2) + FLT_EPSILON));
+    Gq[i] = V * inv_sinc;
 }
 
 void launch_scattering_table(float* Gq, int N, KirklandRow kr, float d1, float d2, float sigma,
@@ -59,12 +60,12 @@ __global__ void k_propagator_table(cpx* __restrict__ Pq, int N, float d1, float 
     if (i >= Q * Q) return;
     const int i2 = i % Q, i1 = i / Q;    // stored [|kx|][|ky|], ky fastest (see k_scattering_table)
     const int dim1 = N, dim2 = N;
-    float d3 = d3in;
+    const float d3 = d3in;
     const float t1 = ((float)(i1) / ((float)dim1)) * (d3 / d1);
     const float t2 = ((float)(i2) / ((float)dim2)) * (d3 / d2);
-    d3 = lambda / d3;
-    d3 = -pi * (t1 * t1 + t2 * t2) * d3;
-    cpx p = make_float2(cosf(d3), sinf(d3));
+    const float lambda_over_d3 = lambda / d3;
+    const float phase = -pi * (t1 * t1 + t2 * t2) * lambda_over_d3;       // -pi lambda dz |k|^2
+    cpx p = make_float2(cosf(phase), sinf(phase));
     const float mindim = (float)N;
     if (((float)(i1 * i1 + i2 * i2) * 9.f / (mindim * mindim)) > 1.f) p = make_float2(0.f, 0.f);
     const float alpha = 1.f / ((float)(N * N));
@@ -93,10 +94,11 @@ __global__ void k_lens_table(cpx* __restrict__ tab, int N, LensParams lp, float 
     if (i2 > N / 2) i2 -= N;
     i2 = -i2;  // row index points up
     const float dim1 = (float)N, dim2 = (float)N;
-    float nu = (((float)i1) / dim1) * (lp.lambda / lp.d1);
-    float nu2 = (((float)i2) / dim2) * (lp.lambda / lp.d2);
-    float phi = atan2f(nu2, nu);
-    nu = sqrtf(nu * nu + nu2 * nu2);
+    // scattering angle (nu1, nu2) = lambda k, its azimuth phi and magnitude nu
+    const float nu1 = (((float)i1) / dim1) * (lp.lambda / lp.d1);
+    const float nu2 = (((float)i2) / dim2) * (lp.lambda / lp.d2);
+    const float phi = atan2f(nu2, nu1);
+    const float nu = sqrtf(nu1 * nu1 + nu2 * nu2);
     cpx out = make_float2(0.f, 0.f);
     if (nu < lp.ObjAp) {
         // index: 0 C1, 1 A1, 2 A2, 3 B2, 4 C3, 5 A3, 6 S3, 7 A4, 8 B4, 9 D4, 10 C5, 11 A5, 12 R5, 13 S5
